@@ -43,7 +43,7 @@ class IpmOptions(C.Structure):
     _fields_ = [("tol", C.c_double), ("constr_viol_tol", C.c_double),
                 ("compl_inf_tol", C.c_double), ("dual_inf_tol", C.c_double),
                 ("max_iter", C.c_int), ("mu_init", C.c_double), ("mu_strategy", C.c_int),
-                ("sigma_w", C.c_double), ("verbose", C.c_int)]
+                ("sigma_w", C.c_double), ("verbose", C.c_int), ("delta_c", C.c_double)]
 
 
 class IpmResult(C.Structure):
@@ -54,7 +54,7 @@ class IpmResult(C.Structure):
                 ("tr_inf_pr", C.c_double * 256), ("tr_inf_du", C.c_double * 256),
                 ("tr_mu", C.c_double * 256), ("tr_dnorm", C.c_double * 256),
                 ("tr_alpha_pr", C.c_double * 256), ("tr_alpha_du", C.c_double * 256),
-                ("tr_ls", C.c_int * 256)]
+                ("tr_ls", C.c_int * 256), ("chol_fix", C.c_int)]
 
 
 def build(force=False):

@@ -135,6 +135,7 @@ typedef struct {
 	int    mu_strategy;       /* 0 monotone, 1 adaptive (loqo-type) */
 	double sigma_w;           /* W = sigma_w * I */
 	int    verbose;
+	double delta_c;           /* equality-block regularisation (condensed as Jc'Jc/delta_c) */
 } orc_ipm_options;
 
 typedef struct {
@@ -147,6 +148,7 @@ typedef struct {
 	double tr_inf_pr[256], tr_inf_du[256], tr_mu[256], tr_dnorm[256],
 	       tr_alpha_pr[256], tr_alpha_du[256];
 	int tr_ls[256];
+	int chol_fix;             /* factorizations that hit a non-positive pivot */
 } orc_ipm_result;
 
 void orc_ipm_default_options(orc_ipm_options *o);
