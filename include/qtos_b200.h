@@ -1,0 +1,149 @@
+/*
+ * qtos_b200.h -- C ABI of the B200-native batched gait-planning NLP solver.
+ *
+ * Drop-in boundary for the QTOS local planner.  The reference crosses this boundary as a
+ * process call `docker exec <id> ./main <flags>` (ref: QTOS/utils.py:15-26,644-670;
+ * scripts/main.py:48-50,90-92; QTOS/generateHeightField.py:385-386) into
+ * solver/towr/src/main.cpp:133-471.  The entry points below are what an in-process FFI for
+ * that path binds; INTEGRATION.md shows the ctypes stub on the reference side.
+ * Plain pointers and sizes only; every array is caller-owned.  All functions return 0 on
+ * success or a negative QTOS_E* code; qtos_last_error() gives the message.  There is no CPU
+ * fallback: without a CUDA device qtos_create fails with QTOS_ENODEV.
+ */
+#ifndef QTOS_B200_H_
+#define QTOS_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QTOS_NEE 4                /* LF, RF, LH, RH (ref: towr/models/endeffector_mappings.h:44) */
+#define QTOS_CSV_COLS 37          /* ref: solver/towr/src/main.cpp:92-131 */
+
+enum { QTOS_OK = 0, QTOS_EINVAL = -1, QTOS_ENODEV = -2, QTOS_ECUDA = -3, QTOS_ENOMEM = -4, QTOS_ESHAPE = -5 };
+
+/* gait combos, ref: solver/towr/src/quadruped_gait_generator.cc:76-88 */
+enum { QTOS_C0 = 0, QTOS_C1, QTOS_C2, QTOS_C3, QTOS_C4, QTOS_CUSTOM };
+
+/* per-problem solver status; exit code of ./main (ref: main.cpp:463,471) is status & 0xff */
+enum {
+	QTOS_SOLVE_SUCCEEDED = 0,         /* Ipopt Solve_Succeeded */
+	QTOS_MAX_ITER = -1,               /* Ipopt Maximum_Iterations_Exceeded */
+	QTOS_STEP_FAILED = -2,            /* line search could not make progress */
+	QTOS_RUNNING = 99
+};
+
+/* Everything main.cpp + Parameters + the Solo12 model hard-code, made explicit
+ * (ref: solver/towr/src/parameters.cc:40-73; models/examples/solo12_model.h:17-37;
+ *  height_map.h:137; swing_constraint.h:68; main.cpp:299-306,424-433). */
+typedef struct {
+	double mass;
+	double I_b[9];                    /* row-major body inertia */
+	double nominal[QTOS_NEE][3];
+	double max_dev[3];
+	double mu;                        /* friction coefficient */
+	double force_limit;
+	double t_swing_avg;
+	double dt_base_poly;
+	int    force_polys_per_stance;
+	int    ee_polys_per_swing;
+	double dt_dynamic;
+	double dt_rom;
+	int    combo;                     /* QTOS_C0 .. QTOS_CUSTOM */
+	double duration;
+} qtos_shape;
+
+/* one local-plan window = the flags of ./main (ref: main.cpp:163-306) */
+typedef struct {
+	double start_pos[3];              /* -s */
+	double start_ang[3];              /* -s_ang */
+	double start_vel[3];              /* -s_vel (zeroed by main.cpp when -n is absent) */
+	double start_ang_vel[3];          /* -s_ang_vel */
+	double goal[3];                   /* -g (z unused downstream) */
+	double ee[QTOS_NEE][3];           /* -e1..-e4 */
+	double t_start;                   /* -t */
+	int    hf_id;                     /* heightfield handle from qtos_upload_heightfield */
+	int    group;                     /* multi-start group id (best-plan selection), else 0 */
+} qtos_problem;
+
+typedef struct {
+	double tol;                       /* 1e-3 (ifopt default in force, logs/towr_log.out) */
+	double constr_viol_tol;           /* 1e-4 */
+	double compl_inf_tol;             /* 1e-4 */
+	double dual_inf_tol;              /* 1.0  */
+	int    max_iter;                  /* 200 (ref: main.cpp:461) */
+	double mu_init;                   /* 0.1 */
+	double sigma_w;                   /* Hessian model sigma_w * I */
+	double delta_c;                   /* equality-block regularisation */
+} qtos_options;
+
+typedef struct {
+	int    status;
+	int    iters;
+	double constr_viol;               /* unscaled max violation of g_L <= g(x) <= g_U */
+	double dual_inf;
+	double compl_inf;
+	double nlp_error;                 /* Ipopt's scaled overall error E_0 */
+	double mu;
+	double cost;                      /* post-hoc plan cost used for best-plan selection */
+} qtos_result;
+
+typedef struct {
+	int n_vars;                       /* ifopt variable count (1040 for T=5 s Custom) */
+	int n_cons;                       /* constraint rows (1730) */
+	int n_free;                       /* after fixed-variable elimination (1005) */
+	int n_eq, n_ineq;
+	int nnz_jac;                      /* structural non-zeros kept on the device */
+	int csv_rows;                     /* rows of the 1 kHz trajectory (5001) */
+	int kkt_order, kkt_block, kkt_blocks;    /* condensed system: padded order, block size, stored blocks */
+	double flops_factor;              /* algorithmic flops of one factorization (sum of w_i^2) */
+	long long workspace_bytes_per_problem;
+} qtos_dims;
+
+typedef struct qtos_ctx qtos_ctx;
+
+void qtos_default_shape(qtos_shape *s);            /* Solo12 constants as vendored, Custom gait, T = 5 s */
+void qtos_default_options(qtos_options *o);
+
+/* One context = one device + one compiled shape + workspace for max_batch concurrent problems. */
+int  qtos_create(int device, const qtos_shape *shape, int max_batch, qtos_ctx **out);
+void qtos_destroy(qtos_ctx *ctx);
+const char *qtos_last_error(const qtos_ctx *ctx);  /* ctx may be NULL: error of the last failed qtos_create */
+int  qtos_get_dims(const qtos_ctx *ctx, qtos_dims *d);
+
+/* hf[ix*ny + iy], ix = row of towr_heightfield.txt = world x (ref: custom_terrain.cpp:12-49) */
+int  qtos_upload_heightfield(qtos_ctx *ctx, const double *hf, int nx, int ny, double res, int *hf_id);
+/* batched CustomTerrain::GetHeight (ref: custom_terrain.cpp:51-94), bit-exact; xy = n pairs */
+int  qtos_heightfield_query(qtos_ctx *ctx, int hf_id, const double *xy, int n, double *h_out);
+int  qtos_heightfield_cells(qtos_ctx *ctx, int hf_id, const double *xy, int n, long long *idx4_out);
+
+/* problem structure for one instance: x0, bounds (host arrays, n_vars / n_cons long, nullable) */
+int  qtos_get_initial(qtos_ctx *ctx, const qtos_problem *p, int n, double *x0, double *xl, double *xu,
+                      double *gl, double *gu);
+/* constraint values and dense row-major Jacobian (n_cons x n_vars, fixed columns zero) at x;
+ * x = n * n_vars; g_out, jac_out nullable */
+int  qtos_eval(qtos_ctx *ctx, const qtos_problem *p, int n, const double *x, double *g_out, double *jac_out);
+
+/* solve n independent windows (host buffers; H2D/D2H inside).  x_out: n * n_vars node values;
+ * csv_out (nullable): n * csv_rows * 37 doubles */
+int  qtos_solve_batch(qtos_ctx *ctx, const qtos_problem *p, int n, const qtos_options *o,
+                      qtos_result *res, double *x_out, double *csv_out);
+/* same with device-resident buffers (problems, results, x) on the context's stream */
+int  qtos_solve_batch_device(qtos_ctx *ctx, const qtos_problem *d_p, int n, const qtos_options *o,
+                             qtos_result *d_res, double *d_x_out);
+/* 1 kHz sampler (ref: main.cpp:92-131): rows_out = n * csv_rows * 37 */
+int  qtos_sample_csv(qtos_ctx *ctx, const qtos_problem *p, int n, const double *x, double *rows_out);
+/* write one trajectory as the reference's traj.csv text ("%g", comma separated) */
+int  qtos_write_csv(const double *rows, int n_rows, const char *path);
+
+/* instrumentation: kernel launches issued by this context, and device time of the last solve per phase */
+long long qtos_launch_count(const qtos_ctx *ctx);
+int  qtos_last_timing(const qtos_ctx *ctx, float *ms_phase /*8*/, int *iters_total);
+void *qtos_stream(const qtos_ctx *ctx);            /* cudaStream_t the context launches on */
+/* FP64 FMA throughput of the device measured with a register-resident FMA loop, TFLOP/s */
+int  qtos_measure_fp64_peak(qtos_ctx *ctx, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,596 @@
+/*
+ * qtos_compile.cpp -- host "problem compiler": (gait, horizon, Parameters, model) -> static tables.
+ *
+ * Replaces, for the QTOS path, the structure-building half of the reference:
+ *   gait tables            ref: solver/towr/src/quadruped_gait_generator.cc:39-369, gait_generator.cc:54-150
+ *   Parameters             ref: solver/towr/src/parameters.cc:40-135
+ *   variable sets          ref: solver/towr/src/nlp_formulation.cc:63-198, nodes_variables_all.cc:45-61,
+ *                               nodes_variables_phase_based.cc:38-58,197-298
+ *   constraint sets/order  ref: solver/towr/src/nlp_formulation.cc:200-331, parameters.cc:55-60
+ *   sample times           ref: solver/towr/src/time_discretization_constraint.cc:41-49
+ *   spline segment lookup  ref: solver/towr/src/spline.cc:48-79, polynomial.cc:140-234
+ * and adds what a GPU solve needs on top: dense Jacobian "elements", a bandwidth-reducing
+ * ordering of the condensed KKT matrix, its block-skyline layout, and owner-computes gather
+ * lists for J'DJ assembly and J'w products.
+ */
+#include "qtos_tables.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <queue>
+#include <set>
+
+namespace {
+
+/* ------------------------------------------------------------------ gait */
+
+struct Stride { std::vector<double> t; std::vector<const char *> c; };
+
+enum Gait { Stand, Flight, Walk1, Walk2, Walk2E, Run1, Run2, Run2E, Run3, Run3E, Hop1, Hop1E, Hop2, Hop3, Hop3E, Hop5 };
+
+/* two-letter contact code: [hind][front]; I none, P left, b right, B both */
+void decode(const char *c, bool on[QTOS_NEE])
+{
+	on[2] = c[0] == 'P' || c[0] == 'B';
+	on[3] = c[0] == 'b' || c[0] == 'B';
+	on[0] = c[1] == 'P' || c[1] == 'B';
+	on[1] = c[1] == 'b' || c[1] == 'B';
+}
+
+Stride drop_transition(Stride s)
+{
+	double last = s.t.back();
+	s.t.pop_back(); s.c.pop_back();
+	s.t.back() += last;
+	return s;
+}
+
+Stride stride_of(Gait g)
+{
+	switch (g) {
+	case Stand:  return {{0.3}, {"BB"}};
+	case Flight: return {{0.3}, {"Bb"}};
+	case Walk1:  return {{0.3, 0.2, 0.3, 0.2, 0.3, 0.2, 0.3, 0.2}, {"bB", "BB", "Bb", "BB", "PB", "BB", "BP", "BB"}};
+	case Walk2:  return {{0.25, 0.13, 0.25, 0.13, 0.25, 0.13, 0.25, 0.13}, {"bB", "bb", "Bb", "Pb", "PB", "PP", "BP", "bP"}};
+	case Walk2E: return drop_transition(stride_of(Walk2));
+	case Run1:   return {{0.3, 0.2, 0.3, 0.2}, {"bP", "BB", "Pb", "BB"}};
+	case Run2:   return {{0.4, 0.1, 0.4, 0.1}, {"bP", "II", "Pb", "II"}};
+	case Run2E:  return {{0.4}, {"bP"}};
+	case Run3:   return {{0.3, 0.1, 0.3, 0.1}, {"PP", "II", "bb", "II"}};
+	case Run3E:  return {{0.3}, {"PP"}};
+	case Hop1:   return {{0.3, 0.1, 0.3, 0.1}, {"BI", "II", "IB", "II"}};
+	case Hop1E:  return {{0.3}, {"BI"}};
+	case Hop2:   return {{0.3, 0.4, 0.3}, {"BB", "II", "BB"}};
+	case Hop3:   return {{0.2, 0.3, 0.2, 0.2, 0.2, 0.3, 0.2, 0.2}, {"Bb", "BI", "BP", "bP", "bB", "IB", "PB", "Pb"}};
+	case Hop3E:  return drop_transition(stride_of(Hop3));
+	default:     return {{0.1, 0.2, 0.1, 0.1, 0.2, 0.1}, {"Bb", "BB", "IP", "Bb", "BB", "IP"}};
+	}
+}
+
+bool phase_durations(int combo, double T, std::vector<double> dur[QTOS_NEE], bool contact0[QTOS_NEE])
+{
+	static const Gait table[6][6] = {
+		{Stand, Walk2, Walk2, Walk2, Walk2E, Stand}, {Stand, Run2, Run2, Run2, Run2E, Stand},
+		{Stand, Run3, Run3, Run3, Run3E, Stand},     {Stand, Hop1, Hop1, Hop1, Hop1E, Stand},
+		{Stand, Hop3, Hop3, Hop3, Hop3E, Stand},     {Stand, Walk1, Walk1, Walk1, Walk2E, Stand}};
+	if (combo < 0 || combo > 5) return false;
+	std::vector<double> times; std::vector<const char *> codes;
+	for (Gait g : table[combo]) {
+		Stride s = stride_of(g);
+		times.insert(times.end(), s.t.begin(), s.t.end());
+		codes.insert(codes.end(), s.c.begin(), s.c.end());
+	}
+	const int np = (int)times.size();
+	for (int ee = 0; ee < QTOS_NEE; ++ee) {
+		std::vector<double> raw; double acc = 0.0;
+		for (int k = 0; k + 1 < np; ++k) {
+			bool a[QTOS_NEE], b[QTOS_NEE];
+			decode(codes[k], a); decode(codes[k + 1], b);
+			acc += times[k];
+			if (a[ee] != b[ee]) { raw.push_back(acc); acc = 0.0; }
+		}
+		raw.push_back(acc + times[np - 1]);
+		double total = 0.0;
+		for (double v : raw) total += v;
+		dur[ee].clear();
+		for (double v : raw) dur[ee].push_back((v / total) * T);
+		bool a[QTOS_NEE]; decode(codes[0], a);
+		contact0[ee] = a[ee];
+	}
+	return true;
+}
+
+/* ------------------------------------------------------------------ splines */
+
+struct Spl {
+	std::vector<double> dur;
+	std::vector<int> phase, is_const;
+	std::vector<int> opt;            /* [n_nodes*6] set-local index or -1 */
+	int n_vars = 0;
+	int n_polys() const { return (int)dur.size(); }
+	int n_nodes() const { return (int)dur.size() + 1; }
+	int &o(int node, int deriv, int dim) { return opt[node * 6 + deriv * 3 + dim]; }
+	bool const_node(int node) const
+	{
+		if (node == 0) return is_const.front();
+		if (node == n_nodes() - 1) return is_const.back();
+		return is_const[node - 1] || is_const[node];
+	}
+};
+
+Spl make_phase_spline(const std::vector<double> &phase_dur, bool first_const, int polys_changing)
+{
+	Spl s; bool c = first_const;
+	for (size_t i = 0; i < phase_dur.size(); ++i, c = !c) {
+		int np = c ? 1 : polys_changing;
+		for (int j = 0; j < np; ++j) { s.dur.push_back(phase_dur[i] / np); s.phase.push_back((int)i); s.is_const.push_back(c); }
+	}
+	s.opt.assign(s.n_nodes() * 6, -1);
+	return s;
+}
+
+void locate(const std::vector<double> &dur, double t, int *id, double *tl)
+{
+	const double eps = 1e-10;
+	double acc = 0.0; int found = (int)dur.size() - 1;
+	for (int i = 0; i < (int)dur.size(); ++i) { acc += dur[i]; if (acc >= t - eps) { found = i; break; } }
+	double loc = t;
+	for (int i = 0; i < found; ++i) loc -= dur[i];
+	*id = found; *tl = loc;
+}
+
+/* d{p,v,a}(t)/d{p0,v0,p1,v1} of a cubic Hermite polynomial of duration T */
+void hermite_weights(double T, double t, int deriv, double w[4])
+{
+	const double t2 = std::pow(t, 2), t3 = std::pow(t, 3), T2 = std::pow(T, 2), T3 = std::pow(T, 3);
+	if (deriv == 0) {
+		w[0] = (2 * t3) / T3 - (3 * t2) / T2 + 1; w[1] = t - (2 * t2) / T + t3 / T2;
+		w[2] = (3 * t2) / T2 - (2 * t3) / T3;     w[3] = t3 / T2 - t2 / T;
+	} else if (deriv == 1) {
+		w[0] = (6 * t2) / T3 - (6 * t) / T2;      w[1] = (3 * t2) / T2 - (4 * t) / T + 1;
+		w[2] = (6 * t) / T2 - (6 * t2) / T3;      w[3] = (3 * t2) / T2 - (2 * t) / T;
+	} else {
+		w[0] = (12 * t) / T3 - 6 / T2;            w[1] = (6 * t) / T2 - 4 / T;
+		w[2] = 6 / T2 - (12 * t) / T3;            w[3] = (6 * t) / T2 - 2 / T;
+	}
+}
+
+std::vector<double> sample_times(double T, double dt)
+{
+	std::vector<double> t; double acc = 0.0;
+	t.push_back(acc);
+	for (int i = 0; i < (int)std::floor(T / dt); ++i) { acc += dt; t.push_back(acc); }
+	t.push_back(T);
+	return t;
+}
+
+/* ------------------------------------------------------------------ ordering */
+
+std::vector<int> rcm(int n, const std::vector<std::set<int>> &adj)
+{
+	std::vector<int> order; order.reserve(n);
+	std::vector<char> seen(n, 0);
+	auto bfs_far = [&](int s) {
+		std::vector<int> lvl(n, -1); std::queue<int> q; q.push(s); lvl[s] = 0; int far = s;
+		while (!q.empty()) {
+			int u = q.front(); q.pop();
+			if (lvl[u] > lvl[far] || (lvl[u] == lvl[far] && adj[u].size() < adj[far].size())) far = u;
+			for (int v : adj[u]) if (lvl[v] < 0 && !seen[v]) { lvl[v] = lvl[u] + 1; q.push(v); }
+		}
+		return far;
+	};
+	while ((int)order.size() < n) {
+		int s = -1;
+		for (int i = 0; i < n; ++i) if (!seen[i] && (s < 0 || adj[i].size() < adj[s].size())) s = i;
+		for (int rep = 0; rep < 4; ++rep) { int f = bfs_far(s); if (f == s) break; s = f; }
+		size_t head = order.size();
+		order.push_back(s); seen[s] = 1;
+		while (head < order.size()) {
+			int u = order[head++];
+			std::vector<int> nb;
+			for (int v : adj[u]) if (!seen[v]) { nb.push_back(v); seen[v] = 1; }
+			std::stable_sort(nb.begin(), nb.end(), [&](int a, int b) { return adj[a].size() < adj[b].size(); });
+			order.insert(order.end(), nb.begin(), nb.end());
+		}
+	}
+	std::reverse(order.begin(), order.end());
+	return order;
+}
+
+struct LinRow { int row; std::vector<std::pair<int, double>> terms; };   /* (full var, coef), merged */
+
+void lin_add(LinRow &r, int var, double coef)
+{
+	if (var < 0) return;
+	for (auto &t : r.terms) if (t.first == var) { t.second += coef; return; }
+	r.terms.push_back({var, coef});
+}
+
+}  // namespace
+
+int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int errlen)
+{
+	auto fail = [&](const char *msg) { std::snprintf(err, errlen, "%s", msg); return (int)QTOS_ESHAPE; };
+	const qtos_shape &sh = *shape;
+	H->shape = sh;
+	if (!(sh.duration > 0) || !(sh.dt_base_poly > 0) || !(sh.dt_dynamic > 0) || !(sh.dt_rom > 0) || !(sh.mass > 0))
+		return fail("shape: duration, dt_* and mass must be positive");
+	if (sh.force_polys_per_stance < 1 || sh.ee_polys_per_swing != 2)
+		return fail("shape: force_polys_per_stance >= 1 and ee_polys_per_swing == 2 required");
+
+	std::vector<double> ph[QTOS_NEE]; bool contact0[QTOS_NEE];
+	if (!phase_durations(sh.combo, sh.duration, ph, contact0)) return fail("shape: unknown gait combo");
+	for (int ee = 0; ee < QTOS_NEE; ++ee)
+		if (!contact0[ee]) return fail("shape: every foot must start in contact");
+	double T = 0.0;
+	for (double v : ph[0]) T += v;
+	H->T = T;
+
+	/* ---- splines and variable layout (ifopt order) ---- */
+	Spl spl[10];
+	{
+		std::vector<double> bd; double left = T;
+		while (left > 1e-10) { bd.push_back(left > sh.dt_base_poly ? sh.dt_base_poly : left); left -= sh.dt_base_poly; }
+		for (int s = 0; s < 2; ++s) {
+			spl[s].dur = bd; spl[s].phase.assign(bd.size(), 0); spl[s].is_const.assign(bd.size(), 0);
+			spl[s].opt.resize(spl[s].n_nodes() * 6);
+			for (int i = 0; i < spl[s].n_nodes() * 6; ++i) spl[s].opt[i] = i;
+			spl[s].n_vars = spl[s].n_nodes() * 6;
+		}
+	}
+	for (int ee = 0; ee < QTOS_NEE; ++ee) {
+		Spl &mo = spl[2 + ee];
+		mo = make_phase_spline(ph[ee], contact0[ee], sh.ee_polys_per_swing);
+		int idx = 0;
+		for (int node = 0; node < mo.n_nodes(); ++node) {
+			if (!mo.const_node(node)) {
+				for (int d = 0; d < 3; ++d) { mo.o(node, 0, d) = idx++; if (d != 2) mo.o(node, 1, d) = idx++; }
+			} else {
+				for (int d = 0; d < 3; ++d) { mo.o(node, 0, d) = idx; mo.o(node + 1, 0, d) = idx; idx++; }
+				node++;
+			}
+		}
+		mo.n_vars = idx;
+		Spl &fo = spl[6 + ee];
+		fo = make_phase_spline(ph[ee], !contact0[ee], sh.force_polys_per_stance);
+		idx = 0;
+		for (int node = 0; node < fo.n_nodes(); ++node) {
+			if (!fo.const_node(node)) { for (int d = 0; d < 3; ++d) { fo.o(node, 0, d) = idx++; fo.o(node, 1, d) = idx++; } }
+			else node++;
+		}
+		fo.n_vars = idx;
+	}
+	int off = 0, max_nodes = 0;
+	for (int s = 0; s < 10; ++s) {
+		H->var_off[s] = off; off += spl[s].n_vars;
+		H->n_nodes[s] = spl[s].n_nodes(); H->n_polys[s] = spl[s].n_polys();
+		H->dur[s] = spl[s].dur;
+		max_nodes = std::max(max_nodes, spl[s].n_nodes());
+		if (spl[s].n_polys() > 250) return fail("shape: too many polynomials (horizon too long)");
+	}
+	H->var_off[10] = off;
+	const int n_all = off;
+	if (n_all > 32000) return fail("shape: too many variables");
+	H->n_all = n_all; H->max_nodes = max_nodes;
+	H->node_var.assign((size_t)10 * max_nodes * 6, -1);
+	auto nv = [&](int s, int node, int q) -> int16_t & { return H->node_var[((size_t)s * max_nodes + node) * 6 + q]; };
+	H->x0_spline.assign(n_all, 0); H->x0_deriv.assign(n_all, 0); H->x0_dim.assign(n_all, 0); H->x0_node.assign(n_all, 0);
+	for (int s = 0; s < 10; ++s)
+		for (int node = 0; node < spl[s].n_nodes(); ++node)
+			for (int q = 0; q < 6; ++q) {
+				int o = spl[s].opt[node * 6 + q];
+				if (o < 0) continue;
+				int v = H->var_off[s] + o;
+				nv(s, node, q) = (int16_t)v;
+				/* later node overwrites: GetValues() reports the last node mapped to an index */
+				H->x0_spline[v] = (uint8_t)s; H->x0_node[v] = (int16_t)node; H->x0_deriv[v] = (uint8_t)(q / 3); H->x0_dim[v] = (uint8_t)(q % 3);
+			}
+	/* fixed variables = equal bounds (ref: nlp_formulation.cc:110-121,151; parameters.cc:66-69) */
+	H->fix_src.assign(n_all, -1);
+	auto fix = [&](int s, int node, int deriv, int dim, int src) { int v = nv(s, node, deriv * 3 + dim); if (v >= 0) H->fix_src[v] = (int8_t)src; };
+	{
+		const int last = spl[0].n_nodes() - 1;
+		for (int d = 0; d < 3; ++d) {
+			fix(0, 0, 0, d, QP_START_POS + d); fix(0, 0, 1, d, QP_START_VEL + d); fix(0, last, 1, d, QP_ZERO);
+			fix(1, 0, 0, d, QP_START_ANG + d); fix(1, 0, 1, d, QP_START_ANGVEL + d);
+			fix(1, last, 0, d, QP_ZERO);       fix(1, last, 1, d, QP_ZERO);
+		}
+		fix(0, last, 0, 0, QP_GOAL + 0); fix(0, last, 0, 1, QP_GOAL + 1);
+		for (int ee = 0; ee < QTOS_NEE; ++ee) for (int d = 0; d < 3; ++d) fix(2 + ee, 0, 0, d, QP_EE + 3 * ee + d);
+	}
+	std::vector<int> free_of(n_all, -1), var_of_free;
+	for (int v = 0; v < n_all; ++v) if (H->fix_src[v] < 0) { free_of[v] = (int)var_of_free.size(); var_of_free.push_back(v); }
+	const int n_free = (int)var_of_free.size();
+	H->n_free = n_free;
+
+	/* ---- rows (ifopt order: Terrain, Dynamic, BaseAcc, EndeffectorRom, Force, Swing) ---- */
+	std::vector<double> t_dyn = sample_times(T, sh.dt_dynamic), t_rom = sample_times(T, sh.dt_rom);
+	H->n_dyn = (int)t_dyn.size(); H->n_rom = (int)t_rom.size();
+	int row = 0, ro = 0;
+	int row_ter[QTOS_NEE], row_rom[QTOS_NEE], row_force[QTOS_NEE], row_swing[QTOS_NEE];
+	for (int ee = 0; ee < QTOS_NEE; ++ee) { row_ter[ee] = row; H->row_off[ro++] = row; row += spl[2 + ee].n_nodes() - 1; }
+	const int row_dyn = row; H->row_off[ro++] = row; row += 6 * H->n_dyn;
+	const int row_acc[2] = {row, row + 3 * (spl[0].n_polys() - 1)};
+	H->row_off[ro++] = row_acc[0]; H->row_off[ro++] = row_acc[1];
+	row += 6 * (spl[0].n_polys() - 1);
+	for (int ee = 0; ee < QTOS_NEE; ++ee) { row_rom[ee] = row; H->row_off[ro++] = row; row += 3 * H->n_rom; }
+	for (int ee = 0; ee < QTOS_NEE; ++ee) {
+		int cnt = 0; for (int nd = 0; nd < spl[6 + ee].n_nodes(); ++nd) cnt += !spl[6 + ee].const_node(nd);
+		row_force[ee] = row; H->row_off[ro++] = row; row += 5 * cnt;
+	}
+	for (int ee = 0; ee < QTOS_NEE; ++ee) {
+		int cnt = 0; for (int nd = 0; nd < spl[2 + ee].n_nodes(); ++nd) cnt += !spl[2 + ee].const_node(nd);
+		row_swing[ee] = row; H->row_off[ro++] = row; row += 4 * cnt;
+	}
+	H->row_off[ro] = row;
+	const int m = row;
+	H->m = m;
+	const double INF = 1e20;
+	H->gl.assign(m, 0.0); H->gu.assign(m, 0.0); H->row_elem.assign(m, -1);
+
+	/* ---- elements ---- */
+	std::vector<std::vector<int>> ecols;      /* element -> free (unpermuted) columns */
+	std::vector<std::vector<double>> econst;  /* element -> col-major constant values (empty for dyn/rom) */
+	auto new_elem = [&](int type, int row0, int nrows, const std::vector<int> &cols) {
+		Element e; e.type = type; e.row0 = row0; e.nrows = nrows; e.ncols = (int)cols.size(); e.valoff = 0; e.coloff = 0;
+		H->elems.push_back(e); ecols.push_back(cols); econst.push_back({});
+		for (int r = 0; r < nrows; ++r) H->row_elem[row0 + r] = (int)H->elems.size() - 1;
+		return (int)H->elems.size() - 1;
+	};
+	std::vector<LinRow> lin;
+	/* const element from a group of consecutive linear rows */
+	auto const_elem = [&](const std::vector<LinRow> &rows) {
+		std::vector<int> cols;
+		for (auto &r : rows) for (auto &t : r.terms) {
+			int f = free_of[t.first];
+			if (f >= 0 && std::find(cols.begin(), cols.end(), f) == cols.end()) cols.push_back(f);
+		}
+		int e = new_elem(EL_CONST, rows[0].row, (int)rows.size(), cols);
+		econst[e].assign(cols.size() * rows.size(), 0.0);
+		for (size_t r = 0; r < rows.size(); ++r) for (auto &t : rows[r].terms) {
+			int f = free_of[t.first]; if (f < 0) continue;
+			size_t a = std::find(cols.begin(), cols.end(), f) - cols.begin();
+			econst[e][a * rows.size() + r] += t.second;
+		}
+	};
+	/* terrain (ref: terrain_constraint.cc:59-108): g = z - h(x,y); dh/dx = dh/dy = 0 on this path */
+	for (int ee = 0; ee < QTOS_NEE; ++ee) {
+		const Spl &s = spl[2 + ee];
+		for (int nd = 1; nd < s.n_nodes(); ++nd) {
+			int r = row_ter[ee] + nd - 1;
+			if (!s.const_node(nd)) H->gu[r] = INF;
+			int vx = nv(2 + ee, nd, 0), vy = nv(2 + ee, nd, 1), vz = nv(2 + ee, nd, 2);
+			H->ter_row.push_back(r);
+			H->ter_var.push_back((int16_t)vx); H->ter_var.push_back((int16_t)vy); H->ter_var.push_back((int16_t)vz);
+			LinRow lr; lr.row = r; lin_add(lr, vz, 1.0);
+			const_elem({lr});              /* J only; g comes from the terrain table */
+		}
+	}
+	/* dynamics (ref: dynamic_constraint.cc:37-137) */
+	H->dyn.resize(H->n_dyn);
+	for (int k = 0; k < H->n_dyn; ++k) {
+		DynSample &D = H->dyn[k];
+		double tl; locate(spl[0].dur, t_dyn[k], &D.base_id, &tl);
+		for (int d = 0; d < 3; ++d) hermite_weights(spl[0].dur[D.base_id], tl, d, D.W[d]);
+		std::vector<int> cols; std::vector<int> canon_var(QTOS_DYN_CANON, -1);
+		for (int q = 0; q < 12; ++q) {
+			canon_var[q] = H->var_off[0] + (D.base_id + q / 6) * 6 + q % 6;
+			canon_var[12 + q] = H->var_off[1] + (D.base_id + q / 6) * 6 + q % 6;
+		}
+		for (int ee = 0; ee < QTOS_NEE; ++ee) {
+			locate(spl[2 + ee].dur, t_dyn[k], &D.mo_id[ee], &tl);
+			hermite_weights(spl[2 + ee].dur[D.mo_id[ee]], tl, 0, D.mo_w[ee]);
+			locate(spl[6 + ee].dur, t_dyn[k], &D.fo_id[ee], &tl);
+			hermite_weights(spl[6 + ee].dur[D.fo_id[ee]], tl, 0, D.fo_w[ee]);
+			for (int q = 0; q < 12; ++q) {
+				canon_var[24 + ee * 24 + q] = nv(2 + ee, D.mo_id[ee] + q / 6, q % 6);
+				canon_var[24 + ee * 24 + 12 + q] = nv(6 + ee, D.fo_id[ee] + q / 6, q % 6);
+			}
+		}
+		for (int c = 0; c < QTOS_DYN_CANON; ++c) {
+			D.slot[c] = -1;
+			int f = canon_var[c] >= 0 ? free_of[canon_var[c]] : -1;
+			if (f < 0) continue;
+			size_t a = std::find(cols.begin(), cols.end(), f) - cols.begin();
+			if (a == cols.size()) cols.push_back(f);
+			D.slot[c] = (int8_t)a;
+		}
+		if (cols.size() > 127) return fail("dyn element too wide");
+		D.elem = new_elem(EL_DYN, row_dyn + 6 * k, 6, cols);
+	}
+	/* base acceleration continuity (ref: spline_acc_constraint.cc:48-80) */
+	for (int w = 0; w < 2; ++w)
+		for (int j = 0; j + 1 < spl[w].n_polys(); ++j)
+			for (int d = 0; d < 3; ++d) {
+				LinRow lr; lr.row = row_acc[w] + 3 * j + d;
+				double a0[4], a1[4];
+				hermite_weights(spl[w].dur[j], spl[w].dur[j], 2, a0);
+				hermite_weights(spl[w].dur[j + 1], 0.0, 2, a1);
+				for (int q = 0; q < 4; ++q) {
+					lin_add(lr, H->var_off[w] + (j + q / 2) * 6 + (q % 2) * 3 + d, a0[q]);
+					lin_add(lr, H->var_off[w] + (j + 1 + q / 2) * 6 + (q % 2) * 3 + d, -a1[q]);
+				}
+				lin.push_back(lr); const_elem({lr});
+			}
+	/* range of motion (ref: range_of_motion_constraint.cc:59-109) */
+	for (int ee = 0; ee < QTOS_NEE; ++ee)
+		for (int k = 0; k < H->n_rom; ++k) {
+			RomSample R; double tl;
+			R.ee = ee;
+			locate(spl[0].dur, t_rom[k], &R.base_id, &tl);
+			hermite_weights(spl[0].dur[R.base_id], tl, 0, R.wp);
+			locate(spl[2 + ee].dur, t_rom[k], &R.mo_id, &tl);
+			hermite_weights(spl[2 + ee].dur[R.mo_id], tl, 0, R.mo_w);
+			std::vector<int> cols;
+			for (int c = 0; c < QTOS_ROM_CANON; ++c) {
+				int q = c % 12, var;
+				if (c < 12) var = H->var_off[0] + (R.base_id + q / 6) * 6 + q % 6;
+				else if (c < 24) var = H->var_off[1] + (R.base_id + q / 6) * 6 + q % 6;
+				else var = nv(2 + ee, R.mo_id + q / 6, q % 6);
+				/* only position weights act: velocity nodes still enter through the Hermite basis */
+				R.slot[c] = -1;
+				int f = var >= 0 ? free_of[var] : -1;
+				if (f < 0) continue;
+				size_t a = std::find(cols.begin(), cols.end(), f) - cols.begin();
+				if (a == cols.size()) cols.push_back(f);
+				R.slot[c] = (int8_t)a;
+			}
+			const int r0 = row_rom[ee] + 3 * k;
+			for (int d = 0; d < 3; ++d) { H->gl[r0 + d] = sh.nominal[ee][d] - sh.max_dev[d]; H->gu[r0 + d] = sh.nominal[ee][d] + sh.max_dev[d]; }
+			R.elem = new_elem(EL_ROM, r0, 3, cols);
+			H->rom.push_back(R);
+		}
+	/* force (ref: force_constraint.cc:67-135); terrain basis is n=ez, t1=ex, t2=ey on this path */
+	for (int ee = 0; ee < QTOS_NEE; ++ee) {
+		int r = row_force[ee];
+		for (int nd = 0; nd < spl[6 + ee].n_nodes(); ++nd) {
+			if (spl[6 + ee].const_node(nd)) continue;
+			const int fx = nv(6 + ee, nd, 0), fy = nv(6 + ee, nd, 1), fz = nv(6 + ee, nd, 2);
+			std::vector<LinRow> rows(5);
+			for (int q = 0; q < 5; ++q) rows[q].row = r + q;
+			lin_add(rows[0], fz, 1.0);
+			lin_add(rows[1], fx, 1.0); lin_add(rows[1], fz, -sh.mu);
+			lin_add(rows[2], fx, 1.0); lin_add(rows[2], fz, sh.mu);
+			lin_add(rows[3], fy, 1.0); lin_add(rows[3], fz, -sh.mu);
+			lin_add(rows[4], fy, 1.0); lin_add(rows[4], fz, sh.mu);
+			H->gl[r] = 0.0;      H->gu[r] = sh.force_limit;
+			H->gl[r + 1] = -INF; H->gu[r + 1] = 0.0;
+			H->gl[r + 2] = 0.0;  H->gu[r + 2] = INF;
+			H->gl[r + 3] = -INF; H->gu[r + 3] = 0.0;
+			H->gl[r + 4] = 0.0;  H->gu[r + 4] = INF;
+			for (auto &lr : rows) lin.push_back(lr);
+			const_elem(rows);
+			r += 5;
+		}
+	}
+	/* swing (ref: swing_constraint.cc:59-108) */
+	for (int ee = 0; ee < QTOS_NEE; ++ee) {
+		int r = row_swing[ee];
+		for (int nd = 0; nd < spl[2 + ee].n_nodes(); ++nd) {
+			if (spl[2 + ee].const_node(nd)) continue;
+			std::vector<LinRow> rows(4);
+			for (int d = 0; d < 2; ++d) {
+				const int cur_p = nv(2 + ee, nd, d), cur_v = nv(2 + ee, nd, 3 + d);
+				const int prev = nv(2 + ee, nd - 1, d), next = nv(2 + ee, nd + 1, d);
+				LinRow &rp = rows[2 * d], &rv = rows[2 * d + 1];
+				rp.row = r + 2 * d; rv.row = r + 2 * d + 1;
+				lin_add(rp, cur_p, 1.0); lin_add(rp, next, -0.5); lin_add(rp, prev, -0.5);
+				lin_add(rv, cur_v, 1.0); lin_add(rv, next, -1.0 / sh.t_swing_avg); lin_add(rv, prev, 1.0 / sh.t_swing_avg);
+			}
+			for (auto &lr : rows) lin.push_back(lr);
+			const_elem(rows);
+			r += 4;
+		}
+	}
+	for (int r = 0; r < m; ++r) if (H->row_elem[r] < 0) return fail("internal: row without element");
+	/* row flags */
+	H->row_flags.assign(m, 0); H->n_eq = H->n_ineq = H->n_bounds = 0;
+	for (int r = 0; r < m; ++r) {
+		if (H->gl[r] == H->gu[r]) { H->row_flags[r] = ROW_EQ; H->n_eq++; continue; }
+		H->n_ineq++;
+		if (H->gl[r] > -1e19) { H->row_flags[r] |= ROW_HASL; H->n_bounds++; }
+		if (H->gu[r] < 1e19) { H->row_flags[r] |= ROW_HASU; H->n_bounds++; }
+	}
+	/* linear-row table */
+	H->lin_ptr.push_back(0);
+	for (auto &lr : lin) {
+		H->lin_row.push_back(lr.row);
+		for (auto &t : lr.terms) { H->lin_col.push_back((int16_t)t.first); H->lin_val.push_back(t.second); }
+		H->lin_ptr.push_back((int)H->lin_col.size());
+	}
+
+	/* ---- ordering of the condensed KKT matrix ---- */
+	std::vector<std::set<int>> adj(n_free);
+	for (auto &c : ecols) for (int a : c) for (int b : c) if (a != b) adj[a].insert(b);
+	std::vector<int> order = rcm(n_free, adj);           /* order[new] = old free index */
+	std::vector<int> pos(n_free);
+	for (int i = 0; i < n_free; ++i) pos[order[i]] = i;
+	const int NB = QTOS_NB;
+	const int npad = ((n_free + NB - 1) / NB) * NB, nb = npad / NB;
+	H->npad = npad; H->nb = nb;
+	H->perm_of_var.assign(n_all, -1); H->var_of_perm.assign(npad, -1);
+	for (int f = 0; f < n_free; ++f) { H->perm_of_var[var_of_free[f]] = (int16_t)pos[f]; H->var_of_perm[pos[f]] = (int16_t)var_of_free[f]; }
+	std::vector<int> first(npad);
+	for (int i = 0; i < npad; ++i) first[i] = i;
+	for (auto &c : ecols) {
+		int mn = npad;
+		for (int a : c) mn = std::min(mn, pos[a]);
+		for (int a : c) first[pos[a]] = std::min(first[pos[a]], mn);
+	}
+	H->flops_factor = 0;
+	for (int i = 0; i < n_free; ++i) { double w = i - first[i]; H->flops_factor += w * w; }
+	H->fb.assign(nb, 0); H->blkptr.assign(nb + 1, 0);
+	for (int I = 0; I < nb; ++I) {
+		int mn = npad;
+		for (int i = I * NB; i < (I + 1) * NB; ++i) mn = std::min(mn, first[i]);
+		H->fb[I] = mn / NB;
+		H->blkptr[I + 1] = H->blkptr[I] + (I - H->fb[I] + 1);
+	}
+	H->nM = H->blkptr[nb] * NB * NB;
+	auto m_off = [&](int i, int j) {    /* i >= j, inside the block skyline */
+		int I = i / NB, J = j / NB;
+		return (H->blkptr[I] + J - H->fb[I]) * NB * NB + (i % NB) * NB + (j % NB);
+	};
+	H->diag_off.resize(npad);
+	for (int i = 0; i < npad; ++i) H->diag_off[i] = m_off(i, i);
+
+	/* ---- element storage, gather lists ---- */
+	int valoff = 0; H->nnz_jac = 0;
+	for (size_t e = 0; e < H->elems.size(); ++e) {
+		Element &E = H->elems[e];
+		E.valoff = valoff; E.coloff = (int)H->elem_cols.size();
+		for (int a : ecols[e]) H->elem_cols.push_back((int16_t)pos[a]);
+		valoff += E.nrows * E.ncols;
+		H->nnz_jac += E.nrows * E.ncols;
+		if (E.ncols > 255 || e > 65535) return fail("element table overflow");
+	}
+	H->nJ = valoff;
+	H->Jconst.assign(H->nJ > 0 ? H->nJ : 1, 0.0);
+	for (size_t e = 0; e < H->elems.size(); ++e)
+		for (size_t q = 0; q < econst[e].size(); ++q) H->Jconst[H->elems[e].valoff + q] = econst[e][q];
+	{
+		std::vector<std::pair<int, uint32_t>> terms;       /* (M offset, packed term) */
+		std::vector<std::vector<uint32_t>> jt(npad);
+		for (size_t e = 0; e < H->elems.size(); ++e) {
+			const std::vector<int> &c = ecols[e];
+			for (size_t a = 0; a < c.size(); ++a) {
+				jt[pos[c[a]]].push_back((uint32_t)(e << 8) | (uint32_t)a);
+				for (size_t b = 0; b < c.size(); ++b) {
+					int pa = pos[c[a]], pb = pos[c[b]];
+					if (pa < pb || (pa == pb && a != b)) continue;
+					terms.push_back({m_off(pa, pb), (uint32_t)(e << 16) | (uint32_t)(a << 8) | (uint32_t)b});
+				}
+			}
+		}
+		std::stable_sort(terms.begin(), terms.end(), [](const std::pair<int, uint32_t> &x, const std::pair<int, uint32_t> &y) { return x.first < y.first; });
+		H->asm_ptr.clear(); H->asm_off.clear(); H->asm_terms.clear();
+		for (size_t q = 0; q < terms.size(); ++q) {
+			if (q == 0 || terms[q].first != terms[q - 1].first) { H->asm_ptr.push_back((int)q); H->asm_off.push_back(terms[q].first); }
+			H->asm_terms.push_back(terms[q].second);
+		}
+		H->asm_ptr.push_back((int)terms.size());
+		H->jt_ptr.assign(1, 0);
+		for (int i = 0; i < npad; ++i) {
+			H->jt_terms.insert(H->jt_terms.end(), jt[i].begin(), jt[i].end());
+			H->jt_ptr.push_back((int)H->jt_terms.size());
+		}
+	}
+
+	/* ---- 1 kHz sampler (ref: main.cpp:92-131): t accumulates += 0.001 while t <= T + 1e-4 ---- */
+	{
+		double Tb = 0.0; for (double d : spl[0].dur) Tb += d;
+		double t = 0.0;
+		while (t <= Tb + 1e-4) { H->csv_t.push_back(t); t += 0.001; }
+		H->csv_rows = (int)H->csv_t.size();
+		H->csv_id.resize((size_t)H->csv_rows * 10); H->csv_tl.resize((size_t)H->csv_rows * 10);
+		for (int r = 0; r < H->csv_rows; ++r)
+			for (int s = 0; s < 10; ++s) {
+				int id; double tl; locate(spl[s].dur, H->csv_t[r], &id, &tl);
+				H->csv_id[(size_t)r * 10 + s] = (uint8_t)id; H->csv_tl[(size_t)r * 10 + s] = tl;
+			}
+	}
+	return QTOS_OK;
+}

@@ -1,0 +1,425 @@
+/*
+ * qtos_device.cuh -- device-side view of the compiled shape tables and the per-problem
+ * workspace, plus the evaluation device functions (spline sampling, SRBD dynamics,
+ * range of motion, terrain, linear rows) shared by all kernels.
+ *
+ * Arithmetic restated for the GPU (not a translation): because phase durations are fixed,
+ * every spline sample is a constant linear map of node values (Hermite weights compiled on
+ * the host), and every Jacobian block is (d row / d sampled quantity) x (Hermite weight),
+ * formed directly in the element's dense column-major block.
+ *   spline sampling   ref: solver/towr/src/polynomial.cc:47-257, spline.cc:48-123, node_spline.cc:45-112
+ *   Euler ZYX         ref: solver/towr/src/euler_converter.cc:58-310
+ *   SRBD dynamics     ref: solver/towr/src/single_rigid_body_dynamics.cc:76-192, dynamic_constraint.cc:73-137
+ *   range of motion   ref: solver/towr/src/range_of_motion_constraint.cc:59-109
+ *   terrain           ref: solver/towr/src/terrain_constraint.cc:59-108, custom_terrain.cpp:51-159
+ */
+#ifndef QTOS_DEVICE_CUH_
+#define QTOS_DEVICE_CUH_
+
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "qtos_tables.h"
+
+struct DevHeightfield { const double *h; int nx, ny; double res; };
+
+struct DevTables {
+	/* dims */
+	int n_all, n_free, npad, m, n_eq, n_ineq, n_bounds, n_dyn, n_rom4, n_lin, n_ter, n_elem;
+	int nJ, nb, nM, n_targets, n_chunks, csv_rows, max_nodes;
+	int n_nodes[10], var_off[11];
+	double T, mass, Ib[9], grav;
+	/* tables */
+	const int16_t *node_var;
+	const uint8_t *x0_spline, *x0_deriv, *x0_dim; const int16_t *x0_node; const int8_t *fix_src;
+	const int16_t *perm_of_var, *var_of_perm;
+	const uint8_t *row_flags; const double *gl, *gu; const int *row_elem;
+	const Element *elems; const int16_t *elem_cols; const double *Jconst;
+	const DynSample *dyn; const RomSample *rom;
+	const int *lin_row, *lin_ptr; const int16_t *lin_col; const double *lin_val;
+	const int *ter_row; const int16_t *ter_var;
+	const int *fb, *blkptr, *diag_off;
+	const int *asm_ptr, *asm_off, *asm_chunk; const uint32_t *asm_terms;
+	const int *jt_ptr; const uint32_t *jt_terms;
+	const double *csv_t, *csv_tl; const uint8_t *csv_id;
+	const double *dur; int dur_ld;          /* [10][dur_ld] */
+	double nominal[QTOS_NEE][3];
+};
+
+/* per-problem workspace: arrays of [n_problems][len] */
+struct DevWork {
+	double *x, *xt;                         /* [n_all] */
+	double *r, *rt, *s, *st, *y, *zL, *zU, *dL, *dU, *Sig, *w, *ds, *dy, *dzL, *dzU, *sc;   /* [m] */
+	double *vec, *rx;                       /* [npad] */
+	double *P;                              /* [32] */
+	double *scal;                           /* [16]: 0 mu, 1 nu, 2 sd, 3 sc_, 4 dual_inf, 5 theta_inf, ... */
+	double *Jv;                             /* [nJ] */
+	double *M;                              /* [nM] */
+	double *Dinv;                           /* [nb*256] inverses of the diagonal blocks of L */
+	int *status, *iters, *flags;            /* [1] each */
+	int *n_running;                         /* single counter */
+};
+
+enum { SC_MU = 0, SC_NU, SC_SD, SC_SC, SC_DUAL, SC_THETA, SC_COMPL, SC_VIOL, SC_E0, SC_N };
+
+/* ------------------------------------------------------------------ heightfield */
+
+/* CustomTerrain::GetHeight, bit-exact: same operation order as the reference, no FMA contraction.
+ * ref: solver/towr/src/custom_terrain.cpp:51-94; custom_terrain.hpp:32-35 (offsets -1,-1,0; z scale 1) */
+__device__ __forceinline__ long long qtos_clamp_index(double fl, long long size)
+{
+	/* static_cast<size_t>(negative) wraps, std::min(.., size-1) then clamps to the LAST cell */
+	if (!(fl >= 0.0)) return size - 1;
+	if (fl >= (double)(size - 1)) return size - 1;
+	return (long long)fl;
+}
+
+__device__ __forceinline__ void qtos_height_cell(const DevHeightfield &hf, double x, double y, long long c[4])
+{
+	const double xf = floor(__ddiv_rn(__dadd_rn(x, 1.0), hf.res));
+	const double yf = floor(__ddiv_rn(__dadd_rn(y, 1.0), hf.res));
+	c[0] = qtos_clamp_index(xf, hf.nx);
+	c[1] = qtos_clamp_index(yf, hf.ny);
+	c[2] = c[0] + 1 < hf.nx - 1 ? c[0] + 1 : hf.nx - 1;
+	c[3] = c[1] + 1 < hf.ny - 1 ? c[1] + 1 : hf.ny - 1;
+}
+
+__device__ __forceinline__ double qtos_height(const DevHeightfield &hf, double x, double y)
+{
+	long long c[4];
+	qtos_height_cell(hf, x, y, c);
+	const double res = hf.res;
+	const double x0 = __dadd_rn(__dmul_rn((double)c[0], res), -1.0), x1 = __dadd_rn(__dmul_rn((double)c[2], res), -1.0);
+	const double y0 = __dadd_rn(__dmul_rn((double)c[1], res), -1.0), y1 = __dadd_rn(__dmul_rn((double)c[3], res), -1.0);
+	const double z00 = __ldg(hf.h + c[0] * hf.ny + c[1]), z01 = __ldg(hf.h + c[0] * hf.ny + c[3]);
+	const double z10 = __ldg(hf.h + c[2] * hf.ny + c[1]), z11 = __ldg(hf.h + c[2] * hf.ny + c[3]);
+	const double s = __ddiv_rn(1.0, __dmul_rn(res, res));
+	const double u0 = __dmul_rn(s, __dsub_rn(x1, x)), u1 = __dmul_rn(s, __dsub_rn(x, x0));
+	const double w0 = __dadd_rn(__dmul_rn(u0, z00), __dmul_rn(u1, z10));
+	const double w1 = __dadd_rn(__dmul_rn(u0, z01), __dmul_rn(u1, z11));
+	return __dadd_rn(__dmul_rn(w0, __dsub_rn(y1, y)), __dmul_rn(w1, __dsub_rn(y, y0)));
+}
+
+/* ------------------------------------------------------------------ small algebra */
+
+__device__ __forceinline__ void mat3_vec(const double *A, const double *v, double *o)
+{
+	for (int i = 0; i < 3; ++i) o[i] = A[3 * i] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2];
+}
+__device__ __forceinline__ void mat3T_vec(const double *A, const double *v, double *o)
+{
+	for (int i = 0; i < 3; ++i) o[i] = A[i] * v[0] + A[3 + i] * v[1] + A[6 + i] * v[2];
+}
+__device__ __forceinline__ void cross3(const double *a, const double *b, double *o)
+{
+	o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+struct EulerState {
+	double sx, cx, sy, cy, sz, cz;
+	double R[9], M[9], Md[9];
+};
+
+__device__ __forceinline__ void euler_R(EulerState &E, const double *e)
+{
+	sincos(e[0], &E.sx, &E.cx); sincos(e[1], &E.sy, &E.cy); sincos(e[2], &E.sz, &E.cz);
+	const double sx = E.sx, cx = E.cx, sy = E.sy, cy = E.cy, sz = E.sz, cz = E.cz;
+	E.R[0] = cy * cz; E.R[1] = cz * sx * sy - cx * sz; E.R[2] = sx * sz + cx * cz * sy;
+	E.R[3] = cy * sz; E.R[4] = cx * cz + sx * sy * sz; E.R[5] = cx * sy * sz - cz * sx;
+	E.R[6] = -sy;     E.R[7] = cy * sx;                E.R[8] = cx * cy;
+}
+
+/* dR/d(roll|pitch|yaw) */
+__device__ __forceinline__ void euler_dR(const EulerState &E, int k, double *D)
+{
+	const double sx = E.sx, cx = E.cx, sy = E.sy, cy = E.cy, sz = E.sz, cz = E.cz;
+	if (k == 0) {
+		D[0] = 0; D[1] = sx * sz + cx * cz * sy; D[2] = cx * sz - cz * sx * sy;
+		D[3] = 0; D[4] = cx * sy * sz - cz * sx; D[5] = -cx * cz - sx * sy * sz;
+		D[6] = 0; D[7] = cx * cy;                D[8] = -cy * sx;
+	} else if (k == 1) {
+		D[0] = -cz * sy; D[1] = cy * cz * sx; D[2] = cx * cy * cz;
+		D[3] = -sy * sz; D[4] = cy * sx * sz; D[5] = cx * cy * sz;
+		D[6] = -cy;      D[7] = -sx * sy;     D[8] = -cx * sy;
+	} else {
+		D[0] = -cy * sz; D[1] = -cx * cz - sx * sy * sz; D[2] = cz * sx - cx * sy * sz;
+		D[3] = cy * cz;  D[4] = cz * sx * sy - cx * sz;  D[5] = sx * sz + cx * cz * sy;
+		D[6] = 0;        D[7] = 0;                       D[8] = 0;
+	}
+}
+
+__device__ __forceinline__ void euler_M(EulerState &E, const double *ed)
+{
+	const double sy = E.sy, cy = E.cy, sz = E.sz, cz = E.cz, yd = ed[1], zd = ed[2];
+	E.M[0] = cy * cz; E.M[1] = -sz; E.M[2] = 0;
+	E.M[3] = cy * sz; E.M[4] = cz;  E.M[5] = 0;
+	E.M[6] = -sy;     E.M[7] = 0;   E.M[8] = 1;
+	E.Md[0] = -cz * sy * yd - cy * sz * zd; E.Md[1] = -cz * zd; E.Md[2] = 0;
+	E.Md[3] = cy * cz * zd - sy * sz * yd;  E.Md[4] = -sz * zd; E.Md[5] = 0;
+	E.Md[6] = -cy * yd;                     E.Md[7] = 0;        E.Md[8] = 0;
+}
+
+/* dM/d(e_k) (k = 1 pitch, 2 yaw; roll gives 0) -- also equals dMd/d(ed_k) */
+__device__ __forceinline__ void euler_dM(const EulerState &E, int k, double *D)
+{
+	const double sy = E.sy, cy = E.cy, sz = E.sz, cz = E.cz;
+	for (int i = 0; i < 9; ++i) D[i] = 0;
+	if (k == 1) { D[0] = -sy * cz; D[3] = -sy * sz; D[6] = -cy; }
+	else if (k == 2) { D[0] = -cy * sz; D[1] = -cz; D[3] = cy * cz; D[4] = -sz; }
+}
+
+/* dMd/d(e_k) */
+__device__ __forceinline__ void euler_dMd(const EulerState &E, const double *ed, int k, double *D)
+{
+	const double sy = E.sy, cy = E.cy, sz = E.sz, cz = E.cz, yd = ed[1], zd = ed[2];
+	for (int i = 0; i < 9; ++i) D[i] = 0;
+	if (k == 1) { D[0] = -cz * cy * yd + sy * sz * zd; D[3] = -sy * cz * zd - cy * sz * yd; D[6] = sy * yd; }
+	else if (k == 2) { D[0] = sz * sy * yd - cy * cz * zd; D[1] = sz * zd; D[3] = -cy * sz * zd - sy * cz * yd; D[4] = -cz * zd; }
+}
+
+/* ------------------------------------------------------------------ spline sampling */
+
+__device__ __forceinline__ double node_val(const double *x, int v) { return v >= 0 ? x[v] : 0.0; }
+
+/* value of one dimension of a phase-based spline: sum_q w[q] * node(id + q/2, deriv q%2, dim) */
+__device__ __forceinline__ double phase_sample(const DevTables &T, const double *x, int spline, int id, const double *w, int dim)
+{
+	const int16_t *nv = T.node_var + ((size_t)spline * T.max_nodes + id) * 6;
+	return w[0] * node_val(x, nv[dim]) + w[1] * node_val(x, nv[3 + dim]) + w[2] * node_val(x, nv[6 + dim]) + w[3] * node_val(x, nv[9 + dim]);
+}
+
+__device__ __forceinline__ double base_sample(const double *xs /* x + var_off + id*6 */, const double *w, int dim)
+{
+	return w[0] * xs[dim] + w[1] * xs[3 + dim] + w[2] * xs[6 + dim] + w[3] * xs[9 + dim];
+}
+
+struct DynState {
+	double c[3], cdd[3], e[3], ed[3], edd[3];
+	double p[QTOS_NEE][3], f[QTOS_NEE][3];
+	EulerState E;
+	double w[3], wd[3], Iw[9];
+};
+
+__device__ __forceinline__ void dyn_state(const DevTables &T, const DynSample &D, const double *x, DynState &S)
+{
+	const double *bl = x + T.var_off[0] + D.base_id * 6, *ba = x + T.var_off[1] + D.base_id * 6;
+	for (int d = 0; d < 3; ++d) {
+		S.c[d] = base_sample(bl, D.W[0], d); S.cdd[d] = base_sample(bl, D.W[2], d);
+		S.e[d] = base_sample(ba, D.W[0], d); S.ed[d] = base_sample(ba, D.W[1], d); S.edd[d] = base_sample(ba, D.W[2], d);
+	}
+	for (int i = 0; i < QTOS_NEE; ++i)
+		for (int d = 0; d < 3; ++d) {
+			S.p[i][d] = phase_sample(T, x, 2 + i, D.mo_id[i], D.mo_w[i], d);
+			S.f[i][d] = phase_sample(T, x, 6 + i, D.fo_id[i], D.fo_w[i], d);
+		}
+	euler_R(S.E, S.e); euler_M(S.E, S.ed);
+	mat3_vec(S.E.M, S.ed, S.w);
+	double a[3], b[3];
+	mat3_vec(S.E.Md, S.ed, a); mat3_vec(S.E.M, S.edd, b);
+	for (int d = 0; d < 3; ++d) S.wd[d] = a[d] + b[d];
+	/* I_w = R I_b R' */
+	double RI[9];
+	for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j)
+		RI[3 * i + j] = S.E.R[3 * i] * T.Ib[j] + S.E.R[3 * i + 1] * T.Ib[3 + j] + S.E.R[3 * i + 2] * T.Ib[6 + j];
+	for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j)
+		S.Iw[3 * i + j] = RI[3 * i] * S.E.R[3 * j] + RI[3 * i + 1] * S.E.R[3 * j + 1] + RI[3 * i + 2] * S.E.R[3 * j + 2];
+}
+
+/* 6 rows [AX AY AZ LX LY LZ] (ref: single_rigid_body_dynamics.cc:76-103) */
+__device__ __forceinline__ void dyn_rows(const DevTables &T, const DynState &S, double *g6)
+{
+	double Iwd[3], Iww[3], gyro[3], tau[3] = {0, 0, 0}, fs[3] = {0, 0, 0};
+	mat3_vec(S.Iw, S.wd, Iwd); mat3_vec(S.Iw, S.w, Iww); cross3(S.w, Iww, gyro);
+	for (int i = 0; i < QTOS_NEE; ++i) {
+		double r[3] = {S.c[0] - S.p[i][0], S.c[1] - S.p[i][1], S.c[2] - S.p[i][2]}, t[3];
+		cross3(S.f[i], r, t);
+		for (int d = 0; d < 3; ++d) { tau[d] += t[d]; fs[d] += S.f[i][d]; }
+	}
+	for (int d = 0; d < 3; ++d) g6[d] = Iwd[d] + gyro[d] - tau[d];
+	g6[3] = T.mass * S.cdd[0] - fs[0];
+	g6[4] = T.mass * S.cdd[1] - fs[1];
+	g6[5] = T.mass * S.cdd[2] - fs[2] - (-T.mass * T.grav);
+}
+
+/* one column of d(angular rows)/d(.) given the variation of R, omega and omega_dot */
+__device__ __forceinline__ void ang_column(const DevTables &T, const DynState &S, const double *dR /* nullable */,
+                                           const double *dw, const double *dwd, const double *Ibu, const double *Ibh,
+                                           const double *Iww, double *col)
+{
+	double a[3], b[3] = {0, 0, 0}, t[3], q[3];
+	mat3_vec(S.Iw, dwd, a);                         /* I_w d(wd) */
+	mat3_vec(S.Iw, dw, t);                          /* I_w d(w) */
+	for (int d = 0; d < 3; ++d) b[d] = t[d];
+	if (dR) {
+		mat3_vec(dR, Ibu, t); for (int d = 0; d < 3; ++d) a[d] += t[d];        /* dR I_b R' wd */
+		mat3T_vec(dR, S.wd, t); mat3_vec(T.Ib, t, q);                          /* R I_b dR' wd */
+		mat3_vec(S.E.R, q, t); for (int d = 0; d < 3; ++d) a[d] += t[d];
+		mat3_vec(dR, Ibh, t); for (int d = 0; d < 3; ++d) b[d] += t[d];        /* dR I_b R' w */
+		mat3T_vec(dR, S.w, t); mat3_vec(T.Ib, t, q);
+		mat3_vec(S.E.R, q, t); for (int d = 0; d < 3; ++d) b[d] += t[d];
+	}
+	cross3(S.w, b, t);
+	cross3(dw, Iww, q);
+	for (int d = 0; d < 3; ++d) col[d] = a[d] + t[d] + q[d];
+}
+
+/* dense column-major element block of one dynamics sample; sc6 = row scales */
+__device__ __forceinline__ void dyn_jac(const DevTables &T, const DynSample &D, const DynState &S, const double *sc6, double *blk, int ncols)
+{
+	for (int i = 0; i < 6 * ncols; ++i) blk[i] = 0.0;
+	/* angular rows wrt Euler angle / rate / acceleration */
+	double Gp[9], Gv[9], Ga[9];    /* [r*3+k] */
+	{
+		double u[3], h[3], Ibu[3], Ibh[3], Iww[3], zero[3] = {0, 0, 0};
+		mat3T_vec(S.E.R, S.wd, u); mat3T_vec(S.E.R, S.w, h);
+		mat3_vec(T.Ib, u, Ibu); mat3_vec(T.Ib, h, Ibh); mat3_vec(S.Iw, S.w, Iww);
+		for (int k = 0; k < 3; ++k) {
+			double dR[9], dM[9], dMd[9], dw[3], dwd[3], t1[3], t2[3], col[3];
+			euler_dR(S.E, k, dR); euler_dM(S.E, k, dM); euler_dMd(S.E, S.ed, k, dMd);
+			mat3_vec(dM, S.ed, dw);
+			mat3_vec(dMd, S.ed, t1); mat3_vec(dM, S.edd, t2);
+			for (int d = 0; d < 3; ++d) dwd[d] = t1[d] + t2[d];
+			ang_column(T, S, dR, dw, dwd, Ibu, Ibh, Iww, col);
+			for (int r = 0; r < 3; ++r) Gp[3 * r + k] = col[r];
+			/* rate: dw = M[:,k], dwd = Md[:,k] + dM_k ed */
+			for (int d = 0; d < 3; ++d) { dw[d] = S.E.M[3 * d + k]; dwd[d] = S.E.Md[3 * d + k] + (dM[3 * d] * S.ed[0] + dM[3 * d + 1] * S.ed[1] + dM[3 * d + 2] * S.ed[2]); }
+			ang_column(T, S, nullptr, dw, dwd, Ibu, Ibh, Iww, col);
+			for (int r = 0; r < 3; ++r) Gv[3 * r + k] = col[r];
+			for (int d = 0; d < 3; ++d) dwd[d] = S.E.M[3 * d + k];
+			ang_column(T, S, nullptr, zero, dwd, Ibu, Ibh, Iww, col);
+			for (int r = 0; r < 3; ++r) Ga[3 * r + k] = col[r];
+		}
+	}
+	double F[3] = {0, 0, 0};
+	for (int i = 0; i < QTOS_NEE; ++i) for (int d = 0; d < 3; ++d) F[d] += S.f[i][d];
+	/* Cross(v)[r][k] */
+#define QX(v, r, k) ((r) == (k) ? 0.0 : (((k) - (r) + 3) % 3 == 1 ? -(v)[3 - (r) - (k)] : (v)[3 - (r) - (k)]))
+	for (int q = 0; q < 4; ++q)                 /* q = side*2 + deriv */
+		for (int k = 0; k < 3; ++k) {
+			const int canon = (q >> 1) * 6 + (q & 1) * 3 + k;
+			int sl = D.slot[canon];
+			if (sl >= 0) {                         /* base-lin */
+				double *c = blk + 6 * sl;
+				for (int r = 0; r < 3; ++r) if (r != k) c[r] += sc6[r] * (-QX(F, r, k) * D.W[0][q]);
+				c[3 + k] += sc6[3 + k] * T.mass * D.W[2][q];
+			}
+			sl = D.slot[12 + canon];
+			if (sl >= 0) {                         /* base-ang */
+				double *c = blk + 6 * sl;
+				for (int r = 0; r < 3; ++r) c[r] += sc6[r] * (Gp[3 * r + k] * D.W[0][q] + Gv[3 * r + k] * D.W[1][q] + Ga[3 * r + k] * D.W[2][q]);
+			}
+			for (int i = 0; i < QTOS_NEE; ++i) {
+				sl = D.slot[24 + i * 24 + canon];
+				if (sl >= 0) {                     /* foot position */
+					double *c = blk + 6 * sl;
+					for (int r = 0; r < 3; ++r) if (r != k) c[r] += sc6[r] * QX(S.f[i], r, k) * D.mo_w[i][q];
+				}
+				sl = D.slot[24 + i * 24 + 12 + canon];
+				if (sl >= 0) {                     /* force */
+					double *c = blk + 6 * sl;
+					const double rr[3] = {S.c[0] - S.p[i][0], S.c[1] - S.p[i][1], S.c[2] - S.p[i][2]};
+					for (int r = 0; r < 3; ++r) if (r != k) c[r] += sc6[r] * QX(rr, r, k) * D.fo_w[i][q];
+					c[3 + k] += sc6[3 + k] * (-D.fo_w[i][q]);
+				}
+			}
+		}
+#undef QX
+}
+
+struct RomState { double c[3], e[3], p[3]; EulerState E; };
+
+__device__ __forceinline__ void rom_state(const DevTables &T, const RomSample &R, const double *x, RomState &S)
+{
+	const double *bl = x + T.var_off[0] + R.base_id * 6, *ba = x + T.var_off[1] + R.base_id * 6;
+	for (int d = 0; d < 3; ++d) {
+		S.c[d] = base_sample(bl, R.wp, d); S.e[d] = base_sample(ba, R.wp, d);
+		S.p[d] = phase_sample(T, x, 2 + R.ee, R.mo_id, R.mo_w, d);
+	}
+	euler_R(S.E, S.e);
+}
+
+__device__ __forceinline__ void rom_rows(const RomState &S, double *g3)
+{
+	const double r[3] = {S.p[0] - S.c[0], S.p[1] - S.c[1], S.p[2] - S.c[2]};
+	mat3T_vec(S.E.R, r, g3);
+}
+
+__device__ __forceinline__ void rom_jac(const RomSample &R, const RomState &S, const double *sc3, double *blk, int ncols)
+{
+	for (int i = 0; i < 3 * ncols; ++i) blk[i] = 0.0;
+	const double rW[3] = {S.p[0] - S.c[0], S.p[1] - S.c[1], S.p[2] - S.c[2]};
+	double Gp[9];
+	for (int k = 0; k < 3; ++k) {
+		double dR[9], col[3];
+		euler_dR(S.E, k, dR); mat3T_vec(dR, rW, col);
+		for (int r = 0; r < 3; ++r) Gp[3 * r + k] = col[r];
+	}
+	for (int q = 0; q < 4; ++q)
+		for (int k = 0; k < 3; ++k) {
+			const int canon = (q >> 1) * 6 + (q & 1) * 3 + k;
+			int sl = R.slot[canon];
+			if (sl >= 0) { double *c = blk + 3 * sl; for (int r = 0; r < 3; ++r) c[r] += sc3[r] * (-S.E.R[3 * k + r] * R.wp[q]); }
+			sl = R.slot[12 + canon];
+			if (sl >= 0) { double *c = blk + 3 * sl; for (int r = 0; r < 3; ++r) c[r] += sc3[r] * Gp[3 * r + k] * R.wp[q]; }
+			sl = R.slot[24 + canon];
+			if (sl >= 0) { double *c = blk + 3 * sl; for (int r = 0; r < 3; ++r) c[r] += sc3[r] * S.E.R[3 * k + r] * R.mo_w[q]; }
+		}
+}
+
+/* all constraint values g(x) (unscaled), block-cooperative; no sync inside */
+__device__ __forceinline__ void eval_g_block(const DevTables &T, const DevHeightfield &hf, const double *x, double *g)
+{
+	const int n_tasks = T.n_dyn + T.n_rom4 + T.n_lin + T.n_ter;
+	for (int t = threadIdx.x; t < n_tasks; t += blockDim.x) {
+		int k = t;
+		if (k < T.n_dyn) {
+			const DynSample &D = T.dyn[k];
+			DynState S; dyn_state(T, D, x, S);
+			double g6[6]; dyn_rows(T, S, g6);
+			const int r0 = T.elems[D.elem].row0;
+			for (int r = 0; r < 6; ++r) g[r0 + r] = g6[r];
+			continue;
+		}
+		k -= T.n_dyn;
+		if (k < T.n_rom4) {
+			const RomSample &R = T.rom[k];
+			RomState S; rom_state(T, R, x, S);
+			double g3[3]; rom_rows(S, g3);
+			const int r0 = T.elems[R.elem].row0;
+			for (int r = 0; r < 3; ++r) g[r0 + r] = g3[r];
+			continue;
+		}
+		k -= T.n_rom4;
+		if (k < T.n_lin) {
+			double s = 0.0;
+			for (int a = T.lin_ptr[k]; a < T.lin_ptr[k + 1]; ++a) s += T.lin_val[a] * x[T.lin_col[a]];
+			g[T.lin_row[k]] = s;
+			continue;
+		}
+		k -= T.n_lin;
+		{
+			const int16_t *v = T.ter_var + 3 * k;
+			g[T.ter_row[k]] = x[v[2]] - qtos_height(hf, x[v[0]], x[v[1]]);
+		}
+	}
+}
+
+/* dynamics + range-of-motion element blocks at x, scaled by sc; block-cooperative */
+__device__ __forceinline__ void eval_jac_block(const DevTables &T, const double *x, const double *sc, double *Jv)
+{
+	const int n_tasks = T.n_dyn + T.n_rom4;
+	for (int t = threadIdx.x; t < n_tasks; t += blockDim.x) {
+		if (t < T.n_dyn) {
+			const DynSample &D = T.dyn[t];
+			const Element &E = T.elems[D.elem];
+			DynState S; dyn_state(T, D, x, S);
+			dyn_jac(T, D, S, sc + E.row0, Jv + E.valoff, E.ncols);
+		} else {
+			const RomSample &R = T.rom[t - T.n_dyn];
+			const Element &E = T.elems[R.elem];
+			RomState S; rom_state(T, R, x, S);
+			rom_jac(R, S, sc + E.row0, Jv + E.valoff, E.ncols);
+		}
+	}
+}
+
+#endif

@@ -1,0 +1,108 @@
+/*
+ * qtos_tables.h -- static per-shape tables produced by the host problem compiler
+ * (qtos_compile.cpp) and consumed by the device kernels (qtos_kernels.cu).
+ *
+ * A "shape" is (gait combo, horizon, Parameters, model constants).  Because the reference
+ * never optimises phase durations on this path (ref: solver/towr/src/main.cpp:441 commented,
+ * parameters.cc IsOptimizeTimings() false) every spline sample time maps to a FIXED polynomial
+ * and fixed Hermite weights, so the whole index structure of the NLP is compiled once per shape
+ * and shared by every problem of a batch; only start/goal/feet/heightfield vary per problem.
+ */
+#ifndef QTOS_TABLES_H_
+#define QTOS_TABLES_H_
+
+#include <cstdint>
+#include <vector>
+#include "../../include/qtos_b200.h"
+
+#define QTOS_NB 16                 /* block size of the block-skyline KKT storage */
+#define QTOS_DYN_CANON 120         /* canonical local columns of a dynamics element */
+#define QTOS_ROM_CANON 36          /* canonical local columns of a range-of-motion element */
+#define QTOS_NPARAM 28             /* per-problem parameter vector, see QP_* */
+
+/* layout of the per-problem parameter vector P[] used for x0 / fixed variables */
+enum { QP_START_POS = 0, QP_START_ANG = 3, QP_START_VEL = 6, QP_START_ANGVEL = 9, QP_GOAL = 12,
+       QP_EE = 15, QP_ZERO = 27 };
+
+enum { ROW_EQ = 1, ROW_HASL = 2, ROW_HASU = 4 };
+enum { EL_DYN = 0, EL_ROM = 1, EL_CONST = 2 };
+
+struct DynSample {                 /* one dynamics sample time (6 rows) */
+	int    base_id;                /* base polynomial (nodes base_id, base_id+1) */
+	double W[3][4];                /* d{p,v,a}/d{p0,v0,p1,v1} of the base polynomial at the sample */
+	int    mo_id[QTOS_NEE];        /* foot-motion polynomial */
+	double mo_w[QTOS_NEE][4];      /* position weights */
+	int    fo_id[QTOS_NEE];        /* force polynomial */
+	double fo_w[QTOS_NEE][4];
+	int    elem;
+	int8_t slot[QTOS_DYN_CANON];   /* canonical column -> dense column of the element, -1 = absent */
+};
+
+struct RomSample {                 /* one (foot, time) range-of-motion sample (3 rows) */
+	int    base_id;
+	double wp[4];
+	int    ee;
+	int    mo_id;
+	double mo_w[4];
+	int    elem;
+	int8_t slot[QTOS_ROM_CANON];
+};
+
+struct Element {                   /* dense Jacobian block: rows [row0,row0+nrows) x cols[coloff..+ncols) */
+	int row0, nrows, ncols, valoff, coloff, type;
+};
+
+struct HostTables {
+	qtos_shape shape;
+	/* dimensions */
+	int n_all = 0, n_free = 0, npad = 0, m = 0, n_eq = 0, n_ineq = 0, n_bounds = 0;
+	int n_dyn = 0, n_rom = 0;
+	int nJ = 0, nb = 0, nM = 0, nnz_jac = 0;
+	int csv_rows = 0;
+	double T = 0;
+	double flops_factor = 0;
+	int max_nodes = 0;             /* leading dimension of node_var */
+	int n_nodes[10] = {0}, n_polys[10] = {0}, var_off[11] = {0};
+	int row_off[20] = {0};
+	/* splines: 0 base-lin, 1 base-ang, 2..5 foot motion, 6..9 foot force */
+	std::vector<double> dur[10];
+	std::vector<int16_t> node_var;          /* [10][max_nodes][6] full variable index or -1 */
+	/* variables */
+	std::vector<uint8_t> x0_spline, x0_deriv, x0_dim;   /* [n_all] */
+	std::vector<int16_t> x0_node;                        /* node whose interpolated value wins */
+	std::vector<int8_t>  fix_src;                        /* [n_all] index into P[] or -1 if free */
+	std::vector<int16_t> perm_of_var;                    /* [n_all] permuted free index or -1 */
+	std::vector<int16_t> var_of_perm;                    /* [npad] full index or -1 (padding) */
+	/* rows */
+	std::vector<uint8_t> row_flags;                      /* [m] */
+	std::vector<double>  gl, gu;                         /* [m] */
+	std::vector<int>     row_elem;                       /* [m] */
+	/* elements */
+	std::vector<Element> elems;
+	std::vector<int16_t> elem_cols;                      /* permuted free indices */
+	std::vector<double>  Jconst;                         /* [nJ] unscaled values of constant elements */
+	/* evaluation */
+	std::vector<DynSample> dyn;
+	std::vector<RomSample> rom;
+	std::vector<int>     lin_row, lin_ptr;               /* linear rows: g = sum val * x[col] */
+	std::vector<int16_t> lin_col;
+	std::vector<double>  lin_val;
+	std::vector<int>     ter_row;                        /* terrain rows: g = x[vz] - h(x[vx], x[vy]) */
+	std::vector<int16_t> ter_var;                        /* [n_ter][3] */
+	/* condensed KKT structure */
+	std::vector<int>     fb, blkptr;                     /* [nb], [nb+1] (in blocks) */
+	std::vector<int>     diag_off;                       /* [npad] offset of (i,i) in M */
+	std::vector<int>     asm_ptr, asm_off;               /* targets */
+	std::vector<uint32_t> asm_terms;                     /* e<<16 | a<<8 | b */
+	std::vector<int>     jt_ptr;                         /* [npad+1] */
+	std::vector<uint32_t> jt_terms;                      /* e<<8 | a */
+	/* 1 kHz sampler */
+	std::vector<double>  csv_t;                          /* [csv_rows] accumulated sample times */
+	std::vector<uint8_t> csv_id;                         /* [csv_rows][10] */
+	std::vector<double>  csv_tl;                         /* [csv_rows][10] */
+};
+
+/* returns 0 or QTOS_ESHAPE; err receives a message */
+int qtos_compile_shape(const qtos_shape *shape, HostTables *out, char *err, int errlen);
+
+#endif
