@@ -75,6 +75,8 @@ typedef struct {
 	double mu_init;                   /* 0.1 */
 	double sigma_w;                   /* Hessian model sigma_w * I */
 	double delta_c;                   /* equality-block regularisation */
+	int    feas_exit;                 /* 1: f == 0 on this path, so any point with violation <= constr_viol_tol is
+	                                     optimal with zero multipliers and terminates the solve (default) */
 } qtos_options;
 
 typedef struct {
@@ -136,9 +138,17 @@ int  qtos_sample_csv(qtos_ctx *ctx, const qtos_problem *p, int n, const double *
 /* write one trajectory as the reference's traj.csv text ("%g", comma separated) */
 int  qtos_write_csv(const double *rows, int n_rows, const char *path);
 
-/* instrumentation: kernel launches issued by this context, and device time of the last solve per phase */
-long long qtos_launch_count(const qtos_ctx *ctx);
-int  qtos_last_timing(const qtos_ctx *ctx, float *ms_phase /*8*/, int *iters_total);
+/* instrumentation.  With profiling on, CUDA events are recorded between the kernels of every iteration
+ * on the context's stream (no extra synchronisation) and resolved when the solve ends. */
+typedef struct {
+	float ms[8];                      /* device time of the last solve: init, jac, prepare, assemble, factor, step, 0, 0 */
+	long long factorizations;         /* problems factored, summed over the iterations of the last solve */
+	long long factor_launches;        /* k_factor launches of the last solve */
+	int iterations;                   /* batch iterations of the last solve */
+} qtos_stats;
+long long qtos_launch_count(const qtos_ctx *ctx);  /* kernel launches issued by this context so far */
+int  qtos_set_profiling(qtos_ctx *ctx, int on);
+int  qtos_last_stats(const qtos_ctx *ctx, qtos_stats *st);
 void *qtos_stream(const qtos_ctx *ctx);            /* cudaStream_t the context launches on */
 /* FP64 FMA throughput of the device measured with a register-resident FMA loop, TFLOP/s */
 int  qtos_measure_fp64_peak(qtos_ctx *ctx, double *tflops);

@@ -43,7 +43,7 @@ class IpmOptions(C.Structure):
     _fields_ = [("tol", C.c_double), ("constr_viol_tol", C.c_double),
                 ("compl_inf_tol", C.c_double), ("dual_inf_tol", C.c_double),
                 ("max_iter", C.c_int), ("mu_init", C.c_double), ("mu_strategy", C.c_int),
-                ("sigma_w", C.c_double), ("verbose", C.c_int), ("delta_c", C.c_double)]
+                ("sigma_w", C.c_double), ("verbose", C.c_int), ("delta_c", C.c_double), ("feas_exit", C.c_int)]
 
 
 class IpmResult(C.Structure):

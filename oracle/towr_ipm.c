@@ -46,6 +46,7 @@ void orc_ipm_default_options(orc_ipm_options *o)
 	o->sigma_w = 0.1;
 	o->verbose = 0;
 	o->delta_c = 1e-5;
+	o->feas_exit = 1;
 }
 
 /* ---------------------------------------------------------------- structure */
@@ -279,7 +280,7 @@ int orc_ipm_solve(orc_problem *p, const orc_ipm_options *o, double *x, orc_ipm_r
 	const double rho = 1.0 / o->delta_c, sigma = o->sigma_w;
 	const double kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5;
 	const double mu_min = dmin(o->tol, o->compl_inf_tol) / (kappa_eps + 1.0);
-	int status = -1, it = 0;
+	int status = -1, it = 0, nfail = 0;
 
 	for (it = 0; ; ++it) {
 		GATHER_J();
@@ -306,7 +307,10 @@ int orc_ipm_solve(orc_problem *p, const orc_ipm_options *o, double *x, orc_ipm_r
 		res->constr_viol = viol; res->dual_inf = dual_inf; res->compl_inf = compl0; res->nlp_error = E0; res->mu = mu;
 		if (o->verbose)
 			printf("%3d inf_pr=%9.3e inf_du=%9.3e lg(mu)=%5.1f viol=%9.3e E0=%9.3e", it, theta_inf, dual_inf, log10(mu), viol, E0);
-		if (E0 <= o->tol && viol <= o->constr_viol_tol && compl0 <= o->compl_inf_tol && dual_inf <= o->dual_inf_tol) {
+		/* f == 0 on this path (ref: src/parameters.cc:62-63): every feasible point is a KKT point with
+		 * zero multipliers, so E0 evaluated at (x, y=0, z=0) is just the primal infeasibility */
+		const int feas = o->feas_exit && viol <= o->constr_viol_tol && theta_inf <= o->tol;
+		if (feas || (E0 <= o->tol && viol <= o->constr_viol_tol && compl0 <= o->compl_inf_tol && dual_inf <= o->dual_inf_tol)) {
 			status = 0; if (o->verbose) printf("\n"); break;
 		}
 		if (it >= o->max_iter) { if (o->verbose) printf("\n"); break; }
@@ -406,6 +410,7 @@ int orc_ipm_solve(orc_problem *p, const orc_ipm_options *o, double *x, orc_ipm_r
 			alpha *= 0.5;
 		}
 		if (o->verbose) printf(" |dx|=%8.2e a_pr=%8.2e a_du=%8.2e ls=%d nu=%8.2e\n", dxmax, alpha, a_du, ls, nu);
+		nfail = ls >= 12 ? nfail + 1 : 0;
 		if (it < 256) { res->tr_dnorm[it] = dxmax; res->tr_alpha_pr[it] = alpha; res->tr_alpha_du[it] = a_du; res->tr_ls[it] = ls; }
 		memcpy(x, xt, sizeof(double) * na);
 		for (int i = 0; i < m; ++i) {
@@ -422,6 +427,7 @@ int orc_ipm_solve(orc_problem *p, const orc_ipm_options *o, double *x, orc_ipm_r
 				zU[i] = dmin(dmax(zU[i] + a_du * dzU[i], mu / (1e10 * su)), 1e10 * mu / su);
 			}
 		}
+		if (nfail >= 3) { status = -2; break; }      /* line search stalled three times in a row */
 	}
 	res->status = status; res->iters = it;
 	(void)n_eq; (void)n_iq;

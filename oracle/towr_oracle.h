@@ -136,6 +136,7 @@ typedef struct {
 	double sigma_w;           /* W = sigma_w * I */
 	int    verbose;
 	double delta_c;           /* equality-block regularisation (condensed as Jc'Jc/delta_c) */
+	int    feas_exit;         /* f == 0: accept any point with viol <= constr_viol_tol (zero multipliers are optimal) */
 } orc_ipm_options;
 
 typedef struct {

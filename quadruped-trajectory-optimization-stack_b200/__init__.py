@@ -65,7 +65,7 @@ class Shape(C.Structure):
 class Options(C.Structure):
     _fields_ = [("tol", C.c_double), ("constr_viol_tol", C.c_double), ("compl_inf_tol", C.c_double),
                 ("dual_inf_tol", C.c_double), ("max_iter", C.c_int), ("mu_init", C.c_double),
-                ("sigma_w", C.c_double), ("delta_c", C.c_double)]
+                ("sigma_w", C.c_double), ("delta_c", C.c_double), ("feas_exit", C.c_int)]
 
 
 class Dims(C.Structure):
@@ -73,6 +73,11 @@ class Dims(C.Structure):
                 ("n_ineq", C.c_int), ("nnz_jac", C.c_int), ("csv_rows", C.c_int),
                 ("kkt_order", C.c_int), ("kkt_block", C.c_int), ("kkt_blocks", C.c_int),
                 ("flops_factor", C.c_double), ("workspace_bytes_per_problem", C.c_longlong)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("ms", C.c_float * 8), ("factorizations", C.c_longlong), ("factor_launches", C.c_longlong),
+                ("iterations", C.c_int)]
 
 
 # numpy mirrors of qtos_problem / qtos_result (C layout, checked against ctypes sizes below)
@@ -86,7 +91,8 @@ assert PROBLEM_DTYPE.itemsize == 8 * 28 + 8 and RESULT_DTYPE.itemsize == 56
 EXPORTS = ["qtos_default_shape", "qtos_default_options", "qtos_create", "qtos_destroy", "qtos_last_error",
            "qtos_get_dims", "qtos_upload_heightfield", "qtos_heightfield_query", "qtos_heightfield_cells",
            "qtos_get_initial", "qtos_eval", "qtos_solve_batch", "qtos_solve_batch_device", "qtos_sample_csv",
-           "qtos_write_csv", "qtos_launch_count", "qtos_last_timing", "qtos_stream", "qtos_measure_fp64_peak"]
+           "qtos_write_csv", "qtos_launch_count", "qtos_set_profiling", "qtos_last_stats", "qtos_stream",
+           "qtos_measure_fp64_peak"]
 
 _LIB = None
 
@@ -116,7 +122,8 @@ def lib():
         L.qtos_write_csv.argtypes = [dp, C.c_int, C.c_char_p]
         L.qtos_launch_count.argtypes = [vp]
         L.qtos_launch_count.restype = C.c_longlong
-        L.qtos_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.qtos_set_profiling.argtypes = [vp, C.c_int]
+        L.qtos_last_stats.argtypes = [vp, C.POINTER(Stats)]
         L.qtos_stream.argtypes = [vp]
         L.qtos_stream.restype = vp
         L.qtos_measure_fp64_peak.argtypes = [vp, dp]
@@ -266,12 +273,16 @@ class Solver:
     def launch_count(self):
         return int(self._L.qtos_launch_count(self._h))
 
-    def last_timing(self):
-        ms = (C.c_float * 8)()
-        it = C.c_int()
-        self._L.qtos_last_timing(self._h, ms, C.byref(it))
+    def set_profiling(self, on=True):
+        self._ck(self._L.qtos_set_profiling(self._h, int(bool(on))))
+
+    def last_stats(self):
+        """device ms per phase of the last solve (profiling on), problems factored, iterations."""
+        st = Stats()
+        self._L.qtos_last_stats(self._h, C.byref(st))
         names = ["init", "jac", "prepare", "assemble", "factor", "step"]
-        return dict(zip(names, list(ms)[:6])), it.value
+        return {"ms": dict(zip(names, list(st.ms)[:6])), "factorizations": st.factorizations,
+                "factor_launches": st.factor_launches, "iterations": st.iterations}
 
     def fp64_peak_tflops(self):
         v = C.c_double()

@@ -59,7 +59,7 @@ struct DevWork {
 	int *n_running;                         /* single counter */
 };
 
-enum { SC_MU = 0, SC_NU, SC_SD, SC_SC, SC_DUAL, SC_THETA, SC_COMPL, SC_VIOL, SC_E0, SC_N };
+enum { SC_MU = 0, SC_NU, SC_SD, SC_SC, SC_DUAL, SC_THETA, SC_COMPL, SC_VIOL, SC_E0, SC_NFAIL, SC_N };
 
 /* ------------------------------------------------------------------ heightfield */
 

@@ -139,7 +139,7 @@ k_init(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *
 	}
 	if (threadIdx.x == 0) {
 		double *scal = WS(scal, 16);
-		scal[SC_MU] = opt.mu_init; scal[SC_NU] = 1.0;
+		scal[SC_MU] = opt.mu_init; scal[SC_NU] = 1.0; scal[SC_NFAIL] = 0.0;
 		W.status[pid] = QTOS_RUNNING; W.iters[pid] = 0; W.flags[pid] = 0;
 	}
 }
@@ -197,7 +197,9 @@ k_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 	const double s_c = fmax(100.0, v[5] / (double)(T.n_bounds > 0 ? T.n_bounds : 1)) / 100.0;
 	const double E0 = fmax(fmax(dual_inf / s_d, theta_inf), cmax / s_c);
 	double mu = scal[SC_MU];
-	const bool conv = E0 <= opt.tol && v[6] <= opt.constr_viol_tol && cmax <= opt.compl_inf_tol && dual_inf <= opt.dual_inf_tol;
+	/* f == 0 on this path (ref: parameters.cc:62-63): a feasible point is a KKT point with zero multipliers */
+	const bool feas = opt.feas_exit && v[6] <= opt.constr_viol_tol && theta_inf <= opt.tol;
+	const bool conv = feas || (E0 <= opt.tol && v[6] <= opt.constr_viol_tol && cmax <= opt.compl_inf_tol && dual_inf <= opt.dual_inf_tol);
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		scal[SC_DUAL] = dual_inf; scal[SC_THETA] = theta_inf; scal[SC_COMPL] = cmax; scal[SC_VIOL] = v[6]; scal[SC_E0] = E0;
@@ -489,7 +491,12 @@ k_step(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *
 		if (fl & ROW_HASL) { const double sl = st[i] - dLb[i]; zL[i] = fmin(fmax(zL[i] + a_du * dzL[i], mu / (1e10 * sl)), 1e10 * mu / sl); }
 		if (fl & ROW_HASU) { const double su = dUb[i] - st[i]; zU[i] = fmin(fmax(zU[i] + a_du * dzU[i], mu / (1e10 * su)), 1e10 * mu / su); }
 	}
-	if (tid == 0) { scal[SC_NU] = nu; if (ls >= 12) W.flags[pid] |= 2; }
+	if (tid == 0) {
+		scal[SC_NU] = nu;
+		const double nfail = ls >= 12 ? scal[SC_NFAIL] + 1.0 : 0.0;
+		scal[SC_NFAIL] = nfail;
+		if (nfail >= 3.0) { W.status[pid] = QTOS_STEP_FAILED; atomicSub(W.n_running, 1); }   /* line search stalled */
+	}
 }
 
 /* ------------------------------------------------------------------ results, sampler, queries */

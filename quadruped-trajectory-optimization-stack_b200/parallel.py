@@ -1,0 +1,52 @@
+"""Multi-GPU plumbing: one process per GPU, independent solves sharded statically, and ONE
+all-gather of small per-candidate records where candidates compete (multi-start goals of the same
+window).  torch.distributed is used for the rendezvous/collective only (NCCL on GPUs, gloo on CPU).
+
+The reference has no collective at all: it fans solves out over 32 OS processes
+(ref: QTOS/generateHeightField.py:18,344-404) and never compares plans; best-plan selection is the
+exchange step BASELINE.json's north_star introduces.  Key = (not converged, cost, violation, global id),
+lexicographic, so the winner is identical on every rank and for every GPU count."""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_total, rank, world):
+    """interleaved static shard: candidate c lives on rank c % world (groups of consecutive
+    candidates are spread evenly over the ranks)."""
+    return np.arange(rank, n_total, world, dtype=np.int64)
+
+
+def make_records(results, global_idx, groups):
+    """float64 [n, 5] = (group, not_converged, cost, violation, global id)"""
+    rec = np.empty((len(results), 5), dtype=np.float64)
+    rec[:, 0] = groups
+    rec[:, 1] = (results["status"] != 0).astype(np.float64)
+    rec[:, 2] = results["cost"]
+    rec[:, 3] = results["constr_viol"]
+    rec[:, 4] = global_idx
+    return rec
+
+
+def argmin_per_group(rec):
+    """rec [n, 5] (any order) -> {group: winning global id}; deterministic lexicographic key."""
+    order = np.lexsort((rec[:, 4], rec[:, 3], rec[:, 2], rec[:, 1], rec[:, 0]))
+    srt = rec[order]
+    first = np.ones(len(srt), dtype=bool)
+    first[1:] = srt[1:, 0] != srt[:-1, 0]
+    return {int(g): int(i) for g, i in zip(srt[first, 0], srt[first, 4])}
+
+
+def select_best(rec_local, device=None):
+    """all-gather the records of every rank (equal counts per rank) and pick the winner of each group
+    on every rank identically.  Returns (winners dict, gathered records)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return argmin_per_group(rec_local), rec_local
+    world = dist.get_world_size()
+    t = torch.from_numpy(np.ascontiguousarray(rec_local))
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty((world * t.shape[0], t.shape[1]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t)
+    allrec = out.cpu().numpy()
+    return argmin_per_group(allrec), allrec

@@ -1,0 +1,56 @@
+"""CPU tier: the N>1 host path (static sharding + best-plan all-gather) on gloo, world_size 2."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import qtos_b200 as Q
+from qtos_b200 import parallel
+
+
+def _fake_results(n, seed):
+    rng = np.random.default_rng(seed)
+    r = np.zeros(n, dtype=Q.RESULT_DTYPE)
+    r["status"] = np.where(rng.uniform(size=n) < 0.2, -1, 0)
+    r["cost"] = np.round(rng.uniform(1, 2, n), 3)          # ties on purpose
+    r["constr_viol"] = rng.uniform(0, 1e-4, n)
+    return r
+
+
+def _worker(rank, world, port, n_total, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    allres = _fake_results(n_total, 7)                      # what a single process would have computed
+    idx = parallel.shard_indices(n_total, rank, world)
+    rec = parallel.make_records(allres[idx], idx, idx // 8)
+    winners, gathered = parallel.select_best(rec)
+    out[rank] = (winners, len(gathered))
+    dist.destroy_process_group()
+
+
+def test_shard_and_select_best_world2():
+    n_total = 64
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager(); out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, n_total, out), nprocs=2, join=True)
+    allres = _fake_results(n_total, 7)
+    want = parallel.argmin_per_group(parallel.make_records(allres, np.arange(n_total), np.arange(n_total) // 8))
+    assert out[0][0] == want and out[1][0] == want and out[0][1] == n_total
+    # winners are converged whenever the group has a converged candidate, and minimal in cost among them
+    for g, w in want.items():
+        members = np.arange(8 * g, 8 * g + 8)
+        conv = members[allres["status"][members] == 0]
+        if len(conv):
+            assert allres["status"][w] == 0 and allres["cost"][w] == allres["cost"][conv].min()
+
+
+def test_shards_partition_the_batch():
+    for world in (1, 2, 4, 8):
+        parts = [parallel.shard_indices(4096 * world, r, world) for r in range(world)]
+        assert all(len(p) == 4096 for p in parts)
+        assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(4096 * world))
+        for p in parts:                                      # every group of 8 candidates is split evenly
+            assert np.all(np.bincount(p // 8) == 8 // world if world <= 8 else True)

@@ -1,0 +1,218 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on identical inputs.
+
+Tolerances (north_star): constraint violation <= 1e-4; CoM / foot trajectories within 1 mm of the oracle
+running the same algorithm; heightfield heights and cell indices bit-exact; g and J to round-off
+(1e-10 absolute on values of order 1e0..1e3)."""
+import os
+
+import numpy as np
+import pytest
+
+import qtos_b200 as Q
+from qtos_b200 import heightfield as HF
+from qtos_b200 import towr_cli, workloads
+from conftest import oracle_problem, FEET_19
+
+pytestmark = pytest.mark.gpu
+
+G_TOL = 1e-10
+J_TOL = 1e-10
+TRAJ_TOL_M = 1e-3
+
+
+@pytest.fixture(scope="module")
+def solvers():
+    S = {"S2": Q.Solver(Q.default_shape("C1", 2.0), max_batch=256), "S5": Q.Solver(Q.default_shape("Custom", 5.0), max_batch=64)}
+    yield S
+    for s in S.values():
+        s.close()
+
+
+SHAPES = {"S2": ("C1", 2.0), "S5": ("Custom", 5.0)}
+
+
+def _rough(S, n, seed=1234):
+    grid, res = HF.rough_terrain(seed)
+    hid = S.upload_heightfield(grid, res)
+    return workloads.multistart_problems(n, grid, res, seed=seed, hf_id=hid), grid, res
+
+
+@pytest.mark.parametrize("shape", ["S2", "S5"])
+def test_structure_and_initial_point(solvers, oracle, shape):
+    S = solvers[shape]
+    p, grid, res = _rough(S, 3)
+    p["start_ang"][1] = (0.03, -0.02, 0.2)
+    x0, xl, xu, gl, gu = S.initial(p)
+    so = oracle.default_shape(*SHAPES[shape])
+    for i in range(3):
+        po = oracle_problem(oracle, so, p[i], grid, res)
+        assert (S.n_vars, S.n_cons) == (po.n, po.m)
+        oxl, oxu, ogl, ogu = po.bounds()
+        ox0 = po.x0(); ox0[oxl == oxu] = oxl[oxl == oxu]
+        assert np.array_equal(xl[i], oxl) and np.array_equal(xu[i], oxu)
+        assert np.array_equal(gl[i], ogl) and np.array_equal(gu[i], ogu)
+        assert np.abs(x0[i] - ox0).max() < 1e-14
+    if shape == "S5":
+        assert (S.n_vars, S.n_cons, S.dims.n_free, S.dims.n_eq, S.dims.n_ineq) == (1040, 1730, 1005, 706, 1024)
+
+
+@pytest.mark.parametrize("shape", ["S2", "S5"])
+def test_constraints_and_jacobian_match_oracle(solvers, oracle, shape):
+    S = solvers[shape]
+    p, grid, res = _rough(S, 4, seed=7)
+    p["start_ang"][:] = [(0.0, 0.0, 0.0), (0.05, -0.03, 0.3), (-0.1, 0.08, -0.4), (0.02, 0.02, 1.0)]
+    so = oracle.default_shape(*SHAPES[shape])
+    rng = np.random.default_rng(5)
+    x0 = S.initial(p)[0]
+    X = x0 + 0.05 * rng.standard_normal(x0.shape)
+    g, J = S.eval(p, X)
+    for i in range(4):
+        po = oracle_problem(oracle, so, p[i], grid, res)
+        oxl, oxu, _, _ = po.bounds()
+        fixed = oxl == oxu
+        x = X[i].copy(); x[fixed] = oxl[fixed]
+        og, oJ = po.g(x), po.jac(x)
+        oJ[:, fixed] = 0.0
+        assert np.abs(g[i] - og).max() < G_TOL
+        assert np.abs(J[i] - oJ).max() < J_TOL
+        assert np.all(J[i][:, fixed] == 0.0)
+
+
+def test_heightfield_queries_bit_exact(solvers, oracle, golden_hf):
+    S = solvers["S2"]
+    rng = np.random.default_rng(11)
+    for name in ("exp_1", "exp_3", "exp_5"):
+        grid, res = golden_hf[name + "_towr"], float(golden_hf[name + "_res"])
+        hid = S.upload_heightfield(grid, res)
+        ter = oracle.Terrain(grid, res)
+        pts = np.concatenate([rng.uniform(-1.4, 5.0, (2000, 2)),
+                              [[-1.0, -1.0], [0.0, 0.0], [-1.5, 0.2], [0.2, -1.5], [9.0, 9.0], [1e6, -1e6], [0.5, -1.0 + 7 * res], [-1.0 + 13 * res, 0.3]]])
+        h = S.height(hid, pts)
+        cells = S.height_cells(hid, pts)
+        want = np.array([ter.height(x, y) for x, y in pts])
+        wantc = np.array([ter.cell(x, y) for x, y in pts])[:, [0, 1, 2, 3]]
+        assert np.array_equal(h, want)                      # bit-exact, no tolerance
+        assert np.array_equal(cells, wantc)
+        assert np.array_equal(h, HF.get_height(grid, res, pts[:, 0], pts[:, 1]))
+    assert len(S.height(hid, np.zeros((0, 2)))) == 0        # empty query
+
+
+@pytest.mark.parametrize("shape,n", [("S2", 24), ("S5", 8)])
+def test_solve_matches_oracle_ipm(solvers, oracle, shape, n):
+    """Same algorithm on CPU and GPU: same status, same iteration count (allow +-1 on a tie in the line
+    search), node values and the 1 kHz trajectories within 1 mm."""
+    S = solvers[shape]
+    p, grid, res = _rough(S, n)
+    r, x, rows = S.solve(p, csv=True)
+    so = oracle.default_shape(*SHAPES[shape])
+    worst = 0.0
+    for i in range(n):
+        po = oracle_problem(oracle, so, p[i], grid, res)
+        xo, ro = po.solve()
+        assert r["status"][i] == ro.status
+        assert abs(int(r["iters"][i]) - ro.iters) <= 1
+        ocsv = po.csv(xo)
+        dev = np.abs(rows[i][:, 1:19] - ocsv[:, 1:19]).max()
+        worst = max(worst, dev)
+        assert dev < TRAJ_TOL_M, (i, dev)
+        assert np.abs(rows[i] - po.csv(x[i])).max() < 1e-10          # sampler kernel vs oracle sampler
+        if ro.status == 0:
+            assert r["constr_viol"][i] <= 1e-4
+            g = po.g(x[i]); _, _, gl, gu = po.bounds()
+            assert np.maximum(gl - g, g - gu).max() <= 1e-4 + 1e-9   # re-checked by the oracle's own g(x)
+    print("max trajectory deviation vs oracle [m]:", worst)
+
+
+def test_reference_experiment_windows(solvers, oracle, golden_hf, golden_csv):
+    """exp_1 (flat), exp_3 (0.5 m blocks), exp_5 (stairs): the single-window configs of BASELINE.json."""
+    S = solvers["S5"]
+    so = oracle.default_shape("Custom", 5.0)
+    cases = {"exp_1": ((0.0, 0.0), (0.5, 0.0)), "exp_3": ((0.0, 0.0), (0.5, 0.0)), "exp_5": ((0.0, 0.1), (0.45, 0.1))}
+    for name, (s, g) in cases.items():
+        grid, res = golden_hf[name + "_towr"], float(golden_hf[name + "_res"])
+        hid = S.upload_heightfield(grid, res)
+        p = Q.make_problems(1)
+        h0 = HF.get_height(grid, res, s[0], s[1])
+        p["start_pos"][0] = (s[0], s[1], h0 + 0.24); p["goal"][0] = (g[0], g[1], 0.24); p["hf_id"] = hid
+        p["ee"][0] = [(s[0] + a, s[1] + b, HF.get_height(grid, res, s[0] + a, s[1] + b)) for a, b, _ in FEET_19]
+        r, x, rows = S.solve(p, csv=True)
+        po = oracle_problem(oracle, so, p[0], grid, res)
+        xo, ro = po.solve()
+        assert r["status"][0] == ro.status, name
+        assert np.abs(rows[0][:, 1:19] - po.csv(xo)[:, 1:19]).max() < TRAJ_TOL_M, name
+        if name != "exp_5":
+            assert r["status"][0] == 0 and r["constr_viol"][0] <= 1e-4
+    # G3 inputs with the constants that produced the golden CSV (m = 3.0): feasible, and the measured gap
+    # to Ipopt's own plan is bounded (a feasibility problem has no unique solution; DESIGN.md parity tiers)
+    S3 = Q.Solver(Q.default_shape("Custom", 5.0, mass=3.0), max_batch=1)
+    hid = S3.upload_heightfield(np.zeros((600, 200)), 0.01)
+    p = Q.make_problems(1); p["goal"][0] = (0.502222, 0.0, 0.24); p["ee"][0] = FEET_19; p["hf_id"] = hid
+    r, x, rows = S3.solve(p, csv=True)
+    assert r["status"][0] == 0 and r["constr_viol"][0] <= 1e-4 and rows.shape == (1, 5001, 37)
+    gap = np.abs(rows[0][::10, 1:4] - golden_csv["gait"][:, 1:4]).max()
+    print("CoM gap to Ipopt golden gait.csv [m]:", gap)
+    assert gap < 0.10
+    S3.close()
+
+
+def test_batch_properties_at_bench_size(solvers):
+    """Size-independent properties on a 256-problem batch of the bench workload."""
+    S = solvers["S2"]
+    p, grid, res = _rough(S, 256)
+    r, x, _ = S.solve(p)
+    ok = r["status"] == 0
+    assert ok.mean() >= 0.97
+    assert np.all(r["constr_viol"][ok] <= 1e-4)
+    assert set(np.unique(r["status"])) <= {0, -1, -2}       # every problem reports a status, none dropped
+    x0, xl, xu, gl, gu = S.initial(p)
+    fixed = xl == xu
+    assert np.array_equal(x[fixed], xl[fixed])              # start / goal bounds are held exactly
+    g = S.eval(p, x, jac=False)
+    viol = np.maximum(np.maximum(gl - g, g - gu), 0).max(axis=1)
+    assert np.all(viol[ok] <= 1e-4 + 1e-9)                  # violation recomputed from scratch by the eval entry
+    # solving the same batch twice is deterministic (owner-computes assembly, no atomics in the data path)
+    r2, x2, _ = S.solve(p)
+    assert np.array_equal(x, x2) and np.array_equal(r["iters"], r2["iters"])
+    # order independence: a permuted batch gives the permuted answer
+    perm = np.random.default_rng(0).permutation(256)
+    r3, x3, _ = S.solve(p[perm])
+    assert np.array_equal(x3, x[perm])
+    # stance feet sit on the terrain: CSV foot z equals the heightfield under the foot at contact samples
+    rows = S.sample_csv(p[:4], x[:4])
+    assert rows.shape == (4, 2001, 37) and np.allclose(rows[:, 0, 1:4], p["start_pos"][:4])
+    last = rows[:, -1]
+    for i in range(4):
+        if not ok[i]:
+            continue
+        for e in range(4):
+            fx, fy, fz = last[i, 7 + 3 * e:10 + 3 * e]
+            assert abs(fz - HF.get_height(grid, res, fx, fy)) < 2e-4
+
+
+def test_errors_are_loud(solvers):
+    S = solvers["S2"]
+    p = Q.make_problems(1); p["hf_id"] = 12345
+    with pytest.raises(Q.QtosError, match="heightfield"):
+        S.solve(p)
+    with pytest.raises(Q.QtosError):
+        Q.Solver(Q.default_shape("C1", -1.0))
+    bad = Q.default_shape("C1", 2.0); bad.combo = 17
+    with pytest.raises(Q.QtosError, match="gait"):
+        Q.Solver(bad)
+
+
+def test_cli_clone_writes_reference_csv(tmp_path, golden_hf):
+    """`./main <flags>` drop-in: reads ../data/heightfields/from_pybullet/towr_heightfield.txt, writes traj.csv."""
+    build = tmp_path / "towr" / "build"; build.mkdir(parents=True)
+    hfdir = tmp_path / "towr" / "data" / "heightfields" / "from_pybullet"; hfdir.mkdir(parents=True)
+    HF.write_heightfield(str(hfdir / "towr_heightfield.txt"), golden_hf["exp_1_towr"])
+    args = {"-s": [0, 0, 0.24], "-g": [0.5, 0, 0.24], "-e1": [0.21, 0.19, 0.0], "-e2": [0.21, -0.19, 0.0],
+            "-e3": [-0.21, 0.19, 0.0], "-e4": [-0.21, -0.19, 0.0], "-s_ang": [0, 0, 0], "-t": 1.25, "-r": 15.0, "-resolution": 0.1}
+    rc = towr_cli.towr_main(towr_cli.cmd_args(args).split(), cwd=str(build), quiet=True)
+    assert rc == 0
+    text = open(build / "traj.csv").read().strip().split("\n")
+    assert len(text) == 5001 and all(len(l.split(",")) == 37 for l in text[:50])
+    first = [float(v) for v in text[0].split(",")]
+    assert first[0] == 1.25 and first[1:4] == [0.0, 0.0, 0.24] and first[7:10] == [0.21, 0.19, 0.0]
+    assert float(text[-1].split(",")[0]) == 6.25
+    assert towr_cli.towr_main(["-g", "0.5", "0", "0.24"], cwd=str(tmp_path), quiet=True) == 2      # missing heightfield

@@ -1,0 +1,190 @@
+"""CPU tier: the oracle (oracle/*.c) against every golden artefact the reference holds for this path
+(SURVEY 8c G1-G5).  No GPU, no product code."""
+import numpy as np
+import pytest
+
+from conftest import FEET_19
+
+
+def s5(O, mass=3.0, goal=(0.5, 0.0, 0.24)):
+    sh = O.default_shape("Custom", 5.0, mass=mass)
+    ter = O.Terrain(np.zeros((600, 200)), 0.01)
+    return O.Problem(sh, O.make_instance(goal=goal, ee=FEET_19), ter)
+
+
+def test_structure_matches_ipopt_log(oracle, towr_log):
+    """G1: sizes, fixed variables, inequality split and Jacobian non-zeros of logs/towr_log.out:40-52,98-129."""
+    p = s5(oracle)
+    xl, xu, gl, gu = p.bounds()
+    assert p.n == towr_log["n_vars_total"] and (xl == xu).sum() == towr_log["n_fixed"]
+    eq = gl == gu
+    assert eq.sum() == towr_log["n_eq"] and (~eq).sum() == towr_log["n_ineq"]
+    lo, up = gl > -1e19, gu < 1e19
+    assert (~eq & lo & ~up).sum() == towr_log["ineq_lower_only"]
+    assert (~eq & lo & up).sum() == towr_log["ineq_both"]
+    assert (~eq & ~lo & up).sum() == towr_log["ineq_upper_only"]
+    _, mask = p.jac(p.x0(), with_mask=True)
+    free = xl != xu
+    assert mask[eq][:, free].sum() == towr_log["nnz_eq"]
+    assert mask[~eq][:, free].sum() == towr_log["nnz_ineq"]
+    vo, ro = p.layout()
+    assert vo == [0, 306, 612, 647, 682, 717, 752, 824, 896, 968, 1040]
+    assert ro[4] == 52 and ro[5] == 364 and ro[6] == 511 and ro[7] == 658 and ro[11] == 1426 and ro[15] == 1666 and ro[19] == 1730
+
+
+def test_initial_infeasibility_known_answer(oracle, towr_log):
+    """G5: iteration-0 inf_pr = 1.94e+01 (m = 3.0) in all three logged solves; 9.7094 with m = 1.5."""
+    for mass, want in ((3.0, 19.4188), (1.5, 9.7094)):
+        p = s5(oracle, mass)
+        g = p.g(p.x0())
+        _, _, gl, gu = p.bounds()
+        viol = np.maximum(np.maximum(gl - g, 0), np.maximum(g - gu, 0))
+        assert abs(viol.max() - want) < 1e-3
+        r = int(np.argmax(viol))
+        assert (r - 52) % 6 == 5 and (r - 52) // 6 == 42          # LZ row of the sample at t = 4.2 s
+    assert f"{19.4188:.2e}" == "1.94e+01" and towr_log["inf_pr_iter0"] == 19.4
+
+
+def test_gait_phase_durations(oracle):
+    """A4: LF phases of the Custom combo scaled to T = 5 s."""
+    p = s5(oracle)
+    want = [0.4926, 0.1847, 1.0468, 0.1847, 1.0468, 0.1847, 0.8929, 0.3140, 0.6527]
+    got = p.phase_durations(0)
+    assert len(got) == 9 and np.allclose(got, want, atol=5e-5) and abs(got.sum() - 5.0) < 1e-12
+    for ee in range(4):
+        assert abs(p.phase_durations(ee).sum() - 5.0) < 1e-12
+    # S2 = C1 fly trot, 2 s: 640 variables / 892 constraints
+    p2 = oracle.Problem(oracle.default_shape("C1", 2.0), oracle.make_instance(), oracle.Terrain(np.zeros((40, 20)), 0.1))
+    assert (p2.n, p2.m) == (640, 892)
+
+
+def test_jacobian_finite_differences(oracle):
+    """Ipopt's derivative_test (ref: main.cpp:454) on the restated Jacobian, rough terrain, perturbed x."""
+    rng = np.random.default_rng(0)
+    grid = np.kron(np.round(rng.uniform(0, 0.075, (32, 32)), 4), np.ones((8, 8)))
+    sh = oracle.default_shape("C1", 2.0)
+    inst = oracle.make_instance(start_pos=(1.0, 1.0, 0.28), goal=(1.4, 1.05, 0.24), start_ang=(0.05, -0.04, 0.1),
+                                ee=[(1.21, 1.19, 0.03), (1.21, 0.81, 0.02), (0.79, 1.19, 0.05), (0.79, 0.81, 0.01)])
+    p = oracle.Problem(sh, inst, oracle.Terrain(grid, 0.02))
+    x = p.x0() + 0.02 * rng.standard_normal(p.n)
+    J = p.jac(x)
+    vo, ro = p.layout()
+    terrain_rows = np.arange(0, ro[4])
+    cols = rng.choice(p.n, 60, replace=False)
+    for c in cols:
+        h = 1e-6
+        xp, xm = x.copy(), x.copy()
+        xp[c] += h; xm[c] -= h
+        fd = (p.g(xp) - p.g(xm)) / (2 * h)
+        d = np.abs(fd - J[:, c])
+        d[terrain_rows] = 0.0           # dh/dx, dh/dy are hard zero in the reference (F4)
+        assert d.max() < 2e-5 * max(1.0, np.abs(J[:, c]).max()), (c, d.max())
+
+
+def _hermite_acc(p0, v0, p1, v1, T, t):
+    return (12 * t / T**3 - 6 / T**2) * p0 + (6 * t / T**2 - 4 / T) * v0 + (6 / T**2 - 12 * t / T**3) * p1 + (6 * t / T**2 - 2 / T) * v1
+
+
+def _srbd_residual(c, cdd, e, ed, edd, pee, f, m, Ib):
+    """independent numpy statement of the SRBD rows (ref: single_rigid_body_dynamics.cc:76-103)."""
+    x, y, z = e
+    R = np.array([[np.cos(y) * np.cos(z), np.cos(z) * np.sin(x) * np.sin(y) - np.cos(x) * np.sin(z), np.sin(x) * np.sin(z) + np.cos(x) * np.cos(z) * np.sin(y)],
+                  [np.cos(y) * np.sin(z), np.cos(x) * np.cos(z) + np.sin(x) * np.sin(y) * np.sin(z), np.cos(x) * np.sin(y) * np.sin(z) - np.cos(z) * np.sin(x)],
+                  [-np.sin(y), np.cos(y) * np.sin(x), np.cos(x) * np.cos(y)]])
+    M = np.array([[np.cos(y) * np.cos(z), -np.sin(z), 0], [np.cos(y) * np.sin(z), np.cos(z), 0], [-np.sin(y), 0, 1]])
+    yd, zd = ed[1], ed[2]
+    Md = np.array([[-np.cos(z) * np.sin(y) * yd - np.cos(y) * np.sin(z) * zd, -np.cos(z) * zd, 0],
+                   [np.cos(y) * np.cos(z) * zd - np.sin(y) * np.sin(z) * yd, -np.sin(z) * zd, 0],
+                   [-np.cos(y) * yd, 0, 0]])
+    w, wd = M @ ed, Md @ ed + M @ edd
+    Iw = R @ Ib @ R.T
+    tau = sum(np.cross(f[i], c - pee[i]) for i in range(4))
+    ang = Iw @ wd + np.cross(w, Iw @ w) - tau
+    lin = m * cdd - f.sum(axis=0) - np.array([0, 0, -m * 9.80665])
+    return np.concatenate([ang, lin])
+
+
+def test_dynamics_formula_and_golden_csv(oracle, golden_csv):
+    """(a) the oracle's dynamic rows equal an independent numpy statement at random x;
+    (b) that statement is satisfied by the reference's own golden plans (G2, G3) with m = 3.0 and the
+    mis-ordered inertia tensor the reference actually runs (F5/F6)."""
+    sh = oracle.default_shape("Custom", 5.0, mass=3.0)
+    Ib = np.array(list(sh.I_b)).reshape(3, 3)
+    p = s5(oracle, 3.0)
+    rng = np.random.default_rng(1)
+    x = p.x0() + 0.03 * rng.standard_normal(p.n)
+    g = p.g(x)
+    rows = p.csv(x)                               # 1 kHz samples give positions / forces at t = k * 0.1
+    for k in (1, 7, 23, 42, 50):
+        r = rows[100 * k]
+        bl0, bl1 = x[(k - 1) * 6:(k - 1) * 6 + 6], x[k * 6:k * 6 + 6]
+        ba0, ba1 = x[306 + (k - 1) * 6:306 + (k - 1) * 6 + 6], x[306 + k * 6:306 + k * 6 + 6]
+        cdd = _hermite_acc(bl0[:3], bl0[3:], bl1[:3], bl1[3:], 0.1, 0.1)
+        edd = _hermite_acc(ba0[:3], ba0[3:], ba1[:3], ba1[3:], 0.1, 0.1)
+        res = _srbd_residual(r[1:4], cdd, r[4:7], r[22:25], edd, r[7:19].reshape(4, 3), r[25:37].reshape(4, 3), 3.0, Ib)
+        assert np.allclose(res, g[52 + 6 * k:52 + 6 * k + 6], atol=1e-9)
+    for name in ("gait", "towr_g2"):
+        G = golden_csv[name]                      # every 10th row -> nodes every 10 rows
+        worst_ang = worst_lin = 0.0
+        for k in range(1, 51):
+            a, b = G[10 * (k - 1)].copy(), G[10 * k]
+            if name == "towr_g2" and k == 1:
+                a[19:25] = 0.0                    # spliced row of the previous window; this solve starts at rest (F8)
+            cdd = _hermite_acc(a[1:4], a[19:22], b[1:4], b[19:22], 0.1, 0.1)
+            edd = _hermite_acc(a[4:7], a[22:25], b[4:7], b[22:25], 0.1, 0.1)
+            res = _srbd_residual(b[1:4], cdd, b[4:7], b[22:25], edd, b[7:19].reshape(4, 3), b[25:37].reshape(4, 3), 3.0, Ib)
+            worst_ang = max(worst_ang, np.abs(res[:3]).max()); worst_lin = max(worst_lin, np.abs(res[3:]).max())
+        assert worst_ang < 5e-4 and worst_lin < 2e-2, (name, worst_ang, worst_lin)   # 6-digit CSV rounding
+
+
+def test_golden_csv_layout(oracle, golden_csv):
+    """A18: 5001 x 37 rows, t + t_start in column 0, start state of G2 as logged (towr_log.out:143-160)."""
+    assert int(golden_csv["gait_rows"]) == 5001
+    G2 = golden_csv["towr_g2"]
+    assert abs(G2[0, 0] - 3.756) < 1e-9 and abs(G2[-1, 0] - 8.756) < 1e-9
+    assert np.allclose(G2[0, 1:4], [0.335266, -0.0123145, 0.221551], atol=1e-6)
+    assert np.allclose(G2[0, 4:7], [-0.0422299, -0.0416417, 0.00880732], atol=1e-6)
+    p = s5(oracle, 3.0, goal=(0.502222, 0, 0.24))
+    x = p.x0(); xl, xu, _, _ = p.bounds()
+    assert abs(x[612] - 0.2486) < 1e-3           # shared stance variable: the LATER node's interpolation wins in x0
+    x[xl == xu] = xl[xl == xu]                    # ... and the start bound then pins it (Ipopt make_parameter)
+    rows = p.csv(x)
+    assert rows.shape == (5001, 37) and rows[0, 0] == 0.0 and abs(rows[-1, 0] - 5.0) < 1e-9
+    assert np.allclose(rows[0, 1:4], [0, 0, 0.24]) and np.allclose(rows[0, 7:10], [0.21, 0.19, 0.0])
+
+
+def test_heightfield_indexing(oracle, golden_hf):
+    """A2 / Appendix B: cell selection incl. negative coordinates -> last cell, degenerate clamped edge."""
+    grid = golden_hf["exp_5_towr"]; res = float(golden_hf["exp_5_res"])
+    ter = oracle.Terrain(grid, res)
+    assert grid.shape == (440, 220) and abs(res - 1 / 110) < 1e-15
+    assert ter.cell(-1.5, 0.3)[0] == 439                      # size_t wrap of a negative floor -> clamps to nx-1
+    assert ter.cell(0.0, 5.0)[1] == 219
+    assert ter.height(-1.5, 0.3) == 0.0 or np.isfinite(ter.height(-1.5, 0.3))
+    assert ter.height(10.0, 0.0) == 0.0                       # x0 == x1 at the clamped edge -> degenerate formula gives 0
+    # interior: bilinear between the four cell corners
+    x, y = 0.4321, 0.1234
+    c = ter.cell(x, y)
+    h = ter.height(x, y)
+    corners = [grid[c[0], c[1]], grid[c[0], c[3]], grid[c[2], c[1]], grid[c[2], c[3]]]
+    assert min(corners) - 1e-12 <= h <= max(corners) + 1e-12
+
+
+def test_oracle_ipm_converges_on_reference_cases(oracle, golden_csv):
+    """The restated IPM reaches the reference's convergence criteria on the logged inputs (G1/G3, G2) and
+    reports how far its plan is from Ipopt's (feasibility problems have no unique answer: informational)."""
+    p = s5(oracle, 3.0, goal=(0.502222, 0, 0.24))
+    x, res = p.solve()
+    assert res.status == 0 and res.constr_viol <= 1e-4 and res.iters <= 30
+    g = p.g(x); _, _, gl, gu = p.bounds()
+    assert np.maximum(gl - g, g - gu).max() <= 1e-4
+    gap = np.abs(p.csv(x)[::10, 1:4] - golden_csv["gait"][:, 1:4]).max()
+    assert gap < 0.10                                          # measured 3.3 cm; see DESIGN.md "parity tiers"
+    sh = oracle.default_shape("Custom", 5.0, mass=3.0)
+    G2 = golden_csv["towr_g2"]
+    inst = oracle.make_instance(start_pos=G2[0, 1:4], start_ang=G2[0, 4:7], goal=(0.9100042764, 0.0, 0.24),
+                                ee=G2[0, 7:19].reshape(4, 3), t_start=3.756)
+    p2 = oracle.Problem(sh, inst, oracle.Terrain(np.zeros((600, 200)), 0.01))
+    x2, r2 = p2.solve()
+    assert r2.status == 0 and r2.constr_viol <= 1e-4
+    assert np.allclose(p2.csv(x2)[0, 1:19], G2[0, 1:19], atol=1e-6)

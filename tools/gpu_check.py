@@ -53,8 +53,8 @@ for combo, T in [("C1", 2.0), ("Custom", 5.0)]:
     rows = S.sample_csv(p, x)
     po = oracle_problem(so, p[0], grid, res)
     print(" csv sampler diff", np.abs(rows[0] - po.csv(x[0])).max())
-    os.environ["QTOS_PROFILE_PHASES"] = "1"
+    S.set_profiling(True)
     big = gen(64, grid, res); big["hf_id"] = hid
     t = time.time(); r2, x2, _ = S.solve(big); dt = time.time() - t
-    print(" batch64 %.3fs" % dt, "conv", (r2["status"] == 0).sum(), "iters", r2["iters"].min(), r2["iters"].max(), S.last_timing())
-    del os.environ["QTOS_PROFILE_PHASES"]
+    print(" batch64 %.3fs" % dt, "conv", (r2["status"] == 0).sum(), "iters", r2["iters"].min(), r2["iters"].max(), S.last_stats())
+    S.set_profiling(False)
