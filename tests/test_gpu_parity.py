@@ -127,9 +127,13 @@ def test_reference_experiment_windows(solvers, oracle, golden_hf, golden_csv):
     """exp_1 (flat), exp_3 (0.5 m blocks), exp_5 (stairs): the single-window configs of BASELINE.json."""
     S = solvers["S5"]
     so = oracle.default_shape("Custom", 5.0)
-    cases = {"exp_1": ((0.0, 0.0), (0.5, 0.0)), "exp_3": ((0.0, 0.0), (0.5, 0.0)), "exp_5": ((0.0, 0.1), (0.45, 0.1))}
+    # exp_3: a 0.5 m block covers x in [0.7, 1.1), y in [-0.3, 0.1).  "exp_3" passes beside it; "exp_3_blocked" asks the
+    # right front foot to end ON the block (infeasible range of motion) -- the case PATH_MAP probes for
+    # (ref: QTOS/generateHeightField.py:387-404): both implementations must report a non-zero status.
+    cases = {"exp_1": ((0.0, 0.0), (0.5, 0.0)), "exp_3": ((0.0, 0.35), (0.5, 0.35)), "exp_3_blocked": ((0.0, 0.0), (0.5, 0.0)),
+             "exp_5": ((0.0, 0.1), (0.45, 0.1))}
     for name, (s, g) in cases.items():
-        grid, res = golden_hf[name + "_towr"], float(golden_hf[name + "_res"])
+        grid, res = golden_hf[name[:5] + "_towr"], float(golden_hf[name[:5] + "_res"])
         hid = S.upload_heightfield(grid, res)
         p = Q.make_problems(1)
         h0 = HF.get_height(grid, res, s[0], s[1])
@@ -140,8 +144,10 @@ def test_reference_experiment_windows(solvers, oracle, golden_hf, golden_csv):
         xo, ro = po.solve()
         assert r["status"][0] == ro.status, name
         assert np.abs(rows[0][:, 1:19] - po.csv(xo)[:, 1:19]).max() < TRAJ_TOL_M, name
-        if name != "exp_5":
+        if name in ("exp_1", "exp_3"):
             assert r["status"][0] == 0 and r["constr_viol"][0] <= 1e-4
+        if name == "exp_3_blocked":
+            assert r["status"][0] != 0 and towr_cli.exit_code(r["status"][0]) != 0
     # G3 inputs with the constants that produced the golden CSV (m = 3.0): feasible, and the measured gap
     # to Ipopt's own plan is bounded (a feasibility problem has no unique solution; DESIGN.md parity tiers)
     S3 = Q.Solver(Q.default_shape("Custom", 5.0, mass=3.0), max_batch=1)
