@@ -335,7 +335,7 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 	std::vector<std::vector<int>> ecols;      /* element -> free (unpermuted) columns */
 	std::vector<std::vector<double>> econst;  /* element -> col-major constant values (empty for dyn/rom) */
 	auto new_elem = [&](int type, int row0, int nrows, const std::vector<int> &cols) {
-		Element e; e.type = type; e.row0 = row0; e.nrows = nrows; e.ncols = (int)cols.size(); e.valoff = 0; e.coloff = 0;
+		Element e; e.type = type; e.row0 = row0; e.nrows = nrows; e.ncols = (int)cols.size(); e.valoff = 0; e.coloff = 0; e.ld = (nrows + 1) & ~1; e.pad_ = 0;
 		H->elems.push_back(e); ecols.push_back(cols); econst.push_back({});
 		for (int r = 0; r < nrows; ++r) H->row_elem[row0 + r] = (int)H->elems.size() - 1;
 		return (int)H->elems.size() - 1;
@@ -543,16 +543,20 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 		Element &E = H->elems[e];
 		E.valoff = valoff; E.coloff = (int)H->elem_cols.size();
 		for (int a : ecols[e]) H->elem_cols.push_back((int16_t)pos[a]);
-		valoff += E.nrows * E.ncols;
+		valoff += E.ld * E.ncols;
 		H->nnz_jac += E.nrows * E.ncols;
 		if (E.ncols > 255 || e > 65535) return fail("element table overflow");
 	}
 	H->nJ = valoff;
 	H->Jconst.assign(H->nJ > 0 ? H->nJ : 1, 0.0);
-	for (size_t e = 0; e < H->elems.size(); ++e)
-		for (size_t q = 0; q < econst[e].size(); ++q) H->Jconst[H->elems[e].valoff + q] = econst[e][q];
+	for (size_t e = 0; e < H->elems.size(); ++e) {
+		const Element &E = H->elems[e];
+		if (econst[e].empty()) continue;
+		for (int a = 0; a < E.ncols; ++a) for (int r = 0; r < E.nrows; ++r) H->Jconst[E.valoff + a * E.ld + r] = econst[e][(size_t)a * E.nrows + r];
+	}
+	if (H->nJ >= (1 << 20)) return fail("Jacobian value array too large for packed assembly terms");
 	{
-		std::vector<std::pair<int, uint32_t>> terms;       /* (M offset, packed term) */
+		std::vector<std::pair<int, uint64_t>> terms;       /* (M offset, packed term) */
 		std::vector<std::vector<uint32_t>> jt(npad);
 		for (size_t e = 0; e < H->elems.size(); ++e) {
 			const std::vector<int> &c = ecols[e];
@@ -561,11 +565,12 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 				for (size_t b = 0; b < c.size(); ++b) {
 					int pa = pos[c[a]], pb = pos[c[b]];
 					if (pa < pb || (pa == pb && a != b)) continue;
-					terms.push_back({m_off(pa, pb), (uint32_t)(e << 16) | (uint32_t)(a << 8) | (uint32_t)b});
+					const Element &E = H->elems[e];
+					terms.push_back({m_off(pa, pb), (uint64_t)(E.valoff + a * E.ld) | ((uint64_t)(E.valoff + b * E.ld) << 20) | ((uint64_t)(E.ld / 2) << 40)});
 				}
 			}
 		}
-		std::stable_sort(terms.begin(), terms.end(), [](const std::pair<int, uint32_t> &x, const std::pair<int, uint32_t> &y) { return x.first < y.first; });
+		std::stable_sort(terms.begin(), terms.end(), [](const std::pair<int, uint64_t> &x, const std::pair<int, uint64_t> &y) { return x.first < y.first; });
 		H->asm_ptr.clear(); H->asm_off.clear(); H->asm_terms.clear();
 		for (size_t q = 0; q < terms.size(); ++q) {
 			if (q == 0 || terms[q].first != terms[q - 1].first) { H->asm_ptr.push_back((int)q); H->asm_off.push_back(terms[q].first); }

@@ -38,7 +38,7 @@ struct DevTables {
 	const int *lin_row, *lin_ptr; const int16_t *lin_col; const double *lin_val;
 	const int *ter_row; const int16_t *ter_var;
 	const int *fb, *blkptr, *diag_off;
-	const int *asm_ptr, *asm_off, *asm_chunk; const uint32_t *asm_terms;
+	const int *asm_ptr, *asm_off, *asm_chunk, *asm_rowptr; const uint64_t *asm_terms;
 	const int *jt_ptr; const uint32_t *jt_terms;
 	const double *csv_t, *csv_tl; const uint8_t *csv_id;
 	const double *dur; int dur_ld;          /* [10][dur_ld] */
@@ -53,6 +53,7 @@ struct DevWork {
 	double *P;                              /* [32] */
 	double *scal;                           /* [16]: 0 mu, 1 nu, 2 sd, 3 sc_, 4 dual_inf, 5 theta_inf, ... */
 	double *Jv;                             /* [nJ] */
+	double *DJ;                             /* [nJ] D * J (row weights folded in) for the assembly gather */
 	double *M;                              /* [nM] */
 	double *Dinv;                           /* [nb*256] inverses of the diagonal blocks of L */
 	int *status, *iters, *flags;            /* [1] each */
@@ -345,7 +346,7 @@ __device__ __forceinline__ void rom_rows(const RomState &S, double *g3)
 
 __device__ __forceinline__ void rom_jac(const RomSample &R, const RomState &S, const double *sc3, double *blk, int ncols)
 {
-	for (int i = 0; i < 3 * ncols; ++i) blk[i] = 0.0;
+	for (int i = 0; i < 4 * ncols; ++i) blk[i] = 0.0;       /* column stride 4: 3 rows + zero pad */
 	const double rW[3] = {S.p[0] - S.c[0], S.p[1] - S.c[1], S.p[2] - S.c[2]};
 	double Gp[9];
 	for (int k = 0; k < 3; ++k) {
@@ -357,11 +358,11 @@ __device__ __forceinline__ void rom_jac(const RomSample &R, const RomState &S, c
 		for (int k = 0; k < 3; ++k) {
 			const int canon = (q >> 1) * 6 + (q & 1) * 3 + k;
 			int sl = R.slot[canon];
-			if (sl >= 0) { double *c = blk + 3 * sl; for (int r = 0; r < 3; ++r) c[r] += sc3[r] * (-S.E.R[3 * k + r] * R.wp[q]); }
+			if (sl >= 0) { double *c = blk + 4 * sl; for (int r = 0; r < 3; ++r) c[r] += sc3[r] * (-S.E.R[3 * k + r] * R.wp[q]); }
 			sl = R.slot[12 + canon];
-			if (sl >= 0) { double *c = blk + 3 * sl; for (int r = 0; r < 3; ++r) c[r] += sc3[r] * Gp[3 * r + k] * R.wp[q]; }
+			if (sl >= 0) { double *c = blk + 4 * sl; for (int r = 0; r < 3; ++r) c[r] += sc3[r] * Gp[3 * r + k] * R.wp[q]; }
 			sl = R.slot[24 + canon];
-			if (sl >= 0) { double *c = blk + 3 * sl; for (int r = 0; r < 3; ++r) c[r] += sc3[r] * S.E.R[3 * k + r] * R.mo_w[q]; }
+			if (sl >= 0) { double *c = blk + 4 * sl; for (int r = 0; r < 3; ++r) c[r] += sc3[r] * S.E.R[3 * k + r] * R.mo_w[q]; }
 		}
 }
 

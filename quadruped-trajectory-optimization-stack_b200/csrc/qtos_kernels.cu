@@ -1,15 +1,16 @@
 /*
  * qtos_kernels.cu -- sm_100a kernels of the batched interior-point gait-plan solver.
  *
- * One thread block per problem in every kernel; a batch iteration is five launches
- * (jac -> prepare -> assemble -> factor -> step), all on the context's stream:
+ * One thread block per problem (k_jac: one thread per sample); a batch iteration is five launches
+ * (jac_dyn, jac_rom -> prepare -> factor -> step), all on the context's stream:
  *   k_init      x0, fixed variables, g(x0), J(x0), row scaling, slack/multiplier init
  *               (ref: nlp_formulation.cc:100-190; Ipopt initialisation)
  *   k_jac       dynamics + range-of-motion Jacobian element blocks at x
  *   k_prepare   J'y, error measures, termination test, barrier update, Sigma, rhs = -J'w
- *   k_assemble  M = sigma I + J' D J into block-skyline storage (owner-computes gather)
- *   k_factor    blocked left-looking Cholesky, 16x16 blocks, panels staged in shared memory
- *   k_step      triangular solves, step recovery, fraction-to-boundary, l1-merit backtracking
+ *   k_factor    per block row: assemble sigma I + J' D J (owner-computes gather) into shared memory,
+ *               left-looking Cholesky on 16x16 blocks with FP64 tensor-core MMAs, forward
+ *               substitution; then the backward substitution -> dx
+ *   k_step      step recovery, fraction-to-boundary, l1-merit backtracking
  *               line search with in-kernel g(x) evaluations, iterate update
  *   k_csv       1 kHz trajectory sampler (ref: main.cpp:92-131)
  *   k_height    batched heightfield queries (ref: custom_terrain.cpp:51-94)
@@ -107,13 +108,13 @@ k_init(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *
 		const Element &E = T.elems[T.row_elem[i]];
 		const int rr = i - E.row0;
 		double mx = 0.0;
-		for (int a = 0; a < E.ncols; ++a) mx = fmax(mx, fabs(Jv[E.valoff + a * E.nrows + rr]));
+		for (int a = 0; a < E.ncols; ++a) mx = fmax(mx, fabs(Jv[E.valoff + a * E.ld + rr]));
 		sc[i] = mx > 100.0 ? fmax(100.0 / mx, 1e-8) : 1.0;
 	}
 	__syncthreads();
 	for (int e = threadIdx.x; e < T.n_elem; e += blockDim.x) {
 		const Element &E = T.elems[e];
-		for (int a = 0; a < E.ncols; ++a) for (int rr = 0; rr < E.nrows; ++rr) Jv[E.valoff + a * E.nrows + rr] *= sc[E.row0 + rr];
+		for (int a = 0; a < E.ncols; ++a) for (int rr = 0; rr < E.nrows; ++rr) Jv[E.valoff + a * E.ld + rr] *= sc[E.row0 + rr];
 	}
 	double *s = WS(s, T.m), *y = WS(y, T.m), *zL = WS(zL, T.m), *zU = WS(zU, T.m), *dL = WS(dL, T.m), *dU = WS(dU, T.m);
 	for (int i = threadIdx.x; i < T.m; i += blockDim.x) {
@@ -146,12 +147,31 @@ k_init(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *
 
 /* ------------------------------------------------------------------ k_jac */
 
-__global__ void __launch_bounds__(QTOS_THREADS)
-k_jac(DevTables T, DevWork W)
+/* one thread per (problem, sample): every lane of a warp evaluates the same kind of sample */
+__global__ void __launch_bounds__(64)
+k_jac_dyn(DevTables T, DevWork W, int n)
 {
-	const int pid = blockIdx.x;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n * T.n_dyn) return;
+	const int pid = t / T.n_dyn, k = t - pid * T.n_dyn;
 	if (W.status[pid] != QTOS_RUNNING) return;
-	eval_jac_block(T, WS(x, T.n_all), WS(sc, T.m), WS(Jv, T.nJ));
+	const DynSample &D = T.dyn[k];
+	const Element &E = T.elems[D.elem];
+	DynState S; dyn_state(T, D, WS(x, T.n_all), S);
+	dyn_jac(T, D, S, WS(sc, T.m) + E.row0, WS(Jv, T.nJ) + E.valoff, E.ncols);
+}
+
+__global__ void __launch_bounds__(128)
+k_jac_rom(DevTables T, DevWork W, int n)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n * T.n_rom4) return;
+	const int pid = t / T.n_rom4, k = t - pid * T.n_rom4;
+	if (W.status[pid] != QTOS_RUNNING) return;
+	const RomSample &R = T.rom[k];
+	const Element &E = T.elems[R.elem];
+	RomState S; rom_state(T, R, WS(x, T.n_all), S);
+	rom_jac(R, S, WS(sc, T.m) + E.row0, WS(Jv, T.nJ) + E.valoff, E.ncols);
 }
 
 /* ------------------------------------------------------------------ k_prepare */
@@ -162,7 +182,7 @@ __device__ __forceinline__ double jt_gather(const DevTables &T, const double *Jv
 	for (int q = T.jt_ptr[i]; q < T.jt_ptr[i + 1]; ++q) {
 		const uint32_t t = T.jt_terms[q];
 		const Element &E = T.elems[t >> 8];
-		const double *col = Jv + E.valoff + (t & 255u) * E.nrows;
+		const double *col = Jv + E.valoff + (t & 255u) * E.ld;
 		const double *wr = wrow + E.row0;
 		for (int rr = 0; rr < E.nrows; ++rr) acc += col[rr] * wr[rr];
 	}
@@ -229,121 +249,199 @@ k_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 	}
 	__syncthreads();
 	for (int i = threadIdx.x; i < T.npad; i += blockDim.x) vec[i] = i < T.n_free ? -jt_gather(T, Jv, w, i) : 0.0;
-}
-
-/* ------------------------------------------------------------------ k_assemble */
-
-__global__ void __launch_bounds__(QTOS_THREADS)
-k_assemble(DevTables T, DevWork W, qtos_options opt)
-{
-	const int pid = blockIdx.x, chunk = blockIdx.y;
-	if (W.status[pid] != QTOS_RUNNING) return;
-	const double *Jv = WS(Jv, T.nJ), *Sig = WS(Sig, T.m);
-	double *M = WS(M, T.nM);
-	const int per = (T.nM / NB / NB + T.n_chunks - 1) / T.n_chunks * NB * NB;
-	const int lo = chunk * per, hi = min(T.nM, lo + per);
-	for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) M[i] = 0.0;
-	__syncthreads();
-	for (int t = T.asm_chunk[chunk] + threadIdx.x; t < T.asm_chunk[chunk + 1]; t += blockDim.x) {
-		double acc = 0.0;
-		for (int q = T.asm_ptr[t]; q < T.asm_ptr[t + 1]; ++q) {
-			const uint32_t term = T.asm_terms[q];
-			const Element &E = T.elems[term >> 16];
-			const double *ca = Jv + E.valoff + ((term >> 8) & 255u) * E.nrows, *cb = Jv + E.valoff + (term & 255u) * E.nrows;
-			const double *D = Sig + E.row0;
-			for (int rr = 0; rr < E.nrows; ++rr) acc += D[rr] * ca[rr] * cb[rr];
-		}
-		M[T.asm_off[t]] = acc;
-	}
-	__syncthreads();
-	for (int i = threadIdx.x; i < T.npad; i += blockDim.x) {
-		const int off = T.diag_off[i];
-		if (off >= lo && off < hi) M[off] = i < T.n_free ? M[off] + opt.sigma_w : 1.0;
+	/* D * J for the assembly gather of k_factor (one element column per thread) */
+	double *DJ = WS(DJ, T.nJ);
+	for (int q = threadIdx.x; q < T.jt_ptr[T.npad]; q += blockDim.x) {
+		const uint32_t t = T.jt_terms[q];
+		const Element &E = T.elems[t >> 8];
+		const int o = E.valoff + (t & 255u) * E.ld;
+		for (int rr = 0; rr < E.ld; ++rr) DJ[o + rr] = rr < E.nrows ? Sig[E.row0 + rr] * Jv[o + rr] : 0.0;
 	}
 }
 
 /* ------------------------------------------------------------------ k_factor */
 
-#define OPLD 17          /* padded row stride of operand blocks in shared memory */
+#define FT 128           /* threads of the factor kernel: 4 warps, one 8x8 tile of a 16x16 block each */
+#define TLD 20           /* padded leading dimension of 16x16 tiles in shared memory (conflict-free DMMA fragments) */
 
-__global__ void __launch_bounds__(QTOS_THREADS)
-k_factor(DevTables T, DevWork W, int max_w /* max blocks per block row */)
+/* D = A(8x4) * B(4x8) + C, FP64 tensor-core MMA; fragment layout (PTX ISA, m8n8k4):
+ * a = A[lane>>2][lane&3], b = B[lane&3][lane>>2], c/d = C[lane>>2][2*(lane&3) + {0,1}] */
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
+{
+	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+/* Condensed KKT system of one problem, start to finish in one CTA:
+ *   for each block row I of the block skyline (left-looking):
+ *     assemble  A[I, fI..I] = (sigma I + J' D J) rows, owner-computes gather straight into shared memory
+ *     for J < I   L[I,J] = (A[I,J] - sum_K L[I,K] L[J,K]') inv(L[J,J])'   two DMMA products per 16x16 block
+ *     J = I       Cholesky of the diagonal block + its inverse (one warp), forward substitution of the rhs
+ *   then the backward substitution over the finished factor -> dx.
+ * L is written to global memory once (block rows are re-read by later rows through L2). */
+__global__ void __launch_bounds__(FT)
+k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 {
 	const int pid = blockIdx.x;
 	if (W.status[pid] != QTOS_RUNNING) return;
 	extern __shared__ double sm[];
-	double *rp = sm;                               /* [max_w][16][16] current block row */
-	double *op = rp + (size_t)max_w * 256;         /* [max_w][16][OPLD] operand panel */
-	double *tmp = op + (size_t)max_w * 16 * OPLD;  /* [16][OPLD] */
-	double *inv = tmp + 16 * OPLD;                 /* [16][OPLD] inverse of a diagonal block */
+	double *rp = sm;                               /* [16][rp_ld]  current block row, row-major over the whole panel */
+	double *zs = rp + 16 * rp_ld;                  /* [npad] rhs -> z -> dx */
+	double *tmp = zs + T.npad;                     /* [16][TLD] */
+	double *inv = tmp + 16 * TLD;                  /* [16][TLD] */
+	double *part = inv + 16 * TLD;                 /* [16] */
 	double *M = WS(M, T.nM), *Dinv = WS(Dinv, T.nb * 256);
-	const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+	const double *Jv = WS(Jv, T.nJ), *DJ = WS(DJ, T.nJ);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int tm = warp >> 1, tn = warp & 1;       /* 8x8 tile of the 16x16 block owned by this warp */
+	const int fr = lane >> 2, fc = lane & 3;       /* fragment row / column */
 	__shared__ int bad;
 	if (tid == 0) bad = 0;
+	for (int i = tid; i < T.npad; i += FT) zs[i] = W.vec[(size_t)pid * T.npad + i];
 	for (int I = 0; I < T.nb; ++I) {
 		const int fI = T.fb[I], wI = I - fI + 1;
-		double *rowg = M + (size_t)T.blkptr[I] * 256;
+		const int rowbase = T.blkptr[I] * 256;
 		__syncthreads();
-		for (int q = tid; q < wI * 256; q += QTOS_THREADS) rp[q] = rowg[q];
+		/* ---- assemble the block row into shared memory ---- */
+		for (int q = tid; q < 16 * wI * 16; q += FT) rp[(q / (wI * 16)) * rp_ld + q % (wI * 16)] = 0.0;
+		__syncthreads();
+		for (int t = T.asm_rowptr[I] + tid; t < T.asm_rowptr[I + 1]; t += FT) {
+			double acc = 0.0, acc2 = 0.0;
+			for (int q = T.asm_ptr[t]; q < T.asm_ptr[t + 1]; ++q) {
+				const uint64_t term = T.asm_terms[q];
+				const double2 *ca = reinterpret_cast<const double2 *>(DJ + (term & 0xfffffu));
+				const double2 *cb = reinterpret_cast<const double2 *>(Jv + ((term >> 20) & 0xfffffu));
+				const int n2 = (int)(term >> 40);
+				for (int rr = 0; rr < n2; ++rr) { const double2 u = ca[rr], v = cb[rr]; acc += u.x * v.x; acc2 += u.y * v.y; }
+			}
+			acc += acc2;
+			const int off = T.asm_off[t] - rowbase;           /* (Jrel, ti, k) block-major */
+			rp[((off >> 4) & 15) * rp_ld + (off >> 8) * 16 + (off & 15)] = acc;
+		}
+		__syncthreads();
+		if (tid < 16) {
+			const int i = I * 16 + tid;
+			double *d = rp + tid * rp_ld + (wI - 1) * 16 + tid;
+			*d = i < T.n_free ? *d + opt.sigma_w : 1.0;
+		}
+		/* ---- off-diagonal blocks ---- */
 		for (int J = fI; J <= I; ++J) {
 			const int K0 = max(fI, T.fb[J]), nK = J - K0;
 			__syncthreads();
+			double c0 = 0.0, c1 = 0.0;
+			const double *a = rp + (tm * 8 + fr) * rp_ld + (K0 - fI) * 16 + fc;
 			if (J < I) {
-				const double *src = M + (size_t)(T.blkptr[J] + K0 - T.fb[J]) * 256;
-				for (int q = tid; q < nK * 256; q += QTOS_THREADS) op[(q >> 4) * OPLD + (q & 15)] = src[q];
-				inv[ti * OPLD + tj] = Dinv[(size_t)J * 256 + tid];
-			} else {
-				for (int q = tid; q < nK * 256; q += QTOS_THREADS) op[(q >> 4) * OPLD + (q & 15)] = rp[(size_t)(K0 - fI) * 256 + q];
-			}
-			__syncthreads();
-			double acc = rp[(size_t)(J - fI) * 256 + ti * 16 + tj];
-			const double *a = rp + (size_t)(K0 - fI) * 256 + ti * 16;
-			const double *b = op + tj * OPLD;
-			for (int K = 0; K < nK; ++K) {
-#pragma unroll
-				for (int k = 0; k < 16; ++k) acc -= a[K * 256 + k] * b[K * 16 * OPLD + k];
-			}
-			tmp[ti * OPLD + tj] = acc;
-			__syncthreads();
-			if (J < I) {
-				/* L[I,J] = S * inv(L[J,J])' */
-				double v = 0.0;
-				for (int k = 0; k <= tj; ++k) v += tmp[ti * OPLD + k] * inv[tj * OPLD + k];
-				rp[(size_t)(J - fI) * 256 + ti * 16 + tj] = v;
-			} else {
-				/* Cholesky of the 16x16 diagonal block in tmp (lower), then its inverse */
-				for (int j = 0; j < 16; ++j) {
-					if (tid == 0) {
-						double d = tmp[j * OPLD + j];
-						if (!(d > 0.0)) { d = 1e-30; bad = 1; }
-						tmp[j * OPLD + j] = sqrt(d);
-					}
-					__syncthreads();
-					if (tj == j && ti > j) tmp[ti * OPLD + j] /= tmp[j * OPLD + j];
-					__syncthreads();
-					if (tj > j && ti >= tj) tmp[ti * OPLD + tj] -= tmp[ti * OPLD + j] * tmp[tj * OPLD + j];
-					__syncthreads();
+				const double *b = M + (size_t)(T.blkptr[J] + K0 - T.fb[J]) * 256 + (tn * 8 + fr) * 16 + fc;
+				for (int K = 0; K < nK; ++K) {
+					const double b0 = b[K * 256], b1 = b[K * 256 + 4], b2 = b[K * 256 + 8], b3 = b[K * 256 + 12];   /* plain loads: written earlier in this kernel */
+					dmma(c0, c1, a[K * 16], b0); dmma(c0, c1, a[K * 16 + 4], b1);
+					dmma(c0, c1, a[K * 16 + 8], b2); dmma(c0, c1, a[K * 16 + 12], b3);
 				}
-				if (tid < 16) {
-					/* column tid of inv(L): forward substitution of e_tid */
-					const int c = tid;
-					double xcol[16];
-					for (int i = 0; i < 16; ++i) {
-						double sacc = i == c ? 1.0 : 0.0;
-						for (int k = c; k < i; ++k) sacc -= tmp[i * OPLD + k] * xcol[k];
-						xcol[i] = i < c ? 0.0 : sacc / tmp[i * OPLD + i];
+			} else {
+				const double *b = rp + (tn * 8 + fr) * rp_ld + (K0 - fI) * 16 + fc;
+				for (int K = 0; K < nK; ++K) {
+					dmma(c0, c1, a[K * 16], b[K * 16]); dmma(c0, c1, a[K * 16 + 4], b[K * 16 + 4]);
+					dmma(c0, c1, a[K * 16 + 8], b[K * 16 + 8]); dmma(c0, c1, a[K * 16 + 12], b[K * 16 + 12]);
+				}
+			}
+			{   /* S = A[I,J] - sum */
+				const double *cA = rp + (tm * 8 + fr) * rp_ld + (J - fI) * 16 + tn * 8 + 2 * fc;
+				double *ct = tmp + (tm * 8 + fr) * TLD + tn * 8 + 2 * fc;
+				ct[0] = cA[0] - c0; ct[1] = cA[1] - c1;
+			}
+			if (J < I) {
+				/* L[I,J] = S * inv(L[J,J])' : second DMMA product, B = inv(L[J,J]) rows from global */
+				const double *bi = Dinv + (size_t)J * 256 + (tn * 8 + fr) * 16 + fc;
+				const double i0 = bi[0], i1 = bi[4], i2 = bi[8], i3 = bi[12];
+				__syncthreads();
+				const double *ta = tmp + (tm * 8 + fr) * TLD + fc;
+				double x0 = 0.0, x1 = 0.0;
+				dmma(x0, x1, ta[0], i0); dmma(x0, x1, ta[4], i1); dmma(x0, x1, ta[8], i2); dmma(x0, x1, ta[12], i3);
+				double *cX = rp + (tm * 8 + fr) * rp_ld + (J - fI) * 16 + tn * 8 + 2 * fc;
+				cX[0] = x0; cX[1] = x1;
+			} else {
+				__syncthreads();
+				if (warp == 0) {
+					/* Cholesky of the 16x16 diagonal block (lower), warp-synchronous, lane = row */
+					for (int j = 0; j < 16; ++j) {
+						__syncwarp();
+						double d = tmp[j * TLD + j];
+						if (!(d > 0.0)) { d = 1e-30; if (lane == 0) bad = 1; }
+						const double rl = rsqrt(d), ljj = d * rl;
+						double lij = 0.0;
+						if (lane < 16 && lane > j) { lij = tmp[lane * TLD + j] * rl; tmp[lane * TLD + j] = lij; }
+						__syncwarp();
+						if (lane == j) { tmp[j * TLD + j] = ljj; part[j] = rl; }
+						if (lane < 16 && lane > j)
+							for (int k = j + 1; k <= lane; ++k) tmp[lane * TLD + k] -= lij * tmp[k * TLD + j];
 					}
-					for (int i = 0; i < 16; ++i) inv[i * OPLD + c] = xcol[i];
+					__syncwarp();
+					if (lane < 16) {
+						/* column `lane` of inv(L) by forward substitution of e_lane */
+						const int c = lane;
+						double xc[16];
+#pragma unroll
+						for (int i = 0; i < 16; ++i) {
+							double sacc = i == c ? 1.0 : 0.0;
+#pragma unroll
+							for (int k = 0; k < 16; ++k) if (k < i && k >= c) sacc -= tmp[i * TLD + k] * xc[k];
+							xc[i] = i < c ? 0.0 : sacc * part[i];
+						}
+#pragma unroll
+						for (int i = 0; i < 16; ++i) inv[i * TLD + c] = xc[i];
+					}
 				}
 				__syncthreads();
-				rp[(size_t)(J - fI) * 256 + ti * 16 + tj] = ti >= tj ? tmp[ti * OPLD + tj] : 0.0;
-				Dinv[(size_t)I * 256 + tid] = inv[ti * OPLD + tj];
+				/* L[I,I] into the panel, inv(L[I,I]) to global for later rows and the backward solve */
+				for (int q = tid; q < 256; q += FT) {
+					const int r = q >> 4, c = q & 15;
+					rp[r * rp_ld + (wI - 1) * 16 + c] = r >= c ? tmp[r * TLD + c] : 0.0;
+					Dinv[(size_t)I * 256 + q] = inv[r * TLD + c];
+				}
 			}
 		}
 		__syncthreads();
-		for (int q = tid; q < wI * 256; q += QTOS_THREADS) rowg[q] = rp[q];
+		/* ---- forward substitution of the rhs with the finished row: z_I = inv(L_II) (b_I - L[I,<I] z) ---- */
+		{
+			const int r = tid >> 3, l8 = tid & 7;
+			double acc = 0.0;
+			const double *row = rp + r * rp_ld;
+			const double *zz = zs + fI * 16;
+			for (int c = l8; c < (wI - 1) * 16; c += 8) acc += row[c] * zz[c];
+			acc += __shfl_xor_sync(0xffffffffu, acc, 4); acc += __shfl_xor_sync(0xffffffffu, acc, 2); acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+			if (l8 == 0) part[r] = zs[I * 16 + r] - acc;
+		}
+		/* ---- store the block row of L (block-major in global memory) ---- */
+		for (int q = tid; q < wI * 256; q += FT) M[(size_t)rowbase + q] = rp[((q >> 4) & 15) * rp_ld + (q >> 8) * 16 + (q & 15)];
+		__syncthreads();
+		if (tid < 16) {
+			double v = 0.0;
+			for (int q = 0; q <= tid; ++q) v += inv[tid * TLD + q] * part[q];
+			zs[I * 16 + tid] = v;
+		}
 	}
 	__syncthreads();
+	/* ---- backward substitution: L' x = z ---- */
+	for (int I = T.nb - 1; I >= 0; --I) {
+		const int fI = T.fb[I];
+		const double *rowg = M + (size_t)T.blkptr[I] * 256;
+		if (tid < 16) {
+			double v = 0.0;
+			const double *iv = Dinv + (size_t)I * 256;
+			for (int q = tid; q < 16; ++q) v += iv[q * 16 + tid] * zs[I * 16 + q];
+			part[tid] = v;
+		}
+		__syncthreads();
+		if (tid < 16) zs[I * 16 + tid] = part[tid];
+		for (int c = tid; c < (I - fI) * 16; c += FT) {
+			const double *blk = rowg + (size_t)(c >> 4) * 256 + (c & 15);
+			double acc = 0.0;
+#pragma unroll
+			for (int q = 0; q < 16; ++q) acc += blk[q * 16] * part[q];
+			zs[fI * 16 + c] -= acc;
+		}
+		__syncthreads();
+	}
+	for (int i = tid; i < T.npad; i += FT) W.vec[(size_t)pid * T.npad + i] = zs[i];
 	if (tid == 0 && bad) W.flags[pid] |= 1;
 }
 
@@ -355,57 +453,13 @@ k_step(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *
 	const int pid = blockIdx.x;
 	if (W.status[pid] != QTOS_RUNNING) return;
 	extern __shared__ double sm[];
-	double *b = sm;                       /* [npad] solution vector (permuted order) */
+	double *b = sm;                       /* [npad] dx from k_factor (permuted order) */
 	double *part = b + T.npad;            /* [256] scratch */
 	double *red = part + 256;             /* [8*32] */
-	const double *M = WS(M, T.nM), *Dinv = WS(Dinv, T.nb * 256), *Jv = WS(Jv, T.nJ);
+	const double *Jv = WS(Jv, T.nJ);
 	const int tid = threadIdx.x;
 	for (int i = tid; i < T.npad; i += blockDim.x) b[i] = W.vec[(size_t)pid * T.npad + i];
 	__syncthreads();
-	/* forward: L z = b */
-	{
-		const int k = tid & 15, ti = tid >> 4;
-		for (int I = 0; I < T.nb; ++I) {
-			const int fI = T.fb[I];
-			const double *rowg = M + (size_t)T.blkptr[I] * 256;
-			double acc = 0.0;
-			for (int J = fI; J < I; ++J) acc += rowg[(size_t)(J - fI) * 256 + ti * 16 + k] * b[J * 16 + k];
-			for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-			if (k == 0) part[ti] = b[I * 16 + ti] - acc;
-			__syncthreads();
-			/* z_I = inv(L_II) * part */
-			if (tid < 16) {
-				double v = 0.0;
-				const double *iv = Dinv + (size_t)I * 256 + tid * 16;
-				for (int q = 0; q <= tid; ++q) v += iv[q] * part[q];
-				b[I * 16 + tid] = v;
-			}
-			__syncthreads();
-		}
-		/* backward: L' x = z */
-		for (int I = T.nb - 1; I >= 0; --I) {
-			const int fI = T.fb[I];
-			const double *rowg = M + (size_t)T.blkptr[I] * 256;
-			if (tid < 16) {
-				double v = 0.0;
-				const double *iv = Dinv + (size_t)I * 256;
-				for (int q = tid; q < 16; ++q) v += iv[q * 16 + tid] * b[I * 16 + q];
-				part[tid] = v;
-			}
-			__syncthreads();
-			if (tid < 16) b[I * 16 + tid] = part[tid];
-			/* b_J -= L[I,J]' x_I : thread per (J,k) */
-			for (int c = tid; c < (I - fI) * 16; c += blockDim.x) {
-				const int Jr = c >> 4, kk = c & 15;
-				const double *blk = rowg + (size_t)Jr * 256 + kk;
-				double acc = 0.0;
-#pragma unroll
-				for (int q = 0; q < 16; ++q) acc += blk[q * 16] * part[q];
-				b[(fI + Jr) * 16 + kk] -= acc;
-			}
-			__syncthreads();
-		}
-	}
 	/* step recovery */
 	const double *r = WS(r, T.m), *Sig = WS(Sig, T.m), *dLb = WS(dL, T.m), *dUb = WS(dU, T.m);
 	double *s = WS(s, T.m), *y = WS(y, T.m), *zL = WS(zL, T.m), *zU = WS(zU, T.m);
@@ -422,7 +476,7 @@ k_step(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *
 		const int rr = i - E.row0;
 		const int16_t *cols = T.elem_cols + E.coloff;
 		double jdx = 0.0;
-		for (int a = 0; a < E.ncols; ++a) jdx += Jv[E.valoff + a * E.nrows + rr] * b[cols[a]];
+		for (int a = 0; a < E.ncols; ++a) jdx += Jv[E.valoff + a * E.ld + rr] * b[cols[a]];
 		if (fl & ROW_EQ) { dy[i] = rho * (jdx + r[i]); v[2] += fabs(r[i]); continue; }
 		const double rsm = dy[i];
 		const double dsi = jdx + (r[i] - s[i]);
@@ -599,7 +653,7 @@ k_eval_dense(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightf
 		const Element &E = T.elems[e];
 		for (int a = 0; a < E.ncols; ++a) {
 			const int var = T.var_of_perm[T.elem_cols[E.coloff + a]];
-			for (int rr = 0; rr < E.nrows; ++rr) J[(size_t)(E.row0 + rr) * T.n_all + var] = Jv[E.valoff + a * E.nrows + rr];
+			for (int rr = 0; rr < E.nrows; ++rr) J[(size_t)(E.row0 + rr) * T.n_all + var] = Jv[E.valoff + a * E.ld + rr];
 		}
 	}
 }

@@ -48,8 +48,9 @@ struct RomSample {                 /* one (foot, time) range-of-motion sample (3
 	int8_t slot[QTOS_ROM_CANON];
 };
 
-struct Element {                   /* dense Jacobian block: rows [row0,row0+nrows) x cols[coloff..+ncols) */
-	int row0, nrows, ncols, valoff, coloff, type;
+struct Element {                   /* dense Jacobian block: rows [row0,row0+nrows) x cols[coloff..+ncols), column-major,
+                                      column stride ld = nrows rounded up to even (zero padded, 16-byte aligned columns) */
+	int row0, nrows, ncols, valoff, coloff, type, ld, pad_;
 };
 
 struct HostTables {
@@ -93,7 +94,7 @@ struct HostTables {
 	std::vector<int>     fb, blkptr;                     /* [nb], [nb+1] (in blocks) */
 	std::vector<int>     diag_off;                       /* [npad] offset of (i,i) in M */
 	std::vector<int>     asm_ptr, asm_off;               /* targets */
-	std::vector<uint32_t> asm_terms;                     /* e<<16 | a<<8 | b */
+	std::vector<uint64_t> asm_terms;                     /* offA (20 bits) | offB << 20 | (ld/2) << 40: value offsets of the two columns */
 	std::vector<int>     jt_ptr;                         /* [npad+1] */
 	std::vector<uint32_t> jt_terms;                      /* e<<8 | a */
 	/* 1 kHz sampler */
