@@ -399,6 +399,21 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 			D.slot[c] = (int8_t)a;
 		}
 		if (cols.size() > 127) return fail("dyn element too wide");
+		D.col0 = (int)H->jcols.size();
+		H->jcols.resize(H->jcols.size() + cols.size());
+		for (size_t a = 0; a < cols.size(); ++a) { JCol &C = H->jcols[D.col0 + a]; memset(&C, 0, sizeof(C)); C.kind = 255; }
+		for (int c = 0; c < QTOS_DYN_CANON; ++c) {
+			if (D.slot[c] < 0) continue;
+			JCol &C = H->jcols[D.col0 + D.slot[c]];
+			const int grp = c < 12 ? 0 : (c < 24 ? 1 : (((c - 24) % 24) < 12 ? 2 : 3));
+			const int foot = c < 24 ? 0 : (c - 24) / 24, q12 = c < 24 ? c % 12 : (c - 24) % 12;
+			const int q = (q12 / 6) * 2 + (q12 % 6) / 3, dim = q12 % 3;
+			if (C.kind != 255 && (C.kind != grp || C.foot != foot || C.dim != dim)) return fail("internal: inconsistent column merge");
+			C.kind = (uint8_t)grp; C.foot = (uint8_t)foot; C.dim = (uint8_t)dim;
+			if (grp < 2) { C.w[0] += D.W[0][q]; C.w[1] += D.W[1][q]; C.w[2] += D.W[2][q]; }
+			else if (grp == 2) C.w[0] += D.mo_w[foot][q];
+			else C.w[0] += D.fo_w[foot][q];
+		}
 		D.elem = new_elem(EL_DYN, row_dyn + 6 * k, 6, cols);
 	}
 	/* base acceleration continuity (ref: spline_acc_constraint.cc:48-80) */
@@ -440,6 +455,17 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 			}
 			const int r0 = row_rom[ee] + 3 * k;
 			for (int d = 0; d < 3; ++d) { H->gl[r0 + d] = sh.nominal[ee][d] - sh.max_dev[d]; H->gu[r0 + d] = sh.nominal[ee][d] + sh.max_dev[d]; }
+			R.col0 = (int)H->jcols.size();
+			H->jcols.resize(H->jcols.size() + cols.size());
+			for (size_t a = 0; a < cols.size(); ++a) { JCol &C = H->jcols[R.col0 + a]; memset(&C, 0, sizeof(C)); C.kind = 255; }
+			for (int c = 0; c < QTOS_ROM_CANON; ++c) {
+				if (R.slot[c] < 0) continue;
+				JCol &C = H->jcols[R.col0 + R.slot[c]];
+				const int grp = c / 12, q12 = c % 12, q = (q12 / 6) * 2 + (q12 % 6) / 3, dim = q12 % 3;
+				if (C.kind != 255 && (C.kind != grp || C.dim != dim)) return fail("internal: inconsistent column merge");
+				C.kind = (uint8_t)grp; C.foot = (uint8_t)ee; C.dim = (uint8_t)dim;
+				C.w[0] += grp < 2 ? R.wp[q] : R.mo_w[q];
+			}
 			R.elem = new_elem(EL_ROM, r0, 3, cols);
 			H->rom.push_back(R);
 		}

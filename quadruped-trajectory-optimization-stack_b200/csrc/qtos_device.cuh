@@ -34,7 +34,7 @@ struct DevTables {
 	const int16_t *perm_of_var, *var_of_perm;
 	const uint8_t *row_flags; const double *gl, *gu; const int *row_elem;
 	const Element *elems; const int16_t *elem_cols; const double *Jconst;
-	const DynSample *dyn; const RomSample *rom;
+	const DynSample *dyn; const RomSample *rom; const JCol *jcols;
 	const int *lin_row, *lin_ptr; const int16_t *lin_col; const double *lin_val;
 	const int *ter_row; const int16_t *ter_var;
 	const int *fb, *blkptr, *diag_off;
@@ -263,10 +263,10 @@ __device__ __forceinline__ void ang_column(const DevTables &T, const DynState &S
 	for (int d = 0; d < 3; ++d) col[d] = a[d] + t[d] + q[d];
 }
 
-/* dense column-major element block of one dynamics sample; sc6 = row scales */
+/* dense column-major element block of one dynamics sample; sc6 = row scales.  Every column is
+ * written exactly once (6 contiguous doubles), driven by the host-compiled column descriptors. */
 __device__ __forceinline__ void dyn_jac(const DevTables &T, const DynSample &D, const DynState &S, const double *sc6, double *blk, int ncols)
 {
-	for (int i = 0; i < 6 * ncols; ++i) blk[i] = 0.0;
 	/* angular rows wrt Euler angle / rate / acceleration */
 	double Gp[9], Gv[9], Ga[9];    /* [r*3+k] */
 	{
@@ -290,40 +290,36 @@ __device__ __forceinline__ void dyn_jac(const DevTables &T, const DynSample &D, 
 			for (int r = 0; r < 3; ++r) Ga[3 * r + k] = col[r];
 		}
 	}
-	double F[3] = {0, 0, 0};
-	for (int i = 0; i < QTOS_NEE; ++i) for (int d = 0; d < 3; ++d) F[d] += S.f[i][d];
-	/* Cross(v)[r][k] */
-#define QX(v, r, k) ((r) == (k) ? 0.0 : (((k) - (r) + 3) % 3 == 1 ? -(v)[3 - (r) - (k)] : (v)[3 - (r) - (k)]))
-	for (int q = 0; q < 4; ++q)                 /* q = side*2 + deriv */
-		for (int k = 0; k < 3; ++k) {
-			const int canon = (q >> 1) * 6 + (q & 1) * 3 + k;
-			int sl = D.slot[canon];
-			if (sl >= 0) {                         /* base-lin */
-				double *c = blk + 6 * sl;
-				for (int r = 0; r < 3; ++r) if (r != k) c[r] += sc6[r] * (-QX(F, r, k) * D.W[0][q]);
-				c[3 + k] += sc6[3 + k] * T.mass * D.W[2][q];
-			}
-			sl = D.slot[12 + canon];
-			if (sl >= 0) {                         /* base-ang */
-				double *c = blk + 6 * sl;
-				for (int r = 0; r < 3; ++r) c[r] += sc6[r] * (Gp[3 * r + k] * D.W[0][q] + Gv[3 * r + k] * D.W[1][q] + Ga[3 * r + k] * D.W[2][q]);
-			}
-			for (int i = 0; i < QTOS_NEE; ++i) {
-				sl = D.slot[24 + i * 24 + canon];
-				if (sl >= 0) {                     /* foot position */
-					double *c = blk + 6 * sl;
-					for (int r = 0; r < 3; ++r) if (r != k) c[r] += sc6[r] * QX(S.f[i], r, k) * D.mo_w[i][q];
-				}
-				sl = D.slot[24 + i * 24 + 12 + canon];
-				if (sl >= 0) {                     /* force */
-					double *c = blk + 6 * sl;
-					const double rr[3] = {S.c[0] - S.p[i][0], S.c[1] - S.p[i][1], S.c[2] - S.p[i][2]};
-					for (int r = 0; r < 3; ++r) if (r != k) c[r] += sc6[r] * QX(rr, r, k) * D.fo_w[i][q];
-					c[3 + k] += sc6[3 + k] * (-D.fo_w[i][q]);
-				}
-			}
+	/* vectors whose cross-product matrix fills the angular rows: -F (base-lin), f_i (foot), c - p_i (force) */
+	double V[9][3];
+	for (int d = 0; d < 3; ++d) {
+		double F = 0.0;
+		for (int i = 0; i < QTOS_NEE; ++i) { F += S.f[i][d]; V[1 + i][d] = S.f[i][d]; V[5 + i][d] = S.c[d] - S.p[i][d]; }
+		V[0][d] = -F;
+	}
+	const double s0 = sc6[0], s1 = sc6[1], s2 = sc6[2], s3 = sc6[3], s4 = sc6[4], s5 = sc6[5];
+	const JCol *cols = T.jcols + D.col0;
+	for (int sl = 0; sl < ncols; ++sl) {
+		const JCol C = cols[sl];
+		const int k = C.dim;
+		double a0, a1, a2, l0 = 0.0, l1 = 0.0, l2 = 0.0;
+		if (C.kind == 1) {
+			a0 = Gp[k] * C.w[0] + Gv[k] * C.w[1] + Ga[k] * C.w[2];
+			a1 = Gp[3 + k] * C.w[0] + Gv[3 + k] * C.w[1] + Ga[3 + k] * C.w[2];
+			a2 = Gp[6 + k] * C.w[0] + Gv[6 + k] * C.w[1] + Ga[6 + k] * C.w[2];
+		} else {
+			/* column k of Cross(v) = (e_k x v) * (-1) = v x e_k */
+			const double *v = V[C.kind == 0 ? 0 : (C.kind == 2 ? 1 + C.foot : 5 + C.foot)];
+			const double w = C.w[0];
+			a0 = (k == 1 ? -v[2] : (k == 2 ? v[1] : 0.0)) * w;
+			a1 = (k == 0 ? v[2] : (k == 2 ? -v[0] : 0.0)) * w;
+			a2 = (k == 0 ? -v[1] : (k == 1 ? v[0] : 0.0)) * w;
+			const double lin = C.kind == 0 ? T.mass * C.w[2] : (C.kind == 3 ? -w : 0.0);
+			l0 = k == 0 ? lin : 0.0; l1 = k == 1 ? lin : 0.0; l2 = k == 2 ? lin : 0.0;
 		}
-#undef QX
+		double2 *o = reinterpret_cast<double2 *>(blk + 6 * sl);
+		o[0] = make_double2(s0 * a0, s1 * a1); o[1] = make_double2(s2 * a2, s3 * l0); o[2] = make_double2(s4 * l1, s5 * l2);
+	}
 }
 
 struct RomState { double c[3], e[3], p[3]; EulerState E; };
@@ -344,9 +340,8 @@ __device__ __forceinline__ void rom_rows(const RomState &S, double *g3)
 	mat3T_vec(S.E.R, r, g3);
 }
 
-__device__ __forceinline__ void rom_jac(const RomSample &R, const RomState &S, const double *sc3, double *blk, int ncols)
+__device__ __forceinline__ void rom_jac(const DevTables &T, const RomSample &R, const RomState &S, const double *sc3, double *blk, int ncols)
 {
-	for (int i = 0; i < 4 * ncols; ++i) blk[i] = 0.0;       /* column stride 4: 3 rows + zero pad */
 	const double rW[3] = {S.p[0] - S.c[0], S.p[1] - S.c[1], S.p[2] - S.c[2]};
 	double Gp[9];
 	for (int k = 0; k < 3; ++k) {
@@ -354,16 +349,17 @@ __device__ __forceinline__ void rom_jac(const RomSample &R, const RomState &S, c
 		euler_dR(S.E, k, dR); mat3T_vec(dR, rW, col);
 		for (int r = 0; r < 3; ++r) Gp[3 * r + k] = col[r];
 	}
-	for (int q = 0; q < 4; ++q)
-		for (int k = 0; k < 3; ++k) {
-			const int canon = (q >> 1) * 6 + (q & 1) * 3 + k;
-			int sl = R.slot[canon];
-			if (sl >= 0) { double *c = blk + 4 * sl; for (int r = 0; r < 3; ++r) c[r] += sc3[r] * (-S.E.R[3 * k + r] * R.wp[q]); }
-			sl = R.slot[12 + canon];
-			if (sl >= 0) { double *c = blk + 4 * sl; for (int r = 0; r < 3; ++r) c[r] += sc3[r] * Gp[3 * r + k] * R.wp[q]; }
-			sl = R.slot[24 + canon];
-			if (sl >= 0) { double *c = blk + 4 * sl; for (int r = 0; r < 3; ++r) c[r] += sc3[r] * S.E.R[3 * k + r] * R.mo_w[q]; }
-		}
+	const JCol *cols = T.jcols + R.col0;
+	for (int sl = 0; sl < ncols; ++sl) {          /* column stride 4: 3 rows + zero pad */
+		const JCol C = cols[sl];
+		const int k = C.dim;
+		const double w = C.kind == 0 ? -C.w[0] : C.w[0];
+		double v0, v1, v2;
+		if (C.kind == 1) { v0 = Gp[k]; v1 = Gp[3 + k]; v2 = Gp[6 + k]; }
+		else { v0 = S.E.R[3 * k]; v1 = S.E.R[3 * k + 1]; v2 = S.E.R[3 * k + 2]; }
+		double2 *o = reinterpret_cast<double2 *>(blk + 4 * sl);
+		o[0] = make_double2(sc3[0] * v0 * w, sc3[1] * v1 * w); o[1] = make_double2(sc3[2] * v2 * w, 0.0);
+	}
 }
 
 /* all constraint values g(x) (unscaled), block-cooperative; no sync inside */
@@ -418,7 +414,7 @@ __device__ __forceinline__ void eval_jac_block(const DevTables &T, const double 
 			const RomSample &R = T.rom[t - T.n_dyn];
 			const Element &E = T.elems[R.elem];
 			RomState S; rom_state(T, R, x, S);
-			rom_jac(R, S, sc + E.row0, Jv + E.valoff, E.ncols);
+			rom_jac(T, R, S, sc + E.row0, Jv + E.valoff, E.ncols);
 		}
 	}
 }

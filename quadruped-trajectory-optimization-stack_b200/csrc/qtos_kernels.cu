@@ -171,7 +171,7 @@ k_jac_rom(DevTables T, DevWork W, int n)
 	const RomSample &R = T.rom[k];
 	const Element &E = T.elems[R.elem];
 	RomState S; rom_state(T, R, WS(x, T.n_all), S);
-	rom_jac(R, S, WS(sc, T.m) + E.row0, WS(Jv, T.nJ) + E.valoff, E.ncols);
+	rom_jac(T, R, S, WS(sc, T.m) + E.row0, WS(Jv, T.nJ) + E.valoff, E.ncols);
 }
 
 /* ------------------------------------------------------------------ k_prepare */

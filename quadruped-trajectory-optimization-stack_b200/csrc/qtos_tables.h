@@ -35,6 +35,7 @@ struct DynSample {                 /* one dynamics sample time (6 rows) */
 	int    fo_id[QTOS_NEE];        /* force polynomial */
 	double fo_w[QTOS_NEE][4];
 	int    elem;
+	int    col0;                   /* first JCol of this sample */
 	int8_t slot[QTOS_DYN_CANON];   /* canonical column -> dense column of the element, -1 = absent */
 };
 
@@ -45,7 +46,13 @@ struct RomSample {                 /* one (foot, time) range-of-motion sample (3
 	int    mo_id;
 	double mo_w[4];
 	int    elem;
+	int    col0;
 	int8_t slot[QTOS_ROM_CANON];
+};
+
+struct JCol {                      /* one dense column of a dynamics / range-of-motion element */
+	uint8_t kind, foot, dim, pad_[5];      /* kind: 0 base-lin, 1 base-ang, 2 foot motion, 3 foot force */
+	double  w[3];                          /* Hermite weights (pos, vel, acc), merged over nodes sharing the variable */
 };
 
 struct Element {                   /* dense Jacobian block: rows [row0,row0+nrows) x cols[coloff..+ncols), column-major,
@@ -85,6 +92,7 @@ struct HostTables {
 	/* evaluation */
 	std::vector<DynSample> dyn;
 	std::vector<RomSample> rom;
+	std::vector<JCol>    jcols;                          /* column descriptors of dyn / rom elements */
 	std::vector<int>     lin_row, lin_ptr;               /* linear rows: g = sum val * x[col] */
 	std::vector<int16_t> lin_col;
 	std::vector<double>  lin_val;
