@@ -580,6 +580,11 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 		if (econst[e].empty()) continue;
 		for (int a = 0; a < E.ncols; ++a) for (int r = 0; r < E.nrows; ++r) H->Jconst[E.valoff + a * E.ld + r] = econst[e][(size_t)a * E.nrows + r];
 	}
+	H->jrow.assign(H->nJ > 0 ? H->nJ : 1, -1);
+	for (size_t e = 0; e < H->elems.size(); ++e) {
+		const Element &E = H->elems[e];
+		for (int a = 0; a < E.ncols; ++a) for (int r = 0; r < E.nrows; ++r) H->jrow[E.valoff + a * E.ld + r] = (int16_t)(E.row0 + r);
+	}
 	if (H->nJ >= (1 << 20)) return fail("Jacobian value array too large for packed assembly terms");
 	{
 		std::vector<std::pair<int, uint64_t>> terms;       /* (M offset, packed term) */

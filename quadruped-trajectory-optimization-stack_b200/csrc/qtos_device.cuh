@@ -33,7 +33,7 @@ struct DevTables {
 	const uint8_t *x0_spline, *x0_deriv, *x0_dim; const int16_t *x0_node; const int8_t *fix_src;
 	const int16_t *perm_of_var, *var_of_perm;
 	const uint8_t *row_flags; const double *gl, *gu; const int *row_elem;
-	const Element *elems; const int16_t *elem_cols; const double *Jconst;
+	const Element *elems; const int16_t *elem_cols; const double *Jconst; const int16_t *jrow;
 	const DynSample *dyn; const RomSample *rom; const JCol *jcols;
 	const int *lin_row, *lin_ptr; const int16_t *lin_col; const double *lin_val;
 	const int *ter_row; const int16_t *ter_var;

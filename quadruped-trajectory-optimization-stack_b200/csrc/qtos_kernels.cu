@@ -249,13 +249,11 @@ k_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 	}
 	__syncthreads();
 	for (int i = threadIdx.x; i < T.npad; i += blockDim.x) vec[i] = i < T.n_free ? -jt_gather(T, Jv, w, i) : 0.0;
-	/* D * J for the assembly gather of k_factor (one element column per thread) */
+	/* D * J for the assembly gather of k_factor: one stored value per thread, fully coalesced */
 	double *DJ = WS(DJ, T.nJ);
-	for (int q = threadIdx.x; q < T.jt_ptr[T.npad]; q += blockDim.x) {
-		const uint32_t t = T.jt_terms[q];
-		const Element &E = T.elems[t >> 8];
-		const int o = E.valoff + (t & 255u) * E.ld;
-		for (int rr = 0; rr < E.ld; ++rr) DJ[o + rr] = rr < E.nrows ? Sig[E.row0 + rr] * Jv[o + rr] : 0.0;
+	for (int q = threadIdx.x; q < T.nJ; q += blockDim.x) {
+		const int row = T.jrow[q];
+		DJ[q] = row >= 0 ? Sig[row] * Jv[q] : 0.0;
 	}
 }
 

@@ -89,6 +89,7 @@ struct HostTables {
 	std::vector<Element> elems;
 	std::vector<int16_t> elem_cols;                      /* permuted free indices */
 	std::vector<double>  Jconst;                         /* [nJ] unscaled values of constant elements */
+	std::vector<int16_t> jrow;                           /* [nJ] constraint row of every stored value, -1 = padding */
 	/* evaluation */
 	std::vector<DynSample> dyn;
 	std::vector<RomSample> rom;
