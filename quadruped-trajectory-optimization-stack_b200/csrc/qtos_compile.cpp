@@ -608,6 +608,35 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 			H->asm_terms.push_back(terms[q].second);
 		}
 		H->asm_ptr.push_back((int)terms.size());
+		/* per block row: hand consecutive threads entries with equally long term lists (less warp divergence
+		 * in the gather); the entry's own offset travels with it, so any order inside a block row is valid */
+		{
+			const int nt = (int)H->asm_off.size();
+			H->asm_rowptr.assign(nb + 1, 0);
+			int tq = 0;
+			for (int I = 0; I < nb; ++I) {
+				H->asm_rowptr[I] = tq;
+				while (tq < nt && H->asm_off[tq] < H->blkptr[I + 1] * NB * NB) ++tq;
+			}
+			H->asm_rowptr[nb] = nt;
+			std::vector<int> order(nt);
+			for (int t = 0; t < nt; ++t) order[t] = t;
+			auto key = [&](int t) {
+				int64_t w = 0;                                   /* total double2 loads of the entry */
+				for (int q = H->asm_ptr[t]; q < H->asm_ptr[t + 1]; ++q) w += (int64_t)(H->asm_terms[q] >> 40);
+				return ((int64_t)(H->asm_ptr[t + 1] - H->asm_ptr[t]) << 20) + w;
+			};
+			for (int I = 0; I < nb; ++I)
+				std::stable_sort(order.begin() + H->asm_rowptr[I], order.begin() + H->asm_rowptr[I + 1], [&](int x, int y) { return key(x) > key(y); });
+			std::vector<int> nptr(1, 0), noff; std::vector<uint64_t> nterms;
+			for (int t : order) {
+				std::vector<uint64_t> tt(H->asm_terms.begin() + H->asm_ptr[t], H->asm_terms.begin() + H->asm_ptr[t + 1]);
+				std::stable_sort(tt.begin(), tt.end(), [](uint64_t x, uint64_t y) { return (x >> 40) > (y >> 40); });
+				nterms.insert(nterms.end(), tt.begin(), tt.end());
+				nptr.push_back((int)nterms.size()); noff.push_back(H->asm_off[t]);
+			}
+			H->asm_ptr = nptr; H->asm_off = noff; H->asm_terms = nterms;
+		}
 		H->jt_ptr.assign(1, 0);
 		for (int i = 0; i < npad; ++i) {
 			H->jt_terms.insert(H->jt_terms.end(), jt[i].begin(), jt[i].end());

@@ -304,12 +304,25 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 		__syncthreads();
 		for (int t = T.asm_rowptr[I] + tid; t < T.asm_rowptr[I + 1]; t += FT) {
 			double acc = 0.0, acc2 = 0.0;
-			for (int q = T.asm_ptr[t]; q < T.asm_ptr[t + 1]; ++q) {
-				const uint64_t term = T.asm_terms[q];
+			const int q1 = T.asm_ptr[t + 1];
+			int q = T.asm_ptr[t];
+			uint64_t term = q < q1 ? __ldg(T.asm_terms + q) : 0ull;
+			while (q < q1) {
 				const double2 *ca = reinterpret_cast<const double2 *>(DJ + (term & 0xfffffu));
 				const double2 *cb = reinterpret_cast<const double2 *>(Jv + ((term >> 20) & 0xfffffu));
 				const int n2 = (int)(term >> 40);
-				for (int rr = 0; rr < n2; ++rr) { const double2 u = ca[rr], v = cb[rr]; acc += u.x * v.x; acc2 += u.y * v.y; }
+				++q;
+				if (q < q1) term = __ldg(T.asm_terms + q);      /* next term in flight while this one is reduced */
+				if (n2 == 3) {
+					const double2 u0 = ca[0], u1 = ca[1], u2 = ca[2], v0 = cb[0], v1 = cb[1], v2 = cb[2];
+					acc += u0.x * v0.x; acc2 += u0.y * v0.y; acc += u1.x * v1.x; acc2 += u1.y * v1.y; acc += u2.x * v2.x; acc2 += u2.y * v2.y;
+				} else if (n2 == 2) {
+					const double2 u0 = ca[0], u1 = ca[1], v0 = cb[0], v1 = cb[1];
+					acc += u0.x * v0.x; acc2 += u0.y * v0.y; acc += u1.x * v1.x; acc2 += u1.y * v1.y;
+				} else {
+					const double2 u0 = ca[0], v0 = cb[0];
+					acc += u0.x * v0.x; acc2 += u0.y * v0.y;
+				}
 			}
 			acc += acc2;
 			const int off = T.asm_off[t] - rowbase;           /* (Jrel, ti, k) block-major */

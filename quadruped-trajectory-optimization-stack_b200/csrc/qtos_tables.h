@@ -102,7 +102,7 @@ struct HostTables {
 	/* condensed KKT structure */
 	std::vector<int>     fb, blkptr;                     /* [nb], [nb+1] (in blocks) */
 	std::vector<int>     diag_off;                       /* [npad] offset of (i,i) in M */
-	std::vector<int>     asm_ptr, asm_off;               /* targets */
+	std::vector<int>     asm_ptr, asm_off, asm_rowptr;   /* targets (entries of M with contributions), first target of every block row */
 	std::vector<uint64_t> asm_terms;                     /* offA (20 bits) | offB << 20 | (ld/2) << 40: value offsets of the two columns */
 	std::vector<int>     jt_ptr;                         /* [npad+1] */
 	std::vector<uint32_t> jt_terms;                      /* e<<8 | a */
