@@ -563,6 +563,35 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 	H->diag_off.resize(npad);
 	for (int i = 0; i < npad; ++i) H->diag_off[i] = m_off(i, i);
 
+	/* ---- element columns in permuted order (assembly visits a prefix of an element's columns) ---- */
+	{
+		std::vector<int> jc0(ecols.size(), -1);
+		for (auto &D : H->dyn) jc0[D.elem] = D.col0;
+		for (auto &R : H->rom) jc0[R.elem] = R.col0;
+		for (size_t e = 0; e < ecols.size(); ++e) {
+			const int nc = (int)ecols[e].size(), nr = H->elems[e].nrows;
+			std::vector<int> sig(nc), inv(nc);
+			for (int a = 0; a < nc; ++a) sig[a] = a;
+			std::stable_sort(sig.begin(), sig.end(), [&](int a, int b) { return pos[ecols[e][a]] < pos[ecols[e][b]]; });
+			for (int a = 0; a < nc; ++a) inv[sig[a]] = a;
+			std::vector<int> nc_(nc);
+			for (int a = 0; a < nc; ++a) nc_[a] = ecols[e][sig[a]];
+			ecols[e] = nc_;
+			if (!econst[e].empty()) {
+				std::vector<double> v(econst[e].size());
+				for (int a = 0; a < nc; ++a) for (int r = 0; r < nr; ++r) v[(size_t)a * nr + r] = econst[e][(size_t)sig[a] * nr + r];
+				econst[e] = v;
+			}
+			if (jc0[e] >= 0) {
+				std::vector<JCol> v(nc);
+				for (int a = 0; a < nc; ++a) v[a] = H->jcols[jc0[e] + sig[a]];
+				for (int a = 0; a < nc; ++a) H->jcols[jc0[e] + a] = v[a];
+			}
+			if (H->elems[e].type == EL_DYN) { for (auto &D : H->dyn) if (D.elem == (int)e) for (auto &sl : D.slot) if (sl >= 0) sl = (int8_t)inv[sl]; }
+			if (H->elems[e].type == EL_ROM) { for (auto &R : H->rom) if (R.elem == (int)e) for (auto &sl : R.slot) if (sl >= 0) sl = (int8_t)inv[sl]; }
+		}
+	}
+
 	/* ---- element storage, gather lists ---- */
 	int valoff = 0; H->nnz_jac = 0;
 	for (size_t e = 0; e < H->elems.size(); ++e) {
@@ -587,55 +616,44 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 	}
 	if (H->nJ >= (1 << 20)) return fail("Jacobian value array too large for packed assembly terms");
 	{
-		std::vector<std::pair<int, uint64_t>> terms;       /* (M offset, packed term) */
 		std::vector<std::vector<uint32_t>> jt(npad);
-		for (size_t e = 0; e < H->elems.size(); ++e) {
-			const std::vector<int> &c = ecols[e];
-			for (size_t a = 0; a < c.size(); ++a) {
-				jt[pos[c[a]]].push_back((uint32_t)(e << 8) | (uint32_t)a);
-				for (size_t b = 0; b < c.size(); ++b) {
-					int pa = pos[c[a]], pb = pos[c[b]];
-					if (pa < pb || (pa == pb && a != b)) continue;
+		for (size_t e = 0; e < H->elems.size(); ++e)
+			for (size_t a = 0; a < ecols[e].size(); ++a) jt[pos[ecols[e][a]]].push_back((uint32_t)(e << 8) | (uint32_t)a);
+		/* assembly lists: warp w of the factor kernel owns panel rows i % 4 == w of every block row */
+		H->as_ptr.assign(1, 0); H->ag_ptr.assign(1, 0); H->as_col.clear(); H->ag.clear();
+		H->as_max = H->ag_max = 0; H->asm_terms_total = 0;
+		for (int I = 0; I < nb; ++I) {
+			const int s0 = (int)H->as_col.size(), g0 = (int)H->ag.size();
+			for (int w = 0; w < 4; ++w) {
+				for (size_t e = 0; e < H->elems.size(); ++e) {
 					const Element &E = H->elems[e];
-					terms.push_back({m_off(pa, pb), (uint64_t)(E.valoff + a * E.ld) | ((uint64_t)(E.valoff + b * E.ld) << 20) | ((uint64_t)(E.ld / 2) << 40)});
+					const std::vector<int> &c = ecols[e];
+					const int es = (int)H->as_col.size() - s0;
+					int ne = 0, pa_max = -1;
+					for (size_t a = 0; a < c.size(); ++a) {
+						const int pa = pos[c[a]];
+						if (pa / NB != I || (pa % NB) % 4 != w) continue;
+						AsmCol A; A.voff = E.valoff + (int)a * E.ld; A.row0 = (int16_t)E.row0; A.nrows = (uint8_t)E.nrows; A.i = (uint8_t)(pa % NB);
+						H->as_col.push_back(A); ++ne; pa_max = std::max(pa_max, pa);
+						for (size_t b = 0; b < c.size(); ++b) if (pos[c[b]] <= pa) H->asm_terms_total++;
+					}
+					if (!ne) continue;
+					/* columns are sorted by permuted index: only chunks that start at or below the largest row matter */
+					for (int c0 = 0; c0 < (int)c.size() && pos[c[c0]] <= pa_max; c0 += 32) {
+						int nl = 0;
+						while (nl < 32 && c0 + nl < (int)c.size() && pos[c[c0 + nl]] <= pa_max) ++nl;
+						AsmGroup G; memset(&G, 0, sizeof(G));
+						G.boff = E.valoff + c0 * E.ld; G.coloff = E.coloff + c0; G.es = (uint16_t)es; G.ne = (uint16_t)ne;
+						G.n2 = (uint8_t)(E.ld / 2); G.nl = (uint8_t)nl;
+						H->ag.push_back(G);
+					}
 				}
+				H->ag_ptr.push_back((int)H->ag.size());
 			}
-		}
-		std::stable_sort(terms.begin(), terms.end(), [](const std::pair<int, uint64_t> &x, const std::pair<int, uint64_t> &y) { return x.first < y.first; });
-		H->asm_ptr.clear(); H->asm_off.clear(); H->asm_terms.clear();
-		for (size_t q = 0; q < terms.size(); ++q) {
-			if (q == 0 || terms[q].first != terms[q - 1].first) { H->asm_ptr.push_back((int)q); H->asm_off.push_back(terms[q].first); }
-			H->asm_terms.push_back(terms[q].second);
-		}
-		H->asm_ptr.push_back((int)terms.size());
-		/* per block row: hand consecutive threads entries with equally long term lists (less warp divergence
-		 * in the gather); the entry's own offset travels with it, so any order inside a block row is valid */
-		{
-			const int nt = (int)H->asm_off.size();
-			H->asm_rowptr.assign(nb + 1, 0);
-			int tq = 0;
-			for (int I = 0; I < nb; ++I) {
-				H->asm_rowptr[I] = tq;
-				while (tq < nt && H->asm_off[tq] < H->blkptr[I + 1] * NB * NB) ++tq;
-			}
-			H->asm_rowptr[nb] = nt;
-			std::vector<int> order(nt);
-			for (int t = 0; t < nt; ++t) order[t] = t;
-			auto key = [&](int t) {
-				int64_t w = 0;                                   /* total double2 loads of the entry */
-				for (int q = H->asm_ptr[t]; q < H->asm_ptr[t + 1]; ++q) w += (int64_t)(H->asm_terms[q] >> 40);
-				return ((int64_t)(H->asm_ptr[t + 1] - H->asm_ptr[t]) << 20) + w;
-			};
-			for (int I = 0; I < nb; ++I)
-				std::stable_sort(order.begin() + H->asm_rowptr[I], order.begin() + H->asm_rowptr[I + 1], [&](int x, int y) { return key(x) > key(y); });
-			std::vector<int> nptr(1, 0), noff; std::vector<uint64_t> nterms;
-			for (int t : order) {
-				std::vector<uint64_t> tt(H->asm_terms.begin() + H->asm_ptr[t], H->asm_terms.begin() + H->asm_ptr[t + 1]);
-				std::stable_sort(tt.begin(), tt.end(), [](uint64_t x, uint64_t y) { return (x >> 40) > (y >> 40); });
-				nterms.insert(nterms.end(), tt.begin(), tt.end());
-				nptr.push_back((int)nterms.size()); noff.push_back(H->asm_off[t]);
-			}
-			H->asm_ptr = nptr; H->asm_off = noff; H->asm_terms = nterms;
+			H->as_ptr.push_back((int)H->as_col.size());
+			H->as_max = std::max(H->as_max, (int)H->as_col.size() - s0);
+			H->ag_max = std::max(H->ag_max, (int)H->ag.size() - g0);
+			if ((int)H->as_col.size() - s0 > 65535) return fail("assembly: too many staged columns in a block row");
 		}
 		H->jt_ptr.assign(1, 0);
 		for (int i = 0; i < npad; ++i) {

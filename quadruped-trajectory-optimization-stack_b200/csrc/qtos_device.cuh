@@ -25,7 +25,7 @@ struct DevHeightfield { const double *h; int nx, ny; double res; };
 struct DevTables {
 	/* dims */
 	int n_all, n_free, npad, m, n_eq, n_ineq, n_bounds, n_dyn, n_rom4, n_lin, n_ter, n_elem;
-	int nJ, nb, nM, n_targets, n_chunks, csv_rows, max_nodes;
+	int nJ, nb, nM, as_max, csv_rows, max_nodes;
 	int n_nodes[10], var_off[11];
 	double T, mass, Ib[9], grav;
 	/* tables */
@@ -38,7 +38,7 @@ struct DevTables {
 	const int *lin_row, *lin_ptr; const int16_t *lin_col; const double *lin_val;
 	const int *ter_row; const int16_t *ter_var;
 	const int *fb, *blkptr, *diag_off;
-	const int *asm_ptr, *asm_off, *asm_chunk, *asm_rowptr; const uint64_t *asm_terms;
+	const int *as_ptr, *ag_ptr; const AsmCol *as_col; const AsmGroup *ag;
 	const int *jt_ptr; const uint32_t *jt_terms;
 	const double *csv_t, *csv_tl; const uint8_t *csv_id;
 	const double *dur; int dur_ld;          /* [10][dur_ld] */
@@ -53,7 +53,6 @@ struct DevWork {
 	double *P;                              /* [32] */
 	double *scal;                           /* [16]: 0 mu, 1 nu, 2 sd, 3 sc_, 4 dual_inf, 5 theta_inf, ... */
 	double *Jv;                             /* [nJ] */
-	double *DJ;                             /* [nJ] D * J (row weights folded in) for the assembly gather */
 	double *M;                              /* [nM] */
 	double *Dinv;                           /* [nb*256] inverses of the diagonal blocks of L */
 	int *status, *iters, *flags;            /* [1] each */

@@ -249,12 +249,6 @@ k_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 	}
 	__syncthreads();
 	for (int i = threadIdx.x; i < T.npad; i += blockDim.x) vec[i] = i < T.n_free ? -jt_gather(T, Jv, w, i) : 0.0;
-	/* D * J for the assembly gather of k_factor: one stored value per thread, fully coalesced */
-	double *DJ = WS(DJ, T.nJ);
-	for (int q = threadIdx.x; q < T.nJ; q += blockDim.x) {
-		const int row = T.jrow[q];
-		DJ[q] = row >= 0 ? Sig[row] * Jv[q] : 0.0;
-	}
 }
 
 /* ------------------------------------------------------------------ k_factor */
@@ -287,8 +281,10 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 	double *tmp = zs + T.npad;                     /* [16][TLD] */
 	double *inv = tmp + 16 * TLD;                  /* [16][TLD] */
 	double *part = inv + 16 * TLD;                 /* [16] */
+	double *As = part + 16;                        /* [as_max][6] staged D J columns of the block row */
+	uint8_t *ai = reinterpret_cast<uint8_t *>(As + 6 * T.as_max);   /* [as_max] their panel rows */
 	double *M = WS(M, T.nM), *Dinv = WS(Dinv, T.nb * 256);
-	const double *Jv = WS(Jv, T.nJ), *DJ = WS(DJ, T.nJ);
+	const double *Jv = WS(Jv, T.nJ), *Sig = WS(Sig, T.m);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int tm = warp >> 1, tn = warp & 1;       /* 8x8 tile of the 16x16 block owned by this warp */
 	const int fr = lane >> 2, fc = lane & 3;       /* fragment row / column */
@@ -299,34 +295,58 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 		const int fI = T.fb[I], wI = I - fI + 1;
 		const int rowbase = T.blkptr[I] * 256;
 		__syncthreads();
-		/* ---- assemble the block row into shared memory ---- */
-		for (int q = tid; q < 16 * wI * 16; q += FT) rp[(q / (wI * 16)) * rp_ld + q % (wI * 16)] = 0.0;
-		__syncthreads();
-		for (int t = T.asm_rowptr[I] + tid; t < T.asm_rowptr[I + 1]; t += FT) {
-			double acc = 0.0, acc2 = 0.0;
-			const int q1 = T.asm_ptr[t + 1];
-			int q = T.asm_ptr[t];
-			uint64_t term = q < q1 ? __ldg(T.asm_terms + q) : 0ull;
-			while (q < q1) {
-				const double2 *ca = reinterpret_cast<const double2 *>(DJ + (term & 0xfffffu));
-				const double2 *cb = reinterpret_cast<const double2 *>(Jv + ((term >> 20) & 0xfffffu));
-				const int n2 = (int)(term >> 40);
-				++q;
-				if (q < q1) term = __ldg(T.asm_terms + q);      /* next term in flight while this one is reduced */
-				if (n2 == 3) {
-					const double2 u0 = ca[0], u1 = ca[1], u2 = ca[2], v0 = cb[0], v1 = cb[1], v2 = cb[2];
-					acc += u0.x * v0.x; acc2 += u0.y * v0.y; acc += u1.x * v1.x; acc2 += u1.y * v1.y; acc += u2.x * v2.x; acc2 += u2.y * v2.y;
-				} else if (n2 == 2) {
-					const double2 u0 = ca[0], u1 = ca[1], v0 = cb[0], v1 = cb[1];
-					acc += u0.x * v0.x; acc2 += u0.y * v0.y; acc += u1.x * v1.x; acc2 += u1.y * v1.y;
-				} else {
-					const double2 u0 = ca[0], v0 = cb[0];
-					acc += u0.x * v0.x; acc2 += u0.y * v0.y;
-				}
+		/* ---- assemble the block row into shared memory ----
+		 * stage A = D J[:, a] for every (element, column a) of this block row, then each warp visits its
+		 * (element, 32-column chunk) groups: lane = column b, panel[i(a)][perm(b)] += A . J[:, b].
+		 * Warp w owns the panel rows i % 4 == w, so the sums are race-free and in a fixed order. */
+		{
+			const int s0 = T.as_ptr[I], nst = T.as_ptr[I + 1] - s0;
+			for (int q = tid; q < nst * 6; q += FT) {
+				const int k = q / 6, r = q - 6 * k;
+				const AsmCol C = T.as_col[s0 + k];
+				As[q] = r < C.nrows ? Sig[C.row0 + r] * Jv[C.voff + r] : 0.0;
+				if (r == 0) ai[k] = C.i;
 			}
-			acc += acc2;
-			const int off = T.asm_off[t] - rowbase;           /* (Jrel, ti, k) block-major */
-			rp[((off >> 4) & 15) * rp_ld + (off >> 8) * 16 + (off & 15)] = acc;
+			for (int q = tid; q < 16 * wI * 16; q += FT) rp[(q / (wI * 16)) * rp_ld + q % (wI * 16)] = 0.0;
+		}
+		__syncthreads();
+		{
+			int g = T.ag_ptr[I * 4 + warp];
+			const int g1 = T.ag_ptr[I * 4 + warp + 1];
+			const int4 *ag = reinterpret_cast<const int4 *>(T.ag);
+			const int jbase = fI * 16;
+			int4 d0 = g < g1 ? __ldg(ag + g) : make_int4(0, 0, 0, 0);
+			int4 d1 = g + 1 < g1 ? __ldg(ag + g + 1) : make_int4(0, 0, 0, 0);
+			double2 b0, b1, b2; int pb;
+			auto load_b = [&](const int4 &d, double2 &c0, double2 &c1, double2 &c2, int &p) {
+				const int n2 = d.w & 255, nl = (d.w >> 8) & 255;
+				c0 = c1 = c2 = make_double2(0.0, 0.0); p = 0x7fffffff;
+				if (lane < nl) {
+					const double2 *src = reinterpret_cast<const double2 *>(Jv + d.x + lane * 2 * n2);
+					c0 = src[0];
+					if (n2 > 1) c1 = src[1];
+					if (n2 > 2) c2 = src[2];
+					p = __ldg(T.elem_cols + d.y + lane);
+				}
+			};
+			if (g < g1) load_b(d0, b0, b1, b2, pb);
+			for (; g < g1; ++g) {
+				const int4 d2 = g + 2 < g1 ? __ldg(ag + g + 2) : make_int4(0, 0, 0, 0);
+				double2 nb0, nb1, nb2; int npb;
+				if (g + 1 < g1) load_b(d1, nb0, nb1, nb2, npb);
+				const int es = d0.z & 0xffff, ne = (d0.z >> 16) & 0xffff, n2 = d0.w & 255;
+				const int col = pb - jbase;
+				for (int k = es; k < es + ne; ++k) {
+					const double2 *A = reinterpret_cast<const double2 *>(As + 6 * k);
+					const int i = ai[k];
+					const double2 a0 = A[0];
+					double acc = a0.x * b0.x, acc2 = a0.y * b0.y;
+					if (n2 > 1) { const double2 a1 = A[1]; acc += a1.x * b1.x; acc2 += a1.y * b1.y; }
+					if (n2 > 2) { const double2 a2 = A[2]; acc += a2.x * b2.x; acc2 += a2.y * b2.y; }
+					if (pb <= I * 16 + i) rp[i * rp_ld + col] += acc + acc2;
+				}
+				d0 = d1; d1 = d2; b0 = nb0; b1 = nb1; b2 = nb2; pb = npb;
+			}
 		}
 		__syncthreads();
 		if (tid < 16) {

@@ -60,6 +60,19 @@ struct Element {                   /* dense Jacobian block: rows [row0,row0+nrow
 	int row0, nrows, ncols, valoff, coloff, type, ld, pad_;
 };
 
+struct AsmCol {                    /* one staged column (element e, local column a) of a block row's assembly */
+	int      voff;                 /* offset of the column's values in Jv */
+	int16_t  row0;                 /* first constraint row of the element */
+	uint8_t  nrows, i;             /* rows of the element; panel row (variable perm % 16) the column adds into */
+};
+
+struct AsmGroup {                  /* one (element, chunk of <= 32 columns) visit of one warp during assembly */
+	int      boff;                 /* value offset of the chunk's first column */
+	int      coloff;               /* offset of the chunk's first column in elem_cols */
+	uint16_t es, ne;               /* staged columns [es, es+ne) of the block row pair with this chunk */
+	uint8_t  n2, nl, pad_[2];      /* column stride / 2; columns in the chunk */
+};
+
 struct HostTables {
 	qtos_shape shape;
 	/* dimensions */
@@ -102,8 +115,15 @@ struct HostTables {
 	/* condensed KKT structure */
 	std::vector<int>     fb, blkptr;                     /* [nb], [nb+1] (in blocks) */
 	std::vector<int>     diag_off;                       /* [npad] offset of (i,i) in M */
-	std::vector<int>     asm_ptr, asm_off, asm_rowptr;   /* targets (entries of M with contributions), first target of every block row */
-	std::vector<uint64_t> asm_terms;                     /* offA (20 bits) | offB << 20 | (ld/2) << 40: value offsets of the two columns */
+	/* assembly of sigma I + J' D J, one block row at a time (owner-computes: warp w owns panel rows i % 4 == w):
+	 * staged columns A = D J[:, a] of every (element, column a in the block row), then per warp a list of
+	 * (element, 32-column chunk) groups whose columns b are the lanes: panel[i(a)][perm(b)] += A . J[:, b] */
+	std::vector<int>     as_ptr;                         /* [nb+1] first staged column of every block row */
+	std::vector<AsmCol>  as_col;
+	std::vector<int>     ag_ptr;                         /* [nb*4+1] first group of (block row, warp) */
+	std::vector<AsmGroup> ag;
+	int as_max = 0, ag_max = 0;                          /* most staged columns / groups of one block row */
+	long long asm_terms_total = 0;                       /* (a, b) pairs summed = scalar dot products per assembly */
 	std::vector<int>     jt_ptr;                         /* [npad+1] */
 	std::vector<uint32_t> jt_terms;                      /* e<<8 | a */
 	/* 1 kHz sampler */
