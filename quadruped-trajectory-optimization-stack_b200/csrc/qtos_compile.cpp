@@ -619,41 +619,47 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 		std::vector<std::vector<uint32_t>> jt(npad);
 		for (size_t e = 0; e < H->elems.size(); ++e)
 			for (size_t a = 0; a < ecols[e].size(); ++a) jt[pos[ecols[e][a]]].push_back((uint32_t)(e << 8) | (uint32_t)a);
-		/* assembly lists: warp w of the factor kernel owns panel rows i % 4 == w of every block row */
-		H->as_ptr.assign(1, 0); H->ag_ptr.assign(1, 0); H->as_col.clear(); H->ag.clear();
-		H->as_max = H->ag_max = 0; H->asm_terms_total = 0;
+		/* assembly lists: warp w of the factor kernel owns panel rows i % 4 == w of every block row and walks a
+		 * flat stream of terms (element e, row column a, column b <= a in permuted order), 32 per step, one per
+		 * lane.  Inside a step all targets are distinct (steps are closed early with no-op terms otherwise),
+		 * so panel[i][perm(b)] += A_a . J_b is race-free and its summation order is fixed. */
+		int max_w = 0;
+		for (int I = 0; I < nb; ++I) max_w = std::max(max_w, I - H->fb[I] + 1);
+		H->max_w = max_w; H->rp_ld = max_w * NB + 4;
+		if (16 * H->rp_ld >= (1 << 13)) return fail("assembly: panel too wide for packed terms");
+		H->as_ptr.assign(1, 0); H->at_ptr.assign(1, 0); H->as_col.clear(); H->at.clear();
+		H->as_max = 0; H->asm_terms_total = 0;
 		for (int I = 0; I < nb; ++I) {
-			const int s0 = (int)H->as_col.size(), g0 = (int)H->ag.size();
+			const int s0 = (int)H->as_col.size();
 			for (int w = 0; w < 4; ++w) {
+				std::set<int> in_step;
+				auto close_step = [&]() { while (H->at.size() % 32) H->at.push_back(0u); in_step.clear(); };
 				for (size_t e = 0; e < H->elems.size(); ++e) {
 					const Element &E = H->elems[e];
 					const std::vector<int> &c = ecols[e];
-					const int es = (int)H->as_col.size() - s0;
-					int ne = 0, pa_max = -1;
 					for (size_t a = 0; a < c.size(); ++a) {
 						const int pa = pos[c[a]];
 						if (pa / NB != I || (pa % NB) % 4 != w) continue;
+						const int k = (int)H->as_col.size() - s0;
+						if (k > 511) return fail("assembly: too many staged columns in a block row");
 						AsmCol A; A.voff = E.valoff + (int)a * E.ld; A.row0 = (int16_t)E.row0; A.nrows = (uint8_t)E.nrows; A.i = (uint8_t)(pa % NB);
-						H->as_col.push_back(A); ++ne; pa_max = std::max(pa_max, pa);
-						for (size_t b = 0; b < c.size(); ++b) if (pos[c[b]] <= pa) H->asm_terms_total++;
-					}
-					if (!ne) continue;
-					/* columns are sorted by permuted index: only chunks that start at or below the largest row matter */
-					for (int c0 = 0; c0 < (int)c.size() && pos[c[c0]] <= pa_max; c0 += 32) {
-						int nl = 0;
-						while (nl < 32 && c0 + nl < (int)c.size() && pos[c[c0 + nl]] <= pa_max) ++nl;
-						AsmGroup G; memset(&G, 0, sizeof(G));
-						G.boff = E.valoff + c0 * E.ld; G.coloff = E.coloff + c0; G.es = (uint16_t)es; G.ne = (uint16_t)ne;
-						G.n2 = (uint8_t)(E.ld / 2); G.nl = (uint8_t)nl;
-						H->ag.push_back(G);
+						H->as_col.push_back(A);
+						for (size_t b = 0; b <= a; ++b) {        /* columns are sorted: pos[c[b]] <= pa */
+							const int off = (pa % NB) * H->rp_ld + pos[c[b]] - H->fb[I] * NB;
+							if (a - b > 127) return fail("assembly: element too wide for packed terms");
+							if (in_step.count(off)) close_step();
+							in_step.insert(off);
+							H->at.push_back((uint32_t)(E.ld / 2) | ((uint32_t)k << 2) | ((uint32_t)(a - b) << 11) | ((uint32_t)off << 18));
+							H->asm_terms_total++;
+							if (H->at.size() % 32 == 0) in_step.clear();
+						}
 					}
 				}
-				H->ag_ptr.push_back((int)H->ag.size());
+				close_step();
+				H->at_ptr.push_back((int)H->at.size());
 			}
 			H->as_ptr.push_back((int)H->as_col.size());
 			H->as_max = std::max(H->as_max, (int)H->as_col.size() - s0);
-			H->ag_max = std::max(H->ag_max, (int)H->ag.size() - g0);
-			if ((int)H->as_col.size() - s0 > 65535) return fail("assembly: too many staged columns in a block row");
 		}
 		H->jt_ptr.assign(1, 0);
 		for (int i = 0; i < npad; ++i) {

@@ -38,7 +38,7 @@ struct DevTables {
 	const int *lin_row, *lin_ptr; const int16_t *lin_col; const double *lin_val;
 	const int *ter_row; const int16_t *ter_var;
 	const int *fb, *blkptr, *diag_off;
-	const int *as_ptr, *ag_ptr; const AsmCol *as_col; const AsmGroup *ag;
+	const int *as_ptr, *at_ptr; const AsmCol *as_col; const uint32_t *at;
 	const int *jt_ptr; const uint32_t *jt_terms;
 	const double *csv_t, *csv_tl; const uint8_t *csv_id;
 	const double *dur; int dur_ld;          /* [10][dur_ld] */

@@ -282,7 +282,7 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 	double *inv = tmp + 16 * TLD;                  /* [16][TLD] */
 	double *part = inv + 16 * TLD;                 /* [16] */
 	double *As = part + 16;                        /* [as_max][6] staged D J columns of the block row */
-	uint8_t *ai = reinterpret_cast<uint8_t *>(As + 6 * T.as_max);   /* [as_max] their panel rows */
+	int *av = reinterpret_cast<int *>(As + 6 * T.as_max);         /* [as_max] value offsets of the staged columns */
 	double *M = WS(M, T.nM), *Dinv = WS(Dinv, T.nb * 256);
 	const double *Jv = WS(Jv, T.nJ), *Sig = WS(Sig, T.m);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -296,56 +296,52 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 		const int rowbase = T.blkptr[I] * 256;
 		__syncthreads();
 		/* ---- assemble the block row into shared memory ----
-		 * stage A = D J[:, a] for every (element, column a) of this block row, then each warp visits its
-		 * (element, 32-column chunk) groups: lane = column b, panel[i(a)][perm(b)] += A . J[:, b].
-		 * Warp w owns the panel rows i % 4 == w, so the sums are race-free and in a fixed order. */
+		 * stage A = D J[:, a] for every (element, column a) of this block row, then every warp walks its flat
+		 * term stream, one term per lane: panel[i(a)][perm(b)] += A . J[:, b].  Warp w owns the panel rows
+		 * i % 4 == w and the targets inside one step are distinct, so the sums are race-free and ordered. */
 		{
 			const int s0 = T.as_ptr[I], nst = T.as_ptr[I + 1] - s0;
 			for (int q = tid; q < nst * 6; q += FT) {
 				const int k = q / 6, r = q - 6 * k;
 				const AsmCol C = T.as_col[s0 + k];
 				As[q] = r < C.nrows ? Sig[C.row0 + r] * Jv[C.voff + r] : 0.0;
-				if (r == 0) ai[k] = C.i;
+				if (r == 0) av[k] = C.voff;
 			}
-			for (int q = tid; q < 16 * wI * 16; q += FT) rp[(q / (wI * 16)) * rp_ld + q % (wI * 16)] = 0.0;
+			const int wcols = wI * 16;
+			for (int r = warp; r < 16; r += FT / 32)
+				for (int c = lane; c < wcols; c += 32) rp[r * rp_ld + c] = 0.0;
 		}
 		__syncthreads();
 		{
-			int g = T.ag_ptr[I * 4 + warp];
-			const int g1 = T.ag_ptr[I * 4 + warp + 1];
-			const int4 *ag = reinterpret_cast<const int4 *>(T.ag);
-			const int jbase = fI * 16;
-			int4 d0 = g < g1 ? __ldg(ag + g) : make_int4(0, 0, 0, 0);
-			int4 d1 = g + 1 < g1 ? __ldg(ag + g + 1) : make_int4(0, 0, 0, 0);
-			double2 b0, b1, b2; int pb;
-			auto load_b = [&](const int4 &d, double2 &c0, double2 &c1, double2 &c2, int &p) {
-				const int n2 = d.w & 255, nl = (d.w >> 8) & 255;
-				c0 = c1 = c2 = make_double2(0.0, 0.0); p = 0x7fffffff;
-				if (lane < nl) {
-					const double2 *src = reinterpret_cast<const double2 *>(Jv + d.x + lane * 2 * n2);
-					c0 = src[0];
-					if (n2 > 1) c1 = src[1];
-					if (n2 > 2) c2 = src[2];
-					p = __ldg(T.elem_cols + d.y + lane);
+			const int t0 = T.at_ptr[I * 4 + warp], t1 = T.at_ptr[I * 4 + warp + 1];
+			/* four steps in flight: descriptors, then the J columns of all four, then the sums in step order */
+			for (int t = t0 + lane; t < t1; t += 128) {
+				uint32_t d[4];
+				double2 b[4][3];
+#pragma unroll
+				for (int u = 0; u < 4; ++u) d[u] = t + 32 * u < t1 ? __ldg(T.at + t + 32 * u) : 0u;
+#pragma unroll
+				for (int u = 0; u < 4; ++u) {
+					const int n2 = d[u] & 3;
+					b[u][0] = b[u][1] = b[u][2] = make_double2(0.0, 0.0);
+					if (n2) {
+						const double2 *B = reinterpret_cast<const double2 *>(Jv + av[(d[u] >> 2) & 511]) - ((d[u] >> 11) & 127) * n2;
+						b[u][0] = B[0];
+						if (n2 > 1) b[u][1] = B[1];
+						if (n2 > 2) b[u][2] = B[2];
+					}
 				}
-			};
-			if (g < g1) load_b(d0, b0, b1, b2, pb);
-			for (; g < g1; ++g) {
-				const int4 d2 = g + 2 < g1 ? __ldg(ag + g + 2) : make_int4(0, 0, 0, 0);
-				double2 nb0, nb1, nb2; int npb;
-				if (g + 1 < g1) load_b(d1, nb0, nb1, nb2, npb);
-				const int es = d0.z & 0xffff, ne = (d0.z >> 16) & 0xffff, n2 = d0.w & 255;
-				const int col = pb - jbase;
-				for (int k = es; k < es + ne; ++k) {
-					const double2 *A = reinterpret_cast<const double2 *>(As + 6 * k);
-					const int i = ai[k];
-					const double2 a0 = A[0];
-					double acc = a0.x * b0.x, acc2 = a0.y * b0.y;
-					if (n2 > 1) { const double2 a1 = A[1]; acc += a1.x * b1.x; acc2 += a1.y * b1.y; }
-					if (n2 > 2) { const double2 a2 = A[2]; acc += a2.x * b2.x; acc2 += a2.y * b2.y; }
-					if (pb <= I * 16 + i) rp[i * rp_ld + col] += acc + acc2;
+#pragma unroll
+				for (int u = 0; u < 4; ++u) {
+					if (d[u] & 3) {
+						const double2 *A = reinterpret_cast<const double2 *>(As + 6 * ((d[u] >> 2) & 511));
+						const double2 a0 = A[0], a1 = A[1], a2 = A[2];      /* staged columns are zero padded to 6 rows */
+						const double acc = a0.x * b[u][0].x + a1.x * b[u][1].x + a2.x * b[u][2].x;
+						const double acc2 = a0.y * b[u][0].y + a1.y * b[u][1].y + a2.y * b[u][2].y;
+						rp[d[u] >> 18] += acc + acc2;
+					}
+					__syncwarp();
 				}
-				d0 = d1; d1 = d2; b0 = nb0; b1 = nb1; b2 = nb2; pb = npb;
 			}
 		}
 		__syncthreads();
@@ -358,22 +354,24 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 		for (int J = fI; J <= I; ++J) {
 			const int K0 = max(fI, T.fb[J]), nK = J - K0;
 			__syncthreads();
-			double c0 = 0.0, c1 = 0.0;
+			/* four independent accumulator chains (one per k-step of a block) instead of one chain of 4 nK MMAs */
+			double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0, c4 = 0.0, c5 = 0.0, c6 = 0.0, c7 = 0.0;
 			const double *a = rp + (tm * 8 + fr) * rp_ld + (K0 - fI) * 16 + fc;
 			if (J < I) {
 				const double *b = M + (size_t)(T.blkptr[J] + K0 - T.fb[J]) * 256 + (tn * 8 + fr) * 16 + fc;
 				for (int K = 0; K < nK; ++K) {
 					const double b0 = b[K * 256], b1 = b[K * 256 + 4], b2 = b[K * 256 + 8], b3 = b[K * 256 + 12];   /* plain loads: written earlier in this kernel */
-					dmma(c0, c1, a[K * 16], b0); dmma(c0, c1, a[K * 16 + 4], b1);
-					dmma(c0, c1, a[K * 16 + 8], b2); dmma(c0, c1, a[K * 16 + 12], b3);
+					dmma(c0, c1, a[K * 16], b0); dmma(c2, c3, a[K * 16 + 4], b1);
+					dmma(c4, c5, a[K * 16 + 8], b2); dmma(c6, c7, a[K * 16 + 12], b3);
 				}
 			} else {
 				const double *b = rp + (tn * 8 + fr) * rp_ld + (K0 - fI) * 16 + fc;
 				for (int K = 0; K < nK; ++K) {
-					dmma(c0, c1, a[K * 16], b[K * 16]); dmma(c0, c1, a[K * 16 + 4], b[K * 16 + 4]);
-					dmma(c0, c1, a[K * 16 + 8], b[K * 16 + 8]); dmma(c0, c1, a[K * 16 + 12], b[K * 16 + 12]);
+					dmma(c0, c1, a[K * 16], b[K * 16]); dmma(c2, c3, a[K * 16 + 4], b[K * 16 + 4]);
+					dmma(c4, c5, a[K * 16 + 8], b[K * 16 + 8]); dmma(c6, c7, a[K * 16 + 12], b[K * 16 + 12]);
 				}
 			}
+			c0 = (c0 + c2) + (c4 + c6); c1 = (c1 + c3) + (c5 + c7);
 			{   /* S = A[I,J] - sum */
 				const double *cA = rp + (tm * 8 + fr) * rp_ld + (J - fI) * 16 + tn * 8 + 2 * fc;
 				double *ct = tmp + (tm * 8 + fr) * TLD + tn * 8 + 2 * fc;
@@ -392,33 +390,38 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 			} else {
 				__syncthreads();
 				if (warp == 0) {
-					/* Cholesky of the 16x16 diagonal block (lower), warp-synchronous, lane = row */
+					/* Cholesky of the 16x16 diagonal block and its inverse, in registers: lane r (and r + 16)
+					 * holds row r; pivots, columns and the rows of L travel by shuffle */
+					const int r = lane & 15;
+					double a[16], rinv[16];
+#pragma unroll
+					for (int c = 0; c < 16; ++c) a[c] = tmp[r * TLD + c];
+#pragma unroll
 					for (int j = 0; j < 16; ++j) {
-						__syncwarp();
-						double d = tmp[j * TLD + j];
+						double d = __shfl_sync(0xffffffffu, a[j], j);
 						if (!(d > 0.0)) { d = 1e-30; if (lane == 0) bad = 1; }
-						const double rl = rsqrt(d), ljj = d * rl;
-						double lij = 0.0;
-						if (lane < 16 && lane > j) { lij = tmp[lane * TLD + j] * rl; tmp[lane * TLD + j] = lij; }
-						__syncwarp();
-						if (lane == j) { tmp[j * TLD + j] = ljj; part[j] = rl; }
-						if (lane < 16 && lane > j)
-							for (int k = j + 1; k <= lane; ++k) tmp[lane * TLD + k] -= lij * tmp[k * TLD + j];
-					}
-					__syncwarp();
-					if (lane < 16) {
-						/* column `lane` of inv(L) by forward substitution of e_lane */
-						const int c = lane;
-						double xc[16];
+						const double rl = rsqrt(d);
+						rinv[j] = rl;
+						const double lij = r == j ? d * rl : a[j] * rl;      /* L[r][j] for r >= j */
+						a[j] = lij;
 #pragma unroll
-						for (int i = 0; i < 16; ++i) {
-							double sacc = i == c ? 1.0 : 0.0;
-#pragma unroll
-							for (int k = 0; k < 16; ++k) if (k < i && k >= c) sacc -= tmp[i * TLD + k] * xc[k];
-							xc[i] = i < c ? 0.0 : sacc * part[i];
+						for (int k = j + 1; k < 16; ++k) {
+							const double lkj = __shfl_sync(0xffffffffu, lij, k);
+							a[k] -= lij * lkj;                                  /* only r >= k is read later */
 						}
+					}
+					/* column r of inv(L) by forward substitution of e_r: x_i = (delta_ir - sum_{k<i} L[i][k] x_k) / L[i][i] */
+					double x[16];
 #pragma unroll
-						for (int i = 0; i < 16; ++i) inv[i * TLD + c] = xc[i];
+					for (int i = 0; i < 16; ++i) {
+						double sacc = i == r ? 1.0 : 0.0;
+#pragma unroll
+						for (int k = 0; k < i; ++k) sacc -= __shfl_sync(0xffffffffu, a[k], i) * x[k];
+						x[i] = i < r ? 0.0 : sacc * rinv[i];
+					}
+					if (lane < 16) {
+#pragma unroll
+						for (int c = 0; c < 16; ++c) { tmp[r * TLD + c] = a[c]; inv[c * TLD + r] = x[c]; }
 					}
 				}
 				__syncthreads();

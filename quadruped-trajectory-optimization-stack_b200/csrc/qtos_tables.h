@@ -66,13 +66,6 @@ struct AsmCol {                    /* one staged column (element e, local column
 	uint8_t  nrows, i;             /* rows of the element; panel row (variable perm % 16) the column adds into */
 };
 
-struct AsmGroup {                  /* one (element, chunk of <= 32 columns) visit of one warp during assembly */
-	int      boff;                 /* value offset of the chunk's first column */
-	int      coloff;               /* offset of the chunk's first column in elem_cols */
-	uint16_t es, ne;               /* staged columns [es, es+ne) of the block row pair with this chunk */
-	uint8_t  n2, nl, pad_[2];      /* column stride / 2; columns in the chunk */
-};
-
 struct HostTables {
 	qtos_shape shape;
 	/* dimensions */
@@ -116,13 +109,14 @@ struct HostTables {
 	std::vector<int>     fb, blkptr;                     /* [nb], [nb+1] (in blocks) */
 	std::vector<int>     diag_off;                       /* [npad] offset of (i,i) in M */
 	/* assembly of sigma I + J' D J, one block row at a time (owner-computes: warp w owns panel rows i % 4 == w):
-	 * staged columns A = D J[:, a] of every (element, column a in the block row), then per warp a list of
-	 * (element, 32-column chunk) groups whose columns b are the lanes: panel[i(a)][perm(b)] += A . J[:, b] */
+	 * staged columns A = D J[:, a] of every (element, column a in the block row), then per warp a flat stream of
+	 * terms, one per lane: n2 (2 bits, 0 = no-op) | staged column k << 2 (9) | (a - b) << 11 (7) | panel offset << 18 */
 	std::vector<int>     as_ptr;                         /* [nb+1] first staged column of every block row */
 	std::vector<AsmCol>  as_col;
-	std::vector<int>     ag_ptr;                         /* [nb*4+1] first group of (block row, warp) */
-	std::vector<AsmGroup> ag;
-	int as_max = 0, ag_max = 0;                          /* most staged columns / groups of one block row */
+	std::vector<int>     at_ptr;                         /* [nb*4+1] first term of (block row, warp), multiples of 32 */
+	std::vector<uint32_t> at;
+	int as_max = 0;                                      /* most staged columns of one block row */
+	int max_w = 0, rp_ld = 0;                            /* widest block row (blocks); leading dimension of the shared-memory panel */
 	long long asm_terms_total = 0;                       /* (a, b) pairs summed = scalar dot products per assembly */
 	std::vector<int>     jt_ptr;                         /* [npad+1] */
 	std::vector<uint32_t> jt_terms;                      /* e<<8 | a */
