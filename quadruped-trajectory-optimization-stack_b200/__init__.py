@@ -40,6 +40,8 @@ def _deps():
 
 def build(force=False, verbose=False):
     """Compile csrc/ for sm_100a with nvcc into libqtos_b200.so (in-tree)."""
+    if os.environ.get("QTOS_LIB"):          # development: load an experimental build of the same sources
+        return os.environ["QTOS_LIB"]
     stale = force or not os.path.exists(_SO) or any(
         os.path.getmtime(s) > os.path.getmtime(_SO) for s in _deps() if os.path.exists(s))
     if stale:
