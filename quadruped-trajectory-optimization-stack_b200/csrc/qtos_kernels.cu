@@ -254,7 +254,19 @@ k_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 /* ------------------------------------------------------------------ k_factor */
 
 #define FT 128           /* threads of the factor kernel: 4 warps, one 8x8 tile of a 16x16 block each */
-#define TLD 20           /* padded leading dimension of 16x16 tiles in shared memory (conflict-free DMMA fragments) */
+#ifndef FACTOR_MINB
+#define FACTOR_MINB 6    /* resident CTAs per SM the register allocation is bounded for */
+#endif
+#define TLD 18           /* padded leading dimension of 16x16 tiles in shared memory (conflict-free 128-bit fragment loads) */
+
+/* Blocks of L and the inverses of its diagonal blocks live in global memory in FRAGMENT-MAJOR order: the four
+ * contraction values lane (fr, fc) of warp tile tn feeds to its four DMMA steps (k = 4 fc + kk) are stored as two
+ * 16-byte chunks, chunk h of all 32 lanes contiguous, so a B operand is two fully coalesced 128-bit loads:
+ *   offset(r, c) = (r >> 3) * 128 + ((c >> 1) & 1) * 64 + ((r & 7) * 4 + (c >> 2)) * 2 + (c & 1) */
+__device__ __forceinline__ int frag_off(int r, int c)
+{
+	return ((r >> 3) << 7) + (((c >> 1) & 1) << 6) + ((((r & 7) << 2) + (c >> 2)) << 1) + (c & 1);
+}
 
 /* D = A(8x4) * B(4x8) + C, FP64 tensor-core MMA; fragment layout (PTX ISA, m8n8k4):
  * a = A[lane>>2][lane&3], b = B[lane&3][lane>>2], c/d = C[lane>>2][2*(lane&3) + {0,1}] */
@@ -270,12 +282,12 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
  *     J = I       Cholesky of the diagonal block + its inverse (one warp), forward substitution of the rhs
  *   then the backward substitution over the finished factor -> dx.
  * L is written to global memory once (block rows are re-read by later rows through L2). */
-__global__ void __launch_bounds__(FT)
+__global__ void __launch_bounds__(FT, FACTOR_MINB)
 k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 {
 	const int pid = blockIdx.x;
 	if (W.status[pid] != QTOS_RUNNING) return;
-	extern __shared__ double sm[];
+	extern __shared__ __align__(16) double sm[];
 	double *rp = sm;                               /* [16][rp_ld]  current block row, row-major over the whole panel */
 	double *zs = rp + 16 * rp_ld;                  /* [npad] rhs -> z -> dx */
 	double *tmp = zs + T.npad;                     /* [16][TLD] */
@@ -354,39 +366,42 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 		for (int J = fI; J <= I; ++J) {
 			const int K0 = max(fI, T.fb[J]), nK = J - K0;
 			__syncthreads();
-			/* four independent accumulator chains (one per k-step of a block) instead of one chain of 4 nK MMAs */
+			/* four independent accumulator chains (one per k-step of a block) instead of one chain of 4 nK MMAs;
+			 * DMMA step kk of lane (fr, fc) contracts k = 4 fc + kk, so both operands are 128-bit loads */
 			double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0, c4 = 0.0, c5 = 0.0, c6 = 0.0, c7 = 0.0;
-			const double *a = rp + (tm * 8 + fr) * rp_ld + (K0 - fI) * 16 + fc;
+			const double2 *a = reinterpret_cast<const double2 *>(rp + (tm * 8 + fr) * rp_ld + (K0 - fI) * 16 + 4 * fc);
 			if (J < I) {
-				const double *b = M + (size_t)(T.blkptr[J] + K0 - T.fb[J]) * 256 + (tn * 8 + fr) * 16 + fc;
+				const double2 *b = reinterpret_cast<const double2 *>(M + (size_t)(T.blkptr[J] + K0 - T.fb[J]) * 256 + tn * 128) + lane;
 				for (int K = 0; K < nK; ++K) {
-					const double b0 = b[K * 256], b1 = b[K * 256 + 4], b2 = b[K * 256 + 8], b3 = b[K * 256 + 12];   /* plain loads: written earlier in this kernel */
-					dmma(c0, c1, a[K * 16], b0); dmma(c2, c3, a[K * 16 + 4], b1);
-					dmma(c4, c5, a[K * 16 + 8], b2); dmma(c6, c7, a[K * 16 + 12], b3);
+					const double2 b01 = b[K * 128], b23 = b[K * 128 + 32];   /* plain loads: written earlier in this kernel */
+					const double2 a01 = a[K * 8], a23 = a[K * 8 + 1];
+					dmma(c0, c1, a01.x, b01.x); dmma(c2, c3, a01.y, b01.y);
+					dmma(c4, c5, a23.x, b23.x); dmma(c6, c7, a23.y, b23.y);
 				}
 			} else {
-				const double *b = rp + (tn * 8 + fr) * rp_ld + (K0 - fI) * 16 + fc;
+				const double2 *b = reinterpret_cast<const double2 *>(rp + (tn * 8 + fr) * rp_ld + (K0 - fI) * 16 + 4 * fc);
 				for (int K = 0; K < nK; ++K) {
-					dmma(c0, c1, a[K * 16], b[K * 16]); dmma(c2, c3, a[K * 16 + 4], b[K * 16 + 4]);
-					dmma(c4, c5, a[K * 16 + 8], b[K * 16 + 8]); dmma(c6, c7, a[K * 16 + 12], b[K * 16 + 12]);
+					const double2 b01 = b[K * 8], b23 = b[K * 8 + 1];
+					const double2 a01 = a[K * 8], a23 = a[K * 8 + 1];
+					dmma(c0, c1, a01.x, b01.x); dmma(c2, c3, a01.y, b01.y);
+					dmma(c4, c5, a23.x, b23.x); dmma(c6, c7, a23.y, b23.y);
 				}
 			}
 			c0 = (c0 + c2) + (c4 + c6); c1 = (c1 + c3) + (c5 + c7);
 			{   /* S = A[I,J] - sum */
-				const double *cA = rp + (tm * 8 + fr) * rp_ld + (J - fI) * 16 + tn * 8 + 2 * fc;
-				double *ct = tmp + (tm * 8 + fr) * TLD + tn * 8 + 2 * fc;
-				ct[0] = cA[0] - c0; ct[1] = cA[1] - c1;
+				const double2 cA = *reinterpret_cast<const double2 *>(rp + (tm * 8 + fr) * rp_ld + (J - fI) * 16 + tn * 8 + 2 * fc);
+				*reinterpret_cast<double2 *>(tmp + (tm * 8 + fr) * TLD + tn * 8 + 2 * fc) = make_double2(cA.x - c0, cA.y - c1);
 			}
 			if (J < I) {
-				/* L[I,J] = S * inv(L[J,J])' : second DMMA product, B = inv(L[J,J]) rows from global */
-				const double *bi = Dinv + (size_t)J * 256 + (tn * 8 + fr) * 16 + fc;
-				const double i0 = bi[0], i1 = bi[4], i2 = bi[8], i3 = bi[12];
+				/* L[I,J] = S * inv(L[J,J])' : second DMMA product, B = inv(L[J,J]) in fragment order from global */
+				const double2 *bi = reinterpret_cast<const double2 *>(Dinv + (size_t)J * 256 + tn * 128) + lane;
+				const double2 i01 = bi[0], i23 = bi[32];
 				__syncthreads();
-				const double *ta = tmp + (tm * 8 + fr) * TLD + fc;
-				double x0 = 0.0, x1 = 0.0;
-				dmma(x0, x1, ta[0], i0); dmma(x0, x1, ta[4], i1); dmma(x0, x1, ta[8], i2); dmma(x0, x1, ta[12], i3);
-				double *cX = rp + (tm * 8 + fr) * rp_ld + (J - fI) * 16 + tn * 8 + 2 * fc;
-				cX[0] = x0; cX[1] = x1;
+				const double2 *ta = reinterpret_cast<const double2 *>(tmp + (tm * 8 + fr) * TLD + 4 * fc);
+				const double2 t01 = ta[0], t23 = ta[1];
+				double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+				dmma(x0, x1, t01.x, i01.x); dmma(x2, x3, t01.y, i01.y); dmma(x0, x1, t23.x, i23.x); dmma(x2, x3, t23.y, i23.y);
+				*reinterpret_cast<double2 *>(rp + (tm * 8 + fr) * rp_ld + (J - fI) * 16 + tn * 8 + 2 * fc) = make_double2(x0 + x2, x1 + x3);
 			} else {
 				__syncthreads();
 				if (warp == 0) {
@@ -429,7 +444,7 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 				for (int q = tid; q < 256; q += FT) {
 					const int r = q >> 4, c = q & 15;
 					rp[r * rp_ld + (wI - 1) * 16 + c] = r >= c ? tmp[r * TLD + c] : 0.0;
-					Dinv[(size_t)I * 256 + q] = inv[r * TLD + c];
+					Dinv[(size_t)I * 256 + frag_off(r, c)] = inv[r * TLD + c];
 				}
 			}
 		}
@@ -445,7 +460,10 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 			if (l8 == 0) part[r] = zs[I * 16 + r] - acc;
 		}
 		/* ---- store the block row of L (block-major in global memory) ---- */
-		for (int q = tid; q < wI * 256; q += FT) M[(size_t)rowbase + q] = rp[((q >> 4) & 15) * rp_ld + (q >> 8) * 16 + (q & 15)];
+		for (int q = tid; q < wI * 128; q += FT) {          /* q = ((block * 2 + tn) * 2 + h) * 32 + lane, one 16-byte chunk each */
+			const int r = ((q >> 6) & 1) * 8 + ((q & 31) >> 2), c = 4 * (q & 3) + 2 * ((q >> 5) & 1);
+			reinterpret_cast<double2 *>(M + rowbase)[q] = *reinterpret_cast<const double2 *>(rp + r * rp_ld + (q >> 7) * 16 + c);
+		}
 		__syncthreads();
 		if (tid < 16) {
 			double v = 0.0;
@@ -461,16 +479,16 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 		if (tid < 16) {
 			double v = 0.0;
 			const double *iv = Dinv + (size_t)I * 256;
-			for (int q = tid; q < 16; ++q) v += iv[q * 16 + tid] * zs[I * 16 + q];
+			for (int q = tid; q < 16; ++q) v += iv[frag_off(q, tid)] * zs[I * 16 + q];
 			part[tid] = v;
 		}
 		__syncthreads();
 		if (tid < 16) zs[I * 16 + tid] = part[tid];
 		for (int c = tid; c < (I - fI) * 16; c += FT) {
-			const double *blk = rowg + (size_t)(c >> 4) * 256 + (c & 15);
+			const double *blk = rowg + (size_t)(c >> 4) * 256 + frag_off(0, c & 15);
 			double acc = 0.0;
 #pragma unroll
-			for (int q = 0; q < 16; ++q) acc += blk[q * 16] * part[q];
+			for (int q = 0; q < 16; ++q) acc += blk[((q >> 3) << 7) + ((q & 7) << 3)] * part[q];
 			zs[fI * 16 + c] -= acc;
 		}
 		__syncthreads();
@@ -488,7 +506,7 @@ k_step(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *
 {
 	const int pid = blockIdx.x;
 	if (W.status[pid] != QTOS_RUNNING) return;
-	extern __shared__ double sm[];
+	extern __shared__ __align__(16) double sm[];
 	double *b = sm;                       /* [npad] dx from k_factor (permuted order) */
 	double *part = b + T.npad;            /* [256] scratch */
 	double *red = part + 256;             /* [8*32] */
