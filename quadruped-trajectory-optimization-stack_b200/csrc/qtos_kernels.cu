@@ -255,7 +255,10 @@ k_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 
 #define FT 128           /* threads of the factor kernel: 4 warps, one 8x8 tile of a 16x16 block each */
 #ifndef FACTOR_MINB
-#define FACTOR_MINB 6    /* resident CTAs per SM the register allocation is bounded for */
+#define FACTOR_MINB 7    /* resident CTAs per SM the register allocation is bounded for */
+#endif
+#ifndef ASM_MINB
+#define ASM_MINB 6
 #endif
 #define TLD 18           /* padded leading dimension of 16x16 tiles in shared memory (conflict-free 128-bit fragment loads) */
 
@@ -275,13 +278,89 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
 	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-/* Condensed KKT system of one problem, start to finish in one CTA:
- *   for each block row I of the block skyline (left-looking):
- *     assemble  A[I, fI..I] = (sigma I + J' D J) rows, owner-computes gather straight into shared memory
+/* Assembly of one block row of the condensed KKT matrix A = sigma I + J' D J, one CTA per (problem, block row):
+ * stage A_a = D J[:, a] for every (element, column a) of the block row in shared memory, then every warp walks its
+ * flat term stream, one term per lane: panel[i(a)][perm(b)] += A_a . J[:, b].  Warp w owns the panel rows
+ * i % 4 == w and the targets inside one step are distinct, so the sums are race-free and their order is fixed.
+ * Block rows are independent, so the grid is problems x block rows and no CTA carries a serial chain; the finished
+ * panel (16 x 16 w_I, row-major) goes to the block row's slot of M, where k_factor picks it up. */
+__global__ void __launch_bounds__(FT, ASM_MINB)
+k_asm(DevTables T, DevWork W, qtos_options opt, int rp_ld)
+{
+	const int pid = blockIdx.x / T.nb, I = blockIdx.x - pid * T.nb;
+	if (W.status[pid] != QTOS_RUNNING) return;
+	extern __shared__ __align__(16) double sm[];
+	double *rp = sm;                               /* [16][rp_ld]  the block row, row-major over the whole panel */
+	double *As = rp + 16 * rp_ld;                  /* [as_max][6] staged D J columns of the block row */
+	int *av = reinterpret_cast<int *>(As + 6 * T.as_max);         /* [as_max] value offsets of the staged columns */
+	const double *Jv = WS(Jv, T.nJ), *Sig = WS(Sig, T.m);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int fI = T.fb[I], wI = I - fI + 1, wcols = wI * 16;
+	{
+		const int s0 = T.as_ptr[I], nst = T.as_ptr[I + 1] - s0;
+		for (int q = tid; q < nst * 6; q += FT) {
+			const int k = q / 6, r = q - 6 * k;
+			const AsmCol C = T.as_col[s0 + k];
+			As[q] = r < C.nrows ? Sig[C.row0 + r] * Jv[C.voff + r] : 0.0;
+			if (r == 0) av[k] = C.voff;
+		}
+		for (int r = warp; r < 16; r += FT / 32)
+			for (int c = lane; c < wcols; c += 32) rp[r * rp_ld + c] = 0.0;
+	}
+	__syncthreads();
+	{
+		const int t0 = T.at_ptr[I * 4 + warp], t1 = T.at_ptr[I * 4 + warp + 1];
+		/* four steps in flight: descriptors, then the J columns of all four, then the sums in step order */
+		for (int t = t0 + lane; t < t1; t += 128) {
+			uint32_t d[4];
+			double2 b[4][3];
+#pragma unroll
+			for (int u = 0; u < 4; ++u) d[u] = t + 32 * u < t1 ? __ldg(T.at + t + 32 * u) : 0u;
+#pragma unroll
+			for (int u = 0; u < 4; ++u) {
+				const int n2 = d[u] & 3;
+				b[u][0] = b[u][1] = b[u][2] = make_double2(0.0, 0.0);
+				if (n2) {
+					const double2 *B = reinterpret_cast<const double2 *>(Jv + av[(d[u] >> 2) & 511]) - ((d[u] >> 11) & 127) * n2;
+					b[u][0] = B[0];
+					if (n2 > 1) b[u][1] = B[1];
+					if (n2 > 2) b[u][2] = B[2];
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < 4; ++u) {
+				if (d[u] & 3) {
+					const double2 *A = reinterpret_cast<const double2 *>(As + 6 * ((d[u] >> 2) & 511));
+					const double2 a0 = A[0], a1 = A[1], a2 = A[2];      /* staged columns are zero padded to 6 rows */
+					const double acc = a0.x * b[u][0].x + a1.x * b[u][1].x + a2.x * b[u][2].x;
+					const double acc2 = a0.y * b[u][0].y + a1.y * b[u][1].y + a2.y * b[u][2].y;
+					rp[d[u] >> 18] += acc + acc2;
+				}
+				__syncwarp();
+			}
+		}
+	}
+	__syncthreads();
+	if (tid < 16) {
+		const int i = I * 16 + tid;
+		double *d = rp + tid * rp_ld + (wI - 1) * 16 + tid;
+		*d = i < T.n_free ? *d + opt.sigma_w : 1.0;
+	}
+	__syncthreads();
+	double2 *out = reinterpret_cast<double2 *>(WS(M, T.nM) + (size_t)T.blkptr[I] * 256);
+	const int w2 = wcols >> 1;
+	for (int q = tid; q < 16 * w2; q += FT) {
+		const int r = q / w2, c2 = q - r * w2;
+		out[q] = *reinterpret_cast<const double2 *>(rp + r * rp_ld + 2 * c2);
+	}
+}
+
+/* Factorization and solve of the condensed KKT system of one problem in one CTA (left-looking over block rows):
+ *   load the assembled block row A[I, fI..I] (k_asm) into shared memory
  *     for J < I   L[I,J] = (A[I,J] - sum_K L[I,K] L[J,K]') inv(L[J,J])'   two DMMA products per 16x16 block
  *     J = I       Cholesky of the diagonal block + its inverse (one warp), forward substitution of the rhs
  *   then the backward substitution over the finished factor -> dx.
- * L is written to global memory once (block rows are re-read by later rows through L2). */
+ * L overwrites A in global memory, block row by block row (later rows re-read it through L2). */
 __global__ void __launch_bounds__(FT, FACTOR_MINB)
 k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 {
@@ -293,10 +372,7 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 	double *tmp = zs + T.npad;                     /* [16][TLD] */
 	double *inv = tmp + 16 * TLD;                  /* [16][TLD] */
 	double *part = inv + 16 * TLD;                 /* [16] */
-	double *As = part + 16;                        /* [as_max][6] staged D J columns of the block row */
-	int *av = reinterpret_cast<int *>(As + 6 * T.as_max);         /* [as_max] value offsets of the staged columns */
 	double *M = WS(M, T.nM), *Dinv = WS(Dinv, T.nb * 256);
-	const double *Jv = WS(Jv, T.nJ), *Sig = WS(Sig, T.m);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int tm = warp >> 1, tn = warp & 1;       /* 8x8 tile of the 16x16 block owned by this warp */
 	const int fr = lane >> 2, fc = lane & 3;       /* fragment row / column */
@@ -307,60 +383,13 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 		const int fI = T.fb[I], wI = I - fI + 1;
 		const int rowbase = T.blkptr[I] * 256;
 		__syncthreads();
-		/* ---- assemble the block row into shared memory ----
-		 * stage A = D J[:, a] for every (element, column a) of this block row, then every warp walks its flat
-		 * term stream, one term per lane: panel[i(a)][perm(b)] += A . J[:, b].  Warp w owns the panel rows
-		 * i % 4 == w and the targets inside one step are distinct, so the sums are race-free and ordered. */
-		{
-			const int s0 = T.as_ptr[I], nst = T.as_ptr[I + 1] - s0;
-			for (int q = tid; q < nst * 6; q += FT) {
-				const int k = q / 6, r = q - 6 * k;
-				const AsmCol C = T.as_col[s0 + k];
-				As[q] = r < C.nrows ? Sig[C.row0 + r] * Jv[C.voff + r] : 0.0;
-				if (r == 0) av[k] = C.voff;
+		{   /* ---- the assembled block row ---- */
+			const double2 *in = reinterpret_cast<const double2 *>(M + rowbase);
+			const int w2 = wI * 8;
+			for (int q = tid; q < 16 * w2; q += FT) {
+				const int r = q / w2, c2 = q - r * w2;
+				*reinterpret_cast<double2 *>(rp + r * rp_ld + 2 * c2) = in[q];
 			}
-			const int wcols = wI * 16;
-			for (int r = warp; r < 16; r += FT / 32)
-				for (int c = lane; c < wcols; c += 32) rp[r * rp_ld + c] = 0.0;
-		}
-		__syncthreads();
-		{
-			const int t0 = T.at_ptr[I * 4 + warp], t1 = T.at_ptr[I * 4 + warp + 1];
-			/* four steps in flight: descriptors, then the J columns of all four, then the sums in step order */
-			for (int t = t0 + lane; t < t1; t += 128) {
-				uint32_t d[4];
-				double2 b[4][3];
-#pragma unroll
-				for (int u = 0; u < 4; ++u) d[u] = t + 32 * u < t1 ? __ldg(T.at + t + 32 * u) : 0u;
-#pragma unroll
-				for (int u = 0; u < 4; ++u) {
-					const int n2 = d[u] & 3;
-					b[u][0] = b[u][1] = b[u][2] = make_double2(0.0, 0.0);
-					if (n2) {
-						const double2 *B = reinterpret_cast<const double2 *>(Jv + av[(d[u] >> 2) & 511]) - ((d[u] >> 11) & 127) * n2;
-						b[u][0] = B[0];
-						if (n2 > 1) b[u][1] = B[1];
-						if (n2 > 2) b[u][2] = B[2];
-					}
-				}
-#pragma unroll
-				for (int u = 0; u < 4; ++u) {
-					if (d[u] & 3) {
-						const double2 *A = reinterpret_cast<const double2 *>(As + 6 * ((d[u] >> 2) & 511));
-						const double2 a0 = A[0], a1 = A[1], a2 = A[2];      /* staged columns are zero padded to 6 rows */
-						const double acc = a0.x * b[u][0].x + a1.x * b[u][1].x + a2.x * b[u][2].x;
-						const double acc2 = a0.y * b[u][0].y + a1.y * b[u][1].y + a2.y * b[u][2].y;
-						rp[d[u] >> 18] += acc + acc2;
-					}
-					__syncwarp();
-				}
-			}
-		}
-		__syncthreads();
-		if (tid < 16) {
-			const int i = I * 16 + tid;
-			double *d = rp + tid * rp_ld + (wI - 1) * 16 + tid;
-			*d = i < T.n_free ? *d + opt.sigma_w : 1.0;
 		}
 		/* ---- off-diagonal blocks ---- */
 		for (int J = fI; J <= I; ++J) {
