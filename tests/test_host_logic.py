@@ -111,3 +111,24 @@ def test_workload_generator_is_deterministic():
     assert a.tobytes() == b.tobytes() and a["group"].max() == 7
     assert np.all(a["goal"][:, 0] - a["start_pos"][:, 0] >= 0.2) and np.all(a["goal"][:, 0] - a["start_pos"][:, 0] <= 0.6)
     assert np.allclose(a["start_pos"][:, 2] - 0.24, HF.get_height(grid, res, a["start_pos"][:, 0], a["start_pos"][:, 1]))
+
+
+def test_csv_free_handoff_equals_the_text_detour(tmp_path):
+    """arrays handed to the Combiner-side readers carry exactly the values the CSV text would."""
+    import pandas as pd
+    from qtos_b200 import handoff
+    rng = np.random.default_rng(5)
+    rows = rng.normal(size=(200, 37)) * 10.0 ** rng.integers(-7, 4, size=(200, 37))
+    rows[3, 5] = 0.0; rows[4, 6] = -0.0; rows[5, 7] = 1e-5; rows[6, 8] = 123456.5; rows[7, 9] = 0.1 + 0.2
+    path = str(tmp_path / "traj.csv")
+    Q.write_csv(rows, path)                                         # C-ABI writer, "%g" like ofstream << double
+    text = np.loadtxt(path, delimiter=",")
+    assert np.array_equal(handoff.as_csv_values(rows), text)
+    assert np.array_equal(handoff.read_csv_frame(rows), pd.read_csv(path).to_numpy())       # first row eaten as header
+    import csv
+    with open(path, newline="") as f:
+        r7 = list(csv.reader(f))[7]
+    st = handoff.state_of_row(handoff.as_csv_values(rows)[7])
+    assert st["CoM"] == [float(v) for v in r7[1:4]] and st["HR_FOOT"] == [float(v) for v in r7[16:19]]
+    assert st["CoM_vel_ang"] == [float(v) for v in r7[22:25]] and sorted(st) == sorted(
+        ["CoM", "orientation", "FL_FOOT", "FR_FOOT", "HL_FOOT", "HR_FOOT", "CoM_vel", "CoM_vel_ang"])
