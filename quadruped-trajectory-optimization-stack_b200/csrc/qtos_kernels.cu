@@ -255,7 +255,7 @@ k_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 
 #define FT 128           /* threads of the factor kernel: 4 warps, one 8x8 tile of a 16x16 block each */
 #ifndef FACTOR_MINB
-#define FACTOR_MINB 7    /* resident CTAs per SM the register allocation is bounded for */
+#define FACTOR_MINB 6    /* resident CTAs per SM the register allocation is bounded for */
 #endif
 #ifndef ASM_MINB
 #define ASM_MINB 6
@@ -355,13 +355,27 @@ k_asm(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 	}
 }
 
-/* Factorization and solve of the condensed KKT system of one problem in one CTA (left-looking over block rows):
- *   load the assembled block row A[I, fI..I] (k_asm) into shared memory
+/* named barriers of k_factor: the four tile warps among themselves, and the two hand-offs with the diagonal warp */
+#define FTT 160          /* threads of the factor kernel: four tile warps + one diagonal warp */
+__device__ __forceinline__ void tile_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void diag_ready_arrive() { __threadfence_block(); asm volatile("bar.arrive 2, 160;" ::: "memory"); }
+__device__ __forceinline__ void diag_ready_wait() { asm volatile("bar.sync 2, 160;" ::: "memory"); }
+__device__ __forceinline__ void diag_done_arrive() { __threadfence_block(); asm volatile("bar.arrive 3, 160;" ::: "memory"); }
+__device__ __forceinline__ void diag_done_wait() { asm volatile("bar.sync 3, 160;" ::: "memory"); }
+
+/* Factorization and solve of the condensed KKT system of one problem in one CTA (left-looking over block rows),
+ * software-pipelined between four TILE warps (one 8x8 tile of a 16x16 block each) and one DIAGONAL warp:
+ *   tile warps, block row I:   load the assembled row A[I, fI..I] (k_asm) into shared memory
  *     for J < I   L[I,J] = (A[I,J] - sum_K L[I,K] L[J,K]') inv(L[J,J])'   two DMMA products per 16x16 block
- *     J = I       Cholesky of the diagonal block + its inverse (one warp), forward substitution of the rhs
- *   then the backward substitution over the finished factor -> dx.
- * L overwrites A in global memory, block row by block row (later rows re-read it through L2). */
-__global__ void __launch_bounds__(FT, FACTOR_MINB)
+ *     J = I       S = A[I,I] - sum_K L[I,K] L[I,K]' and p = b_I - L[I,<I] z  handed to the diagonal warp,
+ *                 then the row of L is stored (fragment-major) and the next row starts at once
+ *   diagonal warp, block row I: Cholesky of S in registers + inv(L[I,I]) (by shuffles), inv -> global (the only form
+ *                 of the diagonal block anybody needs: later rows and both substitutions multiply by it),
+ *                 z_I = inv(L[I,I]) p
+ * Row I+1 needs inv(L[I,I]) and z_I only for its LAST off-diagonal block, so the serial 16x16 factorization -- a third
+ * of the kernel's critical path when it sat between barriers of all warps -- runs under the sweep of the next row.
+ * Then the backward substitution over the finished factor -> dx (tile warps). */
+__global__ void __launch_bounds__(FTT, FACTOR_MINB)
 k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 {
 	const int pid = blockIdx.x;
@@ -369,161 +383,165 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 	extern __shared__ __align__(16) double sm[];
 	double *rp = sm;                               /* [16][rp_ld]  current block row, row-major over the whole panel */
 	double *zs = rp + 16 * rp_ld;                  /* [npad] rhs -> z -> dx */
-	double *tmp = zs + T.npad;                     /* [16][TLD] */
-	double *inv = tmp + 16 * TLD;                  /* [16][TLD] */
-	double *part = inv + 16 * TLD;                 /* [16] */
+	double *tmp = zs + T.npad;                     /* [16][TLD] S of an off-diagonal block (tile warps) */
+	double *dS = tmp + 16 * TLD;                   /* [16][TLD] S of the diagonal block -> inv(L_II) (hand-off buffer) */
+	double *part = dS + 16 * TLD;                  /* [16] */
 	double *M = WS(M, T.nM), *Dinv = WS(Dinv, T.nb * 256);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int tm = warp >> 1, tn = warp & 1;       /* 8x8 tile of the 16x16 block owned by this warp */
-	const int fr = lane >> 2, fc = lane & 3;       /* fragment row / column */
 	__shared__ int bad;
 	if (tid == 0) bad = 0;
-	for (int i = tid; i < T.npad; i += FT) zs[i] = W.vec[(size_t)pid * T.npad + i];
-	for (int I = 0; I < T.nb; ++I) {
-		const int fI = T.fb[I], wI = I - fI + 1;
-		const int rowbase = T.blkptr[I] * 256;
-		__syncthreads();
-		{   /* ---- the assembled block row ---- */
-			const double2 *in = reinterpret_cast<const double2 *>(M + rowbase);
-			const int w2 = wI * 8;
-			for (int q = tid; q < 16 * w2; q += FT) {
-				const int r = q / w2, c2 = q - r * w2;
-				*reinterpret_cast<double2 *>(rp + r * rp_ld + 2 * c2) = in[q];
-			}
-		}
-		/* ---- off-diagonal blocks ---- */
-		for (int J = fI; J <= I; ++J) {
-			const int K0 = max(fI, T.fb[J]), nK = J - K0;
-			__syncthreads();
-			/* four independent accumulator chains (one per k-step of a block) instead of one chain of 4 nK MMAs;
-			 * DMMA step kk of lane (fr, fc) contracts k = 4 fc + kk, so both operands are 128-bit loads */
-			double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0, c4 = 0.0, c5 = 0.0, c6 = 0.0, c7 = 0.0;
-			const double2 *a = reinterpret_cast<const double2 *>(rp + (tm * 8 + fr) * rp_ld + (K0 - fI) * 16 + 4 * fc);
-			if (J < I) {
-				const double2 *b = reinterpret_cast<const double2 *>(M + (size_t)(T.blkptr[J] + K0 - T.fb[J]) * 256 + tn * 128) + lane;
-				for (int K = 0; K < nK; ++K) {
-					const double2 b01 = b[K * 128], b23 = b[K * 128 + 32];   /* plain loads: written earlier in this kernel */
-					const double2 a01 = a[K * 8], a23 = a[K * 8 + 1];
-					dmma(c0, c1, a01.x, b01.x); dmma(c2, c3, a01.y, b01.y);
-					dmma(c4, c5, a23.x, b23.x); dmma(c6, c7, a23.y, b23.y);
-				}
-			} else {
-				const double2 *b = reinterpret_cast<const double2 *>(rp + (tn * 8 + fr) * rp_ld + (K0 - fI) * 16 + 4 * fc);
-				for (int K = 0; K < nK; ++K) {
-					const double2 b01 = b[K * 8], b23 = b[K * 8 + 1];
-					const double2 a01 = a[K * 8], a23 = a[K * 8 + 1];
-					dmma(c0, c1, a01.x, b01.x); dmma(c2, c3, a01.y, b01.y);
-					dmma(c4, c5, a23.x, b23.x); dmma(c6, c7, a23.y, b23.y);
-				}
-			}
-			c0 = (c0 + c2) + (c4 + c6); c1 = (c1 + c3) + (c5 + c7);
-			{   /* S = A[I,J] - sum */
-				const double2 cA = *reinterpret_cast<const double2 *>(rp + (tm * 8 + fr) * rp_ld + (J - fI) * 16 + tn * 8 + 2 * fc);
-				*reinterpret_cast<double2 *>(tmp + (tm * 8 + fr) * TLD + tn * 8 + 2 * fc) = make_double2(cA.x - c0, cA.y - c1);
-			}
-			if (J < I) {
-				/* L[I,J] = S * inv(L[J,J])' : second DMMA product, B = inv(L[J,J]) in fragment order from global */
-				const double2 *bi = reinterpret_cast<const double2 *>(Dinv + (size_t)J * 256 + tn * 128) + lane;
-				const double2 i01 = bi[0], i23 = bi[32];
-				__syncthreads();
-				const double2 *ta = reinterpret_cast<const double2 *>(tmp + (tm * 8 + fr) * TLD + 4 * fc);
-				const double2 t01 = ta[0], t23 = ta[1];
-				double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
-				dmma(x0, x1, t01.x, i01.x); dmma(x2, x3, t01.y, i01.y); dmma(x0, x1, t23.x, i23.x); dmma(x2, x3, t23.y, i23.y);
-				*reinterpret_cast<double2 *>(rp + (tm * 8 + fr) * rp_ld + (J - fI) * 16 + tn * 8 + 2 * fc) = make_double2(x0 + x2, x1 + x3);
-			} else {
-				__syncthreads();
-				if (warp == 0) {
-					/* Cholesky of the 16x16 diagonal block and its inverse, in registers: lane r (and r + 16)
-					 * holds row r; pivots, columns and the rows of L travel by shuffle */
-					const int r = lane & 15;
-					double a[16], rinv[16];
-#pragma unroll
-					for (int c = 0; c < 16; ++c) a[c] = tmp[r * TLD + c];
-#pragma unroll
-					for (int j = 0; j < 16; ++j) {
-						double d = __shfl_sync(0xffffffffu, a[j], j);
-						if (!(d > 0.0)) { d = 1e-30; if (lane == 0) bad = 1; }
-						const double rl = rsqrt(d);
-						rinv[j] = rl;
-						const double lij = r == j ? d * rl : a[j] * rl;      /* L[r][j] for r >= j */
-						a[j] = lij;
-#pragma unroll
-						for (int k = j + 1; k < 16; ++k) {
-							const double lkj = __shfl_sync(0xffffffffu, lij, k);
-							a[k] -= lij * lkj;                                  /* only r >= k is read later */
-						}
-					}
-					/* column r of inv(L) by forward substitution of e_r: x_i = (delta_ir - sum_{k<i} L[i][k] x_k) / L[i][i] */
-					double x[16];
-#pragma unroll
-					for (int i = 0; i < 16; ++i) {
-						double sacc = i == r ? 1.0 : 0.0;
-#pragma unroll
-						for (int k = 0; k < i; ++k) sacc -= __shfl_sync(0xffffffffu, a[k], i) * x[k];
-						x[i] = i < r ? 0.0 : sacc * rinv[i];
-					}
-					if (lane < 16) {
-#pragma unroll
-						for (int c = 0; c < 16; ++c) { tmp[r * TLD + c] = a[c]; inv[c * TLD + r] = x[c]; }
-					}
-				}
-				__syncthreads();
-				/* L[I,I] into the panel, inv(L[I,I]) to global for later rows and the backward solve */
-				for (int q = tid; q < 256; q += FT) {
-					const int r = q >> 4, c = q & 15;
-					rp[r * rp_ld + (wI - 1) * 16 + c] = r >= c ? tmp[r * TLD + c] : 0.0;
-					Dinv[(size_t)I * 256 + frag_off(r, c)] = inv[r * TLD + c];
-				}
-			}
-		}
-		__syncthreads();
-		/* ---- forward substitution of the rhs with the finished row: z_I = inv(L_II) (b_I - L[I,<I] z) ---- */
-		{
-			const int r = tid >> 3, l8 = tid & 7;
-			double acc = 0.0;
-			const double *row = rp + r * rp_ld;
-			const double *zz = zs + fI * 16;
-			for (int c = l8; c < (wI - 1) * 16; c += 8) acc += row[c] * zz[c];
-			acc += __shfl_xor_sync(0xffffffffu, acc, 4); acc += __shfl_xor_sync(0xffffffffu, acc, 2); acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-			if (l8 == 0) part[r] = zs[I * 16 + r] - acc;
-		}
-		/* ---- store the block row of L (block-major in global memory) ---- */
-		for (int q = tid; q < wI * 128; q += FT) {          /* q = ((block * 2 + tn) * 2 + h) * 32 + lane, one 16-byte chunk each */
-			const int r = ((q >> 6) & 1) * 8 + ((q & 31) >> 2), c = 4 * (q & 3) + 2 * ((q >> 5) & 1);
-			reinterpret_cast<double2 *>(M + rowbase)[q] = *reinterpret_cast<const double2 *>(rp + r * rp_ld + (q >> 7) * 16 + c);
-		}
-		__syncthreads();
-		if (tid < 16) {
-			double v = 0.0;
-			for (int q = 0; q <= tid; ++q) v += inv[tid * TLD + q] * part[q];
-			zs[I * 16 + tid] = v;
-		}
-	}
+	for (int i = tid; i < T.npad; i += FTT) zs[i] = W.vec[(size_t)pid * T.npad + i];
 	__syncthreads();
-	/* ---- backward substitution: L' x = z ---- */
-	for (int I = T.nb - 1; I >= 0; --I) {
-		const int fI = T.fb[I];
-		const double *rowg = M + (size_t)T.blkptr[I] * 256;
-		if (tid < 16) {
-			double v = 0.0;
-			const double *iv = Dinv + (size_t)I * 256;
-			for (int q = tid; q < 16; ++q) v += iv[frag_off(q, tid)] * zs[I * 16 + q];
-			part[tid] = v;
-		}
-		__syncthreads();
-		if (tid < 16) zs[I * 16 + tid] = part[tid];
-		for (int c = tid; c < (I - fI) * 16; c += FT) {
-			const double *blk = rowg + (size_t)(c >> 4) * 256 + frag_off(0, c & 15);
-			double acc = 0.0;
+	if (warp == 4) {
+		/* ---------------- diagonal warp ---------------- */
+		for (int I = 0; I < T.nb; ++I) {
+			diag_ready_wait();
+			/* Cholesky of the 16x16 diagonal block and its inverse, in registers: lane r (and r + 16)
+			 * holds row r; pivots, columns and the rows of L travel by shuffle */
+			const int r = lane & 15;
+			double a[16], rinv[16];
 #pragma unroll
-			for (int q = 0; q < 16; ++q) acc += blk[((q >> 3) << 7) + ((q & 7) << 3)] * part[q];
-			zs[fI * 16 + c] -= acc;
+			for (int c = 0; c < 16; ++c) a[c] = dS[r * TLD + c];
+#pragma unroll
+			for (int j = 0; j < 16; ++j) {
+				double d = __shfl_sync(0xffffffffu, a[j], j);
+				if (!(d > 0.0)) { d = 1e-30; if (lane == 0) bad = 1; }
+				const double rl = rsqrt(d);
+				rinv[j] = rl;
+				const double lij = r == j ? d * rl : a[j] * rl;      /* L[r][j] for r >= j */
+				a[j] = lij;
+#pragma unroll
+				for (int k = j + 1; k < 16; ++k) {
+					const double lkj = __shfl_sync(0xffffffffu, lij, k);
+					a[k] -= lij * lkj;                                  /* only r >= k is read later */
+				}
+			}
+			/* column r of inv(L) by forward substitution of e_r: x_i = (delta_ir - sum_{k<i} L[i][k] x_k) / L[i][i] */
+			double x[16];
+#pragma unroll
+			for (int i = 0; i < 16; ++i) {
+				double sacc = i == r ? 1.0 : 0.0;
+#pragma unroll
+				for (int k = 0; k < i; ++k) sacc -= __shfl_sync(0xffffffffu, a[k], i) * x[k];
+				x[i] = i < r ? 0.0 : sacc * rinv[i];
+			}
+			__syncwarp();
+			if (lane < 16) {
+#pragma unroll
+				for (int c = 0; c < 16; ++c) dS[c * TLD + r] = x[c];
+			}
+			__syncwarp();
+			/* inv(L[I,I]) to global (fragment-major) for later rows and the backward solve; z_I */
+			for (int q = lane; q < 256; q += 32) Dinv[(size_t)I * 256 + frag_off(q >> 4, q & 15)] = dS[(q >> 4) * TLD + (q & 15)];
+			if (lane < 16) {
+				double v = 0.0;
+				for (int q = 0; q <= lane; ++q) v += dS[lane * TLD + q] * part[q];
+				zs[I * 16 + lane] = v;
+			}
+			diag_done_arrive();
 		}
-		__syncthreads();
+	} else {
+		/* ---------------- tile warps ---------------- */
+		const int tm = warp >> 1, tn = warp & 1;       /* 8x8 tile of the 16x16 block owned by this warp */
+		const int fr = lane >> 2, fc = lane & 3;       /* fragment row / column */
+		for (int I = 0; I < T.nb; ++I) {
+			const int fI = T.fb[I], wI = I - fI + 1;
+			const int rowbase = T.blkptr[I] * 256;
+			tile_sync();                               /* the previous row has left the panel */
+			{   /* ---- the assembled block row ---- */
+				const double2 *in = reinterpret_cast<const double2 *>(M + rowbase);
+				const int w2 = wI * 8;
+				for (int q = tid; q < 16 * w2; q += 128) {
+					const int r = q / w2, c2 = q - r * w2;
+					*reinterpret_cast<double2 *>(rp + r * rp_ld + 2 * c2) = in[q];
+				}
+			}
+			if (I > 0 && fI == I) diag_done_wait();    /* no off-diagonal block: keep the hand-off in step */
+			for (int J = fI; J <= I; ++J) {
+				const int K0 = max(fI, T.fb[J]), nK = J - K0;
+				if (J == I - 1) diag_done_wait();      /* inv(L[I-1,I-1]) and z_{I-1} are needed from here on */
+				tile_sync();
+				/* four independent accumulator chains (one per k-step of a block) instead of one chain of 4 nK MMAs;
+				 * DMMA step kk of lane (fr, fc) contracts k = 4 fc + kk, so both operands are 128-bit loads */
+				double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0, c4 = 0.0, c5 = 0.0, c6 = 0.0, c7 = 0.0;
+				const double2 *a = reinterpret_cast<const double2 *>(rp + (tm * 8 + fr) * rp_ld + (K0 - fI) * 16 + 4 * fc);
+				if (J < I) {
+					const double2 *b = reinterpret_cast<const double2 *>(M + (size_t)(T.blkptr[J] + K0 - T.fb[J]) * 256 + tn * 128) + lane;
+					for (int K = 0; K < nK; ++K) {
+						const double2 b01 = b[K * 128], b23 = b[K * 128 + 32];   /* plain loads: written earlier in this kernel */
+						const double2 a01 = a[K * 8], a23 = a[K * 8 + 1];
+						dmma(c0, c1, a01.x, b01.x); dmma(c2, c3, a01.y, b01.y);
+						dmma(c4, c5, a23.x, b23.x); dmma(c6, c7, a23.y, b23.y);
+					}
+				} else {
+					const double2 *b = reinterpret_cast<const double2 *>(rp + (tn * 8 + fr) * rp_ld + (K0 - fI) * 16 + 4 * fc);
+					for (int K = 0; K < nK; ++K) {
+						const double2 b01 = b[K * 8], b23 = b[K * 8 + 1];
+						const double2 a01 = a[K * 8], a23 = a[K * 8 + 1];
+						dmma(c0, c1, a01.x, b01.x); dmma(c2, c3, a01.y, b01.y);
+						dmma(c4, c5, a23.x, b23.x); dmma(c6, c7, a23.y, b23.y);
+					}
+				}
+				c0 = (c0 + c2) + (c4 + c6); c1 = (c1 + c3) + (c5 + c7);
+				/* S = A[I,J] - sum */
+				const double2 cA = *reinterpret_cast<const double2 *>(rp + (tm * 8 + fr) * rp_ld + (J - fI) * 16 + tn * 8 + 2 * fc);
+				double *sdst = J < I ? tmp : dS;
+				*reinterpret_cast<double2 *>(sdst + (tm * 8 + fr) * TLD + tn * 8 + 2 * fc) = make_double2(cA.x - c0, cA.y - c1);
+				if (J < I) {
+					/* L[I,J] = S * inv(L[J,J])' : second DMMA product, B = inv(L[J,J]) in fragment order from global */
+					const double2 *bi = reinterpret_cast<const double2 *>(Dinv + (size_t)J * 256 + tn * 128) + lane;
+					const double2 i01 = bi[0], i23 = bi[32];
+					tile_sync();
+					const double2 *ta = reinterpret_cast<const double2 *>(tmp + (tm * 8 + fr) * TLD + 4 * fc);
+					const double2 t01 = ta[0], t23 = ta[1];
+					double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+					dmma(x0, x1, t01.x, i01.x); dmma(x2, x3, t01.y, i01.y); dmma(x0, x1, t23.x, i23.x); dmma(x2, x3, t23.y, i23.y);
+					*reinterpret_cast<double2 *>(rp + (tm * 8 + fr) * rp_ld + (J - fI) * 16 + tn * 8 + 2 * fc) = make_double2(x0 + x2, x1 + x3);
+				}
+			}
+			/* ---- p = b_I - L[I,<I] z for the forward substitution (the off-diagonal row is final: every warp passed
+			 *      the barrier of the diagonal block after its last write) ---- */
+			{
+				const int r = tid >> 3, l8 = tid & 7;
+				double acc = 0.0;
+				const double *row = rp + r * rp_ld;
+				const double *zz = zs + fI * 16;
+				for (int c = l8; c < (wI - 1) * 16; c += 8) acc += row[c] * zz[c];
+				acc += __shfl_xor_sync(0xffffffffu, acc, 4); acc += __shfl_xor_sync(0xffffffffu, acc, 2); acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+				if (l8 == 0) part[r] = zs[I * 16 + r] - acc;
+			}
+			diag_ready_arrive();                       /* S and p are with the diagonal warp now */
+			/* ---- store the off-diagonal blocks of the row of L (fragment-major in global memory) ---- */
+			for (int q = tid; q < (wI - 1) * 128; q += 128) {   /* q = ((block * 2 + tn) * 2 + h) * 32 + lane, one 16-byte chunk each */
+				const int r = ((q >> 6) & 1) * 8 + ((q & 31) >> 2), c = 4 * (q & 3) + 2 * ((q >> 5) & 1);
+				reinterpret_cast<double2 *>(M + rowbase)[q] = *reinterpret_cast<const double2 *>(rp + r * rp_ld + (q >> 7) * 16 + c);
+			}
+		}
+		diag_done_wait();                              /* last diagonal block */
+		/* ---- backward substitution: L' x = z ---- */
+		for (int I = T.nb - 1; I >= 0; --I) {
+			const int fI = T.fb[I];
+			const double *rowg = M + (size_t)T.blkptr[I] * 256;
+			if (tid < 16) {
+				double v = 0.0;
+				const double *iv = Dinv + (size_t)I * 256;
+				for (int q = tid; q < 16; ++q) v += iv[frag_off(q, tid)] * zs[I * 16 + q];
+				part[tid] = v;
+			}
+			tile_sync();
+			if (tid < 16) zs[I * 16 + tid] = part[tid];
+			for (int c = tid; c < (I - fI) * 16; c += 128) {
+				const double *blk = rowg + (size_t)(c >> 4) * 256 + frag_off(0, c & 15);
+				double acc = 0.0;
+#pragma unroll
+				for (int q = 0; q < 16; ++q) acc += blk[((q >> 3) << 7) + ((q & 7) << 3)] * part[q];
+				zs[fI * 16 + c] -= acc;
+			}
+			tile_sync();
+		}
+		for (int i = tid; i < T.npad; i += 128) W.vec[(size_t)pid * T.npad + i] = zs[i];
+		if (tid == 0 && bad) W.flags[pid] |= 1;
 	}
-	for (int i = tid; i < T.npad; i += FT) W.vec[(size_t)pid * T.npad + i] = zs[i];
-	if (tid == 0 && bad) W.flags[pid] |= 1;
 }
 
 /* ------------------------------------------------------------------ k_step */
