@@ -625,7 +625,7 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 		 * so panel[i][perm(b)] += A_a . J_b is race-free and its summation order is fixed. */
 		int max_w = 0;
 		for (int I = 0; I < nb; ++I) max_w = std::max(max_w, I - H->fb[I] + 1);
-		H->max_w = max_w; H->rp_ld = max_w * NB + 2;    /* rows 16 bytes apart modulo 128: conflict-free 128-bit fragment loads */
+		H->max_w = max_w; H->rp_ld = max_w * NB + 8;    /* rows 64 bytes apart modulo 128: conflict-free fragment loads and stores (SWZ in qtos_kernels.cu) */
 		if (16 * H->rp_ld >= (1 << 13)) return fail("assembly: panel too wide for packed terms");
 		H->as_ptr.assign(1, 0); H->at_ptr.assign(1, 0); H->as_col.clear(); H->at.clear();
 		H->as_max = 0; H->asm_terms_total = 0;

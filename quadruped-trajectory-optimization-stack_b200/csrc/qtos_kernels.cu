@@ -255,12 +255,13 @@ k_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 
 #define FT 128           /* threads of the factor kernel: 4 warps, one 8x8 tile of a 16x16 block each */
 #ifndef FACTOR_MINB
-#define FACTOR_MINB 6    /* resident CTAs per SM the register allocation is bounded for */
+#define FACTOR_MINB 4    /* resident CTAs per SM (two panel buffers: 54 KB of shared memory per CTA for shape S2) */
 #endif
 #ifndef ASM_MINB
 #define ASM_MINB 6
 #endif
-#define TLD 18           /* padded leading dimension of 16x16 tiles in shared memory (conflict-free 128-bit fragment loads) */
+#define TLD 18           /* leading dimension of the diagonal block's hand-off tile (rows 4 banks apart for the row-per-lane reads) */
+#define TLT 24           /* leading dimension of the off-diagonal S tile: rows 16 banks apart, like the panel (see SWZ) */
 
 /* Blocks of L and the inverses of its diagonal blocks live in global memory in FRAGMENT-MAJOR order: the four
  * contraction values lane (fr, fc) of warp tile tn feeds to its four DMMA steps (k = 4 fc + kk) are stored as two
@@ -270,6 +271,13 @@ __device__ __forceinline__ int frag_off(int r, int c)
 {
 	return ((r >> 3) << 7) + (((c >> 1) & 1) << 6) + ((((r & 7) << 2) + (c >> 2)) << 1) + (c & 1);
 }
+
+/* Shared-memory tiles of k_factor (the panel and the off-diagonal S tile) keep rows 16 banks (64 bytes mod 128) apart
+ * and store ODD rows with the two 16-byte halves of every 32-byte group swapped (column pair p lives at p ^ 1).
+ * Accumulator fragments (one pair per lane, four lanes per row) and operand fragments (two pairs per lane, four lanes
+ * per row, 32 bytes apart) then both cover all 32 banks with every quarter-warp: no bank conflicts on either access,
+ * and the swap costs nothing at run time (a loop-invariant pointer offset). */
+#define SWZ(pair, row) ((pair) ^ ((row) & 1))
 
 /* D = A(8x4) * B(4x8) + C, FP64 tensor-core MMA; fragment layout (PTX ISA, m8n8k4):
  * a = A[lane>>2][lane&3], b = B[lane&3][lane>>2], c/d = C[lane>>2][2*(lane&3) + {0,1}] */
@@ -355,6 +363,17 @@ k_asm(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 	}
 }
 
+/* one assembled block row (16 x 2 w2 doubles, row-major in global memory) into a shared-memory panel, swizzled */
+__device__ __forceinline__ void panel_fetch(double *panel, int rp_ld, const double *src, int w2, int warp, int lane)
+{
+	const double2 *in = reinterpret_cast<const double2 *>(src);
+	for (int r = warp; r < 16; r += 4)
+		for (int c2 = lane; c2 < w2; c2 += 32) {
+			const unsigned dst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<double2 *>(panel + r * rp_ld) + SWZ(c2, r));
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(in + r * w2 + c2) : "memory");
+		}
+}
+
 /* named barriers of k_factor: the four tile warps among themselves, and the two hand-offs with the diagonal warp */
 #define FTT 160          /* threads of the factor kernel: four tile warps + one diagonal warp */
 __device__ __forceinline__ void tile_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -381,11 +400,12 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 	const int pid = blockIdx.x;
 	if (W.status[pid] != QTOS_RUNNING) return;
 	extern __shared__ __align__(16) double sm[];
-	double *rp = sm;                               /* [16][rp_ld]  current block row, row-major over the whole panel */
-	double *zs = rp + 16 * rp_ld;                  /* [npad] rhs -> z -> dx */
-	double *tmp = zs + T.npad;                     /* [16][TLD] S of an off-diagonal block (tile warps) */
-	double *dS = tmp + 16 * TLD;                   /* [16][TLD] S of the diagonal block -> inv(L_II) (hand-off buffer) */
-	double *part = dS + 16 * TLD;                  /* [16] */
+	double *rp0 = sm;                              /* [2][16][rp_ld]  block rows I (being swept) and I+1 (arriving), row-major panels */
+	double *zs = rp0 + 2 * 16 * rp_ld;             /* [npad] rhs -> z -> dx */
+	double *tmp = zs + T.npad;                     /* [16][TLT] S of an off-diagonal block (tile warps) */
+	double *dS = tmp + 16 * TLT;                   /* [16][TLD] S of the diagonal block -> inv(L_II) (hand-off buffer) */
+	double *part = dS + 16 * TLD;                  /* [16] rhs of the diagonal solves */
+	double *pp = part + 16;                        /* [2][16] L[I,<I] z, one half of the columns per tile column */
 	double *M = WS(M, T.nM), *Dinv = WS(Dinv, T.nb * 256);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	__shared__ int bad;
@@ -399,15 +419,17 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 			/* Cholesky of the 16x16 diagonal block and its inverse, in registers: lane r (and r + 16)
 			 * holds row r; pivots, columns and the rows of L travel by shuffle */
 			const int r = lane & 15;
-			double a[16], rinv[16];
+			double a[16], x[16];
 #pragma unroll
 			for (int c = 0; c < 16; ++c) a[c] = dS[r * TLD + c];
+			/* step j finishes column j of L, then entry j of this lane's column of inv(L) by forward substitution of e_r:
+			 * x_j = (delta_jr - sum_{k<j} L[j][k] x_k) / L[j][j]; the two are independent instruction streams, so the
+			 * substitution's FMA chain (split in two) runs under the latency of the next pivot's rsqrt */
 #pragma unroll
 			for (int j = 0; j < 16; ++j) {
 				double d = __shfl_sync(0xffffffffu, a[j], j);
 				if (!(d > 0.0)) { d = 1e-30; if (lane == 0) bad = 1; }
 				const double rl = rsqrt(d);
-				rinv[j] = rl;
 				const double lij = r == j ? d * rl : a[j] * rl;      /* L[r][j] for r >= j */
 				a[j] = lij;
 #pragma unroll
@@ -415,15 +437,13 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 					const double lkj = __shfl_sync(0xffffffffu, lij, k);
 					a[k] -= lij * lkj;                                  /* only r >= k is read later */
 				}
-			}
-			/* column r of inv(L) by forward substitution of e_r: x_i = (delta_ir - sum_{k<i} L[i][k] x_k) / L[i][i] */
-			double x[16];
+				double s0 = j == r ? 1.0 : 0.0, s1 = 0.0;
 #pragma unroll
-			for (int i = 0; i < 16; ++i) {
-				double sacc = i == r ? 1.0 : 0.0;
-#pragma unroll
-				for (int k = 0; k < i; ++k) sacc -= __shfl_sync(0xffffffffu, a[k], i) * x[k];
-				x[i] = i < r ? 0.0 : sacc * rinv[i];
+				for (int k = 0; k < j; ++k) {
+					const double ljk = __shfl_sync(0xffffffffu, a[k], j);
+					if (k & 1) s1 -= ljk * x[k]; else s0 -= ljk * x[k];
+				}
+				x[j] = j < r ? 0.0 : (s0 + s1) * rl;
 			}
 			__syncwarp();
 			if (lane < 16) {
@@ -433,6 +453,8 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 			__syncwarp();
 			/* inv(L[I,I]) to global (fragment-major) for later rows and the backward solve; z_I */
 			for (int q = lane; q < 256; q += 32) Dinv[(size_t)I * 256 + frag_off(q >> 4, q & 15)] = dS[(q >> 4) * TLD + (q & 15)];
+			if (lane < 16) part[lane] = zs[I * 16 + lane] - (pp[lane] + pp[16 + lane]);   /* p = b_I - L[I,<I] z */
+			__syncwarp();
 			if (lane < 16) {
 				double v = 0.0;
 				for (int q = 0; q <= lane; ++q) v += dS[lane * TLD + q] * part[q];
@@ -444,77 +466,79 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 		/* ---------------- tile warps ---------------- */
 		const int tm = warp >> 1, tn = warp & 1;       /* 8x8 tile of the 16x16 block owned by this warp */
 		const int fr = lane >> 2, fc = lane & 3;       /* fragment row / column */
+		const int odd = fr & 1;
+		panel_fetch(rp0, rp_ld, M, (T.blkptr[1] - T.blkptr[0]) * 8, warp, lane);
+		asm volatile("cp.async.commit_group;" ::: "memory");
 		for (int I = 0; I < T.nb; ++I) {
 			const int fI = T.fb[I], wI = I - fI + 1;
 			const int rowbase = T.blkptr[I] * 256;
-			tile_sync();                               /* the previous row has left the panel */
-			{   /* ---- the assembled block row ---- */
-				const double2 *in = reinterpret_cast<const double2 *>(M + rowbase);
-				const int w2 = wI * 8;
-				for (int q = tid; q < 16 * w2; q += 128) {
-					const int r = q / w2, c2 = q - r * w2;
-					*reinterpret_cast<double2 *>(rp + r * rp_ld + 2 * c2) = in[q];
-				}
-			}
+			double pacc = 0.0;                         /* this lane's share of L[I,<I] z (forward substitution) */
+			double *rp = rp0 + (I & 1) * 16 * rp_ld;
+			tile_sync();                               /* row I-1 has left the other panel buffer */
+			/* next row's assembled panel (k_asm) starts its way from HBM now and lands under this row's sweep:
+			 * asynchronous 16-byte copies, no register staging; this row's copies were issued one row ago */
+			if (I + 1 < T.nb) panel_fetch(rp0 + ((I + 1) & 1) * 16 * rp_ld, rp_ld, M + (size_t)T.blkptr[I + 1] * 256, (T.blkptr[I + 2] - T.blkptr[I + 1]) * 8, warp, lane);
+			asm volatile("cp.async.commit_group;" ::: "memory");
+			asm volatile("cp.async.wait_group 1;" ::: "memory");
 			if (I > 0 && fI == I) diag_done_wait();    /* no off-diagonal block: keep the hand-off in step */
 			for (int J = fI; J <= I; ++J) {
 				const int K0 = max(fI, T.fb[J]), nK = J - K0;
-				if (J == I - 1) diag_done_wait();      /* inv(L[I-1,I-1]) and z_{I-1} are needed from here on */
 				tile_sync();
 				/* four independent accumulator chains (one per k-step of a block) instead of one chain of 4 nK MMAs;
 				 * DMMA step kk of lane (fr, fc) contracts k = 4 fc + kk, so both operands are 128-bit loads */
 				double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0, c4 = 0.0, c5 = 0.0, c6 = 0.0, c7 = 0.0;
 				const double2 *a = reinterpret_cast<const double2 *>(rp + (tm * 8 + fr) * rp_ld + (K0 - fI) * 16 + 4 * fc);
+				const double2 *a_lo = a + odd, *a_hi = a + (odd ^ 1);       /* columns 4 fc, 4 fc + 1 / 4 fc + 2, 4 fc + 3 */
 				if (J < I) {
 					const double2 *b = reinterpret_cast<const double2 *>(M + (size_t)(T.blkptr[J] + K0 - T.fb[J]) * 256 + tn * 128) + lane;
 					for (int K = 0; K < nK; ++K) {
 						const double2 b01 = b[K * 128], b23 = b[K * 128 + 32];   /* plain loads: written earlier in this kernel */
-						const double2 a01 = a[K * 8], a23 = a[K * 8 + 1];
+						const double2 a01 = a_lo[K * 8], a23 = a_hi[K * 8];
 						dmma(c0, c1, a01.x, b01.x); dmma(c2, c3, a01.y, b01.y);
 						dmma(c4, c5, a23.x, b23.x); dmma(c6, c7, a23.y, b23.y);
 					}
 				} else {
 					const double2 *b = reinterpret_cast<const double2 *>(rp + (tn * 8 + fr) * rp_ld + (K0 - fI) * 16 + 4 * fc);
+					const double2 *b_lo = b + odd, *b_hi = b + (odd ^ 1);
 					for (int K = 0; K < nK; ++K) {
-						const double2 b01 = b[K * 8], b23 = b[K * 8 + 1];
-						const double2 a01 = a[K * 8], a23 = a[K * 8 + 1];
+						const double2 b01 = b_lo[K * 8], b23 = b_hi[K * 8];
+						const double2 a01 = a_lo[K * 8], a23 = a_hi[K * 8];
 						dmma(c0, c1, a01.x, b01.x); dmma(c2, c3, a01.y, b01.y);
 						dmma(c4, c5, a23.x, b23.x); dmma(c6, c7, a23.y, b23.y);
 					}
 				}
 				c0 = (c0 + c2) + (c4 + c6); c1 = (c1 + c3) + (c5 + c7);
 				/* S = A[I,J] - sum */
-				const double2 cA = *reinterpret_cast<const double2 *>(rp + (tm * 8 + fr) * rp_ld + (J - fI) * 16 + tn * 8 + 2 * fc);
-				double *sdst = J < I ? tmp : dS;
-				*reinterpret_cast<double2 *>(sdst + (tm * 8 + fr) * TLD + tn * 8 + 2 * fc) = make_double2(cA.x - c0, cA.y - c1);
+				const int cp = SWZ(tn * 4 + fc, fr);       /* this lane's column pair of the block, as stored */
+				const double2 cA = reinterpret_cast<const double2 *>(rp + (tm * 8 + fr) * rp_ld + (J - fI) * 16)[cp];
+				const double2 sij = make_double2(cA.x - c0, cA.y - c1);
+				if (J < I) reinterpret_cast<double2 *>(tmp + (tm * 8 + fr) * TLT)[cp] = sij;
+				else *reinterpret_cast<double2 *>(dS + (tm * 8 + fr) * TLD + tn * 8 + 2 * fc) = sij;   /* plain layout for the diagonal warp */
 				if (J < I) {
 					/* L[I,J] = S * inv(L[J,J])' : second DMMA product, B = inv(L[J,J]) in fragment order from global */
+					if (J == I - 1) diag_done_wait();  /* inv(L[I-1,I-1]) and z_{I-1} are needed from here on, not earlier */
 					const double2 *bi = reinterpret_cast<const double2 *>(Dinv + (size_t)J * 256 + tn * 128) + lane;
 					const double2 i01 = bi[0], i23 = bi[32];
 					tile_sync();
-					const double2 *ta = reinterpret_cast<const double2 *>(tmp + (tm * 8 + fr) * TLD + 4 * fc);
-					const double2 t01 = ta[0], t23 = ta[1];
+					const double2 *ta = reinterpret_cast<const double2 *>(tmp + (tm * 8 + fr) * TLT + 4 * fc);
+					const double2 t01 = ta[odd], t23 = ta[odd ^ 1];
 					double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
 					dmma(x0, x1, t01.x, i01.x); dmma(x2, x3, t01.y, i01.y); dmma(x0, x1, t23.x, i23.x); dmma(x2, x3, t23.y, i23.y);
-					*reinterpret_cast<double2 *>(rp + (tm * 8 + fr) * rp_ld + (J - fI) * 16 + tn * 8 + 2 * fc) = make_double2(x0 + x2, x1 + x3);
+					const double2 lij = make_double2(x0 + x2, x1 + x3);
+					reinterpret_cast<double2 *>(rp + (tm * 8 + fr) * rp_ld + (J - fI) * 16)[cp] = lij;
+					/* forward substitution fused into the sweep: z_J is final (J <= I-1, hand-off passed above) */
+					const double2 zj = *reinterpret_cast<const double2 *>(zs + J * 16 + tn * 8 + 2 * fc);
+					pacc += lij.x * zj.x + lij.y * zj.y;
 				}
 			}
-			/* ---- p = b_I - L[I,<I] z for the forward substitution (the off-diagonal row is final: every warp passed
-			 *      the barrier of the diagonal block after its last write) ---- */
-			{
-				const int r = tid >> 3, l8 = tid & 7;
-				double acc = 0.0;
-				const double *row = rp + r * rp_ld;
-				const double *zz = zs + fI * 16;
-				for (int c = l8; c < (wI - 1) * 16; c += 8) acc += row[c] * zz[c];
-				acc += __shfl_xor_sync(0xffffffffu, acc, 4); acc += __shfl_xor_sync(0xffffffffu, acc, 2); acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-				if (l8 == 0) part[r] = zs[I * 16 + r] - acc;
-			}
-			diag_ready_arrive();                       /* S and p are with the diagonal warp now */
+			/* ---- L[I,<I] z of this warp's tile column: four lanes per row ---- */
+			pacc += __shfl_xor_sync(0xffffffffu, pacc, 1); pacc += __shfl_xor_sync(0xffffffffu, pacc, 2);
+			if (fc == 0) pp[tn * 16 + tm * 8 + fr] = pacc;
+			diag_ready_arrive();                       /* S and L[I,<I] z are with the diagonal warp now */
 			/* ---- store the off-diagonal blocks of the row of L (fragment-major in global memory) ---- */
-			for (int q = tid; q < (wI - 1) * 128; q += 128) {   /* q = ((block * 2 + tn) * 2 + h) * 32 + lane, one 16-byte chunk each */
-				const int r = ((q >> 6) & 1) * 8 + ((q & 31) >> 2), c = 4 * (q & 3) + 2 * ((q >> 5) & 1);
-				reinterpret_cast<double2 *>(M + rowbase)[q] = *reinterpret_cast<const double2 *>(rp + r * rp_ld + (q >> 7) * 16 + c);
+			for (int q = tid; q < (wI - 1) * 128; q += 128) {   /* chunk ((block * 2 + tn) * 2 + h) * 32 + lane, 16 bytes each */
+				const int r = ((q >> 6) & 1) * 8 + ((q & 31) >> 2);
+				reinterpret_cast<double2 *>(M + rowbase)[q] = reinterpret_cast<const double2 *>(rp + r * rp_ld + (q >> 7) * 16)[SWZ(2 * (q & 3) + ((q >> 5) & 1), r)];
 			}
 		}
 		diag_done_wait();                              /* last diagonal block */
