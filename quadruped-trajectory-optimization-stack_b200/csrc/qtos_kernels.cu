@@ -65,6 +65,10 @@ k_init(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *
 	__shared__ double sfin[6][3];
 	const int hid = pr.hf_id >= 0 && pr.hf_id < n_hf ? pr.hf_id : 0;
 	const DevHeightfield hf = hfs[hid];
+	/* do_solver_init: 0 = x0 only (qtos_get_initial / qtos_eval); 1 = x0, g(x0), constant Jacobian elements, problem
+	 * marked running -- the x-dependent elements then come from k_jac_dyn / k_jac_rom (one thread per sample instead
+	 * of one block per problem); 2 = row scaling from J(x0), scaled J, slacks and multipliers */
+	if (do_solver_init == 2) goto scaling;
 	if (threadIdx.x == 0) {
 		for (int d = 0; d < 3; ++d) {
 			P[QP_START_POS + d] = pr.start_pos[d]; P[QP_START_ANG + d] = pr.start_ang[d];
@@ -100,9 +104,9 @@ k_init(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *
 	__syncthreads();
 	eval_g_block(T, hf, x, r);
 	for (int i = threadIdx.x; i < T.nJ; i += blockDim.x) Jv[i] = T.Jconst[i];
-	__syncthreads();
-	eval_jac_block(T, x, sc, Jv);
-	__syncthreads();
+	if (threadIdx.x == 0) { W.status[pid] = QTOS_RUNNING; W.iters[pid] = 0; W.flags[pid] = 0; }
+	return;
+scaling:
 	/* gradient-based row scaling min(1, 100/||row||_inf) at x0 */
 	for (int i = threadIdx.x; i < T.m; i += blockDim.x) {
 		const Element &E = T.elems[T.row_elem[i]];
@@ -141,7 +145,6 @@ k_init(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *
 	if (threadIdx.x == 0) {
 		double *scal = WS(scal, 16);
 		scal[SC_MU] = opt.mu_init; scal[SC_NU] = 1.0; scal[SC_NFAIL] = 0.0;
-		W.status[pid] = QTOS_RUNNING; W.iters[pid] = 0; W.flags[pid] = 0;
 	}
 }
 

@@ -8,6 +8,8 @@ from bench import build_workload, COMBO, DURATION
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 grid, res, p = build_workload(n)
+if os.environ.get("QTOS_SHAPE") == "S5":        # production shape (Custom gait, 5 s) on the same workload
+    COMBO, DURATION = "Custom", 5.0
 S = Q.Solver(Q.default_shape(COMBO, DURATION), max_batch=n)
 p["hf_id"] = S.upload_heightfield(grid, res)
 S.set_profiling(True)
