@@ -28,9 +28,16 @@ sys.path.insert(0, ROOT)
 PER_GPU = 4096
 GROUP = 8
 COMBO, DURATION = "C1", 2.0
+WORKLOAD = ("batched multi-start: %d start/goal pairs per GPU on a 256x256 rough heightfield (seed 1234), trot C1, "
+            "T=2s, 640 vars / 892 cons; groups of 8 candidates, best-plan all-gather" % PER_GPU)
 # algorithmic work of ONE factorization of the primal normal matrix of shape S2
 # (n_free = 605, RCM envelope 50 728 entries): sum_i w_i^2 = 6.3e6 FP64 flop
 ALG_FLOP_PER_FACTORIZATION = 6.3e6
+# DRAM traffic of k_factor per factorization, from the ncu --set full capture of one launch with all 4096 problems
+# active (profiles/r01d_summary.md: dram__bytes_read.sum + dram__bytes_write.sum over 4096 factorizations); the
+# algorithmic bytes are the assembled matrix read once and the factor written once: 2 x 59 648 doubles = 0.954 MB
+NCU_DRAM_BYTES_PER_FACTORIZATION = 1.337e6
+ALG_BYTES_PER_FACTORIZATION = 2 * 59648 * 8
 
 
 def build_workload(n_total, seed=1234):
@@ -86,14 +93,14 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "converged gait-plan NLP solves/sec", "value": value, "unit": "solves/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_sample / value,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "batched multi-start: start/goal pairs on a 256x256 rough heightfield, trot C1, T=2s (640 vars / 892 cons)",
+            "config": {"workload": WORKLOAD, "problems_per_gpu": PER_GPU, "parallelism": "host cores",
                        "sample": "%d of the %d windows per step" % (n_sample, PER_GPU)},
             "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
                              "sample": "%d windows of the bench workload per step, one process per core; oracle/towr_ipm.c "
                                        "(same IPM as the GPU path; TOWR+Ipopt itself cannot be built here)" % n_sample,
                              "p50_latency_ms": 1e3 * p50},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -264,8 +271,7 @@ def run_gpu(args):
         "metric": "converged gait-plan NLP solves/sec", "value": value, "unit": "solves/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "batched multi-start: %d start/goal pairs per GPU on a 256x256 rough heightfield (seed 1234), trot C1, "
-                               "T=2s, 640 vars / 892 cons; groups of 8 candidates, best-plan all-gather" % PER_GPU,
+        "config": {"workload": WORKLOAD,
                    "problems_per_gpu": PER_GPU, "parallelism": "shard%d" % world,
                    "l2": "per-step working set %.1f GB per GPU > 126 MB L2" % (PER_GPU * dims.workspace_bytes_per_problem / 1e9)},
         "converged_fraction": conv_all / (args.steps * n_total), "iters_mean": float(iters.mean()), "iters_max": int(iters.max()),
@@ -274,23 +280,41 @@ def run_gpu(args):
                 "d2h_bytes_per_step": int(n * (Q.RESULT_DTYPE.itemsize + 8 * S.n_vars)), "ms_per_step": e_ms},
         "gpu_launches": int(launches),
         "phase_ms_per_step": {k: v / args.steps for k, v in phase.items()},
-        "roofline": {"kernel": "k_factor (block-skyline Cholesky of the condensed KKT matrix)", "bound": "fp64",
+        "roofline": {"kernel": "k_factor (block-skyline Cholesky of the condensed KKT matrix)", "bound": "tensor",
+                     "bound_detail": "FP64: 16x16 block updates on the FP64 tensor-core path (DMMA m8n8k4); SURVEY 8(d) names the "
+                                     "FP64 FMA rate as the bounding roofline, and B200's FP64 tensor and FMA peaks coincide",
                      "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (achieved / fp64_peak) if achieved else None,
                      "peak_source": "FP64 FMA loop measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                      "alg_flop_per_factorization": ALG_FLOP_PER_FACTORIZATION, "factorizations_per_step": fact / args.steps,
-                     "avg_launch_ms": fact_ms / max(1, fact_launches), "traffic": None,
+                     "avg_launch_ms": fact_ms / max(1, fact_launches),
+                     "traffic": NCU_DRAM_BYTES_PER_FACTORIZATION * fact / max(1, fact_launches),
+                     "traffic_unit": "bytes per average launch (ncu dram bytes per factorization x factorizations per launch)",
+                     "algorithmic_bytes": ALG_BYTES_PER_FACTORIZATION * fact / max(1, fact_launches),
                      "hbm_peak_gbs": peaks.get("hbm_gbs")},
         "cpu_baseline": {"value": cpu_v, "unit": "solves/s", "cores": cpu_cores, "kind": "port",
                          "sample": "128 windows of the same workload, one process per core, oracle/towr_ipm.c",
                          "p50_latency_ms": 1e3 * cpu_p50},
         "clocks": parse_clocks(clk_path),
     }
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line):
+    """the one JSON line goes to the process's real stdout; everything else that lands on fd 1 (NCCL's version banner,
+    library chatter) was redirected to stderr by main()"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
