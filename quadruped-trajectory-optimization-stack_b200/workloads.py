@@ -30,3 +30,26 @@ def multistart_problems(n, grid, res, seed=1234, hf_id=0, group_size=1):
 def terrain_variants(n_variants=8):
     """seeds 0..n-1 of the config-4 generator."""
     return [rough_terrain(seed=s) for s in range(n_variants)]
+
+
+def replan_problems(prev_problems, rows, lookahead_row, step=(0.4, 0.0)):
+    """Receding-horizon successors (config 5): the next window of every plan starts from the plan's own state at
+    `lookahead_row` of its 1 kHz CSV rows -- what Combiner._state reads back from towr.csv (ref: QTOS/combiner.py:245-296,
+    scripts/main.py:177 lookahead) and scripts/main.py turns into -s / -s_ang / -e1..-e4 / -t; the goal moves on by `step`.
+    The reference never passes `-n`, so ./main zeroes the start velocities (main.cpp:237-242); mirrored here."""
+    from .handoff import state_of_row, EE_NAMES
+    n = len(prev_problems)
+    p = prev_problems.copy()
+    for i in range(n):
+        row = rows[i][lookahead_row]
+        st = state_of_row(row)
+        p["start_pos"][i] = st["CoM"]
+        p["start_ang"][i] = st["orientation"]
+        p["start_vel"][i] = 0.0
+        p["start_ang_vel"][i] = 0.0
+        for e, name in enumerate(EE_NAMES):
+            p["ee"][i, e] = st[name]
+        p["t_start"][i] = row[0]
+        p["goal"][i, 0] = prev_problems["goal"][i, 0] + step[0]
+        p["goal"][i, 1] = prev_problems["goal"][i, 1] + step[1]
+    return p

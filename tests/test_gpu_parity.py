@@ -222,3 +222,64 @@ def test_cli_clone_writes_reference_csv(tmp_path, golden_hf):
     assert first[0] == 1.25 and first[1:4] == [0.0, 0.0, 0.24] and first[7:10] == [0.21, 0.19, 0.0]
     assert float(text[-1].split(",")[0]) == 6.25
     assert towr_cli.towr_main(["-g", "0.5", "0", "0.24"], cwd=str(tmp_path), quiet=True) == 2      # missing heightfield
+
+
+def test_replan_sweep_over_terrain_variants(solvers, oracle):
+    """BASELINE config 5 in small: terrain variants as separate device-resident grids inside ONE batch, then the
+    receding-horizon successors started from each plan's own state (contact-phase row), best plan per group of candidates."""
+    from qtos_b200 import parallel
+    S = solvers["S2"]
+    variants = workloads.terrain_variants(3)
+    probs = []
+    for v, (grid, res) in enumerate(variants):
+        hid = S.upload_heightfield(grid, res)
+        probs.append(workloads.multistart_problems(8, grid, res, seed=100 + v, hf_id=hid, group_size=4))
+        probs[-1]["group"] += 2 * v
+    p = np.concatenate(probs)
+    r, x, rows = S.solve(p, csv=True)
+    assert (r["status"] == 0).mean() >= 0.9
+    so = oracle.default_shape(*SHAPES["S2"])
+    for i in (0, 9, 17, 23):                                  # one window per variant (+1) against the oracle on ITS grid
+        grid, res = variants[i // 8]
+        po = oracle_problem(oracle, so, p[i], grid, res)
+        xo, ro = po.solve()
+        assert r["status"][i] == ro.status
+        assert np.abs(rows[i][:, 1:19] - po.csv(xo)[:, 1:19]).max() < TRAJ_TOL_M
+    # a variant's plan must not depend on which other grids share the batch
+    r1, x1, _ = S.solve(p[8:16])
+    assert np.array_equal(x1, x[8:16])
+    # successors: all four feet are in stance at the last row of a trot window (ref: combiner.check_legs_contact)
+    nxt = workloads.replan_problems(p, rows, rows.shape[1] - 1)
+    assert np.allclose(nxt["t_start"], 2.0) and np.all(nxt["start_vel"] == 0)
+    r2, x2, rows2 = S.solve(nxt, csv=True)
+    ok = (r["status"] == 0) & (r2["status"] == 0)
+    assert ok.mean() >= 0.75
+    assert np.allclose(rows2[ok][:, 0, 1:7], rows[ok][:, -1, 1:7], atol=1e-12)       # CoM pose is continuous across the hand-over
+    assert np.allclose(rows2[ok][:, 0, 7:19], rows[ok][:, -1, 7:19], atol=1e-12)     # and so are the footholds
+    assert np.allclose(rows2[:, 0, 0], 2.0) and np.allclose(rows2[:, -1, 0], 4.0)
+    i = int(np.flatnonzero(ok)[0])
+    grid, res = variants[i // 8]
+    xo, ro = oracle_problem(oracle, so, nxt[i], grid, res).solve()
+    assert ro.status == r2["status"][i]
+    # best plan per group of 4 candidates: deterministic key, one winner per group, winners are converged when any is
+    winners, _ = parallel.select_best(parallel.make_records(r2, np.arange(len(p)), nxt["group"]))
+    assert sorted(winners) == list(range(6))
+    for g, w in winners.items():
+        members = np.flatnonzero(nxt["group"] == g)
+        assert w in members
+        if (r2["status"][members] == 0).any():
+            assert r2["status"][w] == 0 and r2["cost"][w] == r2["cost"][members][r2["status"][members] == 0].min()
+
+
+def test_chunking_and_argument_errors(solvers):
+    """n > max_batch is solved in chunks with identical results; bad calls fail loudly."""
+    S = solvers["S2"]
+    p, grid, res = _rough(S, 20)
+    r, x, _ = S.solve(p)
+    S8 = Q.Solver(Q.default_shape(*SHAPES["S2"]), max_batch=8)
+    p8 = p.copy(); p8["hf_id"] = S8.upload_heightfield(grid, res)
+    r8, x8, rows8 = S8.solve(p8, csv=True)
+    assert np.array_equal(x8, x) and np.array_equal(r8["iters"], r["iters"]) and rows8.shape == (20, 2001, 37)
+    with pytest.raises(Q.QtosError):
+        S8.solve(p8[:0])
+    S8.close()
