@@ -619,7 +619,7 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 		std::vector<std::vector<uint32_t>> jt(npad);
 		for (size_t e = 0; e < H->elems.size(); ++e)
 			for (size_t a = 0; a < ecols[e].size(); ++a) jt[pos[ecols[e][a]]].push_back((uint32_t)(e << 8) | (uint32_t)a);
-		/* assembly lists: warp w of the factor kernel owns panel rows i % 4 == w of every block row and walks a
+		/* assembly lists: warp w of the assembly kernel owns panel rows 4 w .. 4 w + 3 of every block row and walks a
 		 * flat stream of terms (element e, row column a, column b <= a in permuted order), 32 per step, one per
 		 * lane.  Inside a step all targets are distinct (steps are closed early with no-op terms otherwise),
 		 * so panel[i][perm(b)] += A_a . J_b is race-free and its summation order is fixed. */
@@ -637,23 +637,33 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 				for (size_t e = 0; e < H->elems.size(); ++e) {
 					const Element &E = H->elems[e];
 					const std::vector<int> &c = ecols[e];
+					/* the columns of this element that land in the warp's four panel rows, staged in order */
+					std::vector<int> own, own_k;
 					for (size_t a = 0; a < c.size(); ++a) {
 						const int pa = pos[c[a]];
-						if (pa / NB != I || (pa % NB) % 4 != w) continue;
+						if (pa / NB != I || (pa % NB) / 4 != w) continue;
 						const int k = (int)H->as_col.size() - s0;
 						if (k > 511) return fail("assembly: too many staged columns in a block row");
 						AsmCol A; A.voff = E.valoff + (int)a * E.ld; A.row0 = (int16_t)E.row0; A.nrows = (uint8_t)E.nrows; A.i = (uint8_t)(pa % NB);
 						H->as_col.push_back(A);
-						for (size_t b = 0; b <= a; ++b) {        /* columns are sorted: pos[c[b]] <= pa */
+						own.push_back((int)a); own_k.push_back(k);
+					}
+					if (own.empty()) continue;
+					/* terms in (b, a) order: 32 consecutive lanes cover ~32/|own| consecutive columns b times all own
+					 * columns a, so a step touches few distinct J columns (B operand, global) and few staged columns */
+					for (int b = 0; b <= own.back(); ++b)
+						for (size_t j = 0; j < own.size(); ++j) {
+							const int a = own[j];
+							if (b > a) continue;                         /* columns are sorted: pos[c[b]] <= pos[c[a]] */
+							const int pa = pos[c[a]];
 							const int off = (pa % NB) * H->rp_ld + pos[c[b]] - H->fb[I] * NB;
 							if (a - b > 127) return fail("assembly: element too wide for packed terms");
 							if (in_step.count(off)) close_step();
 							in_step.insert(off);
-							H->at.push_back((uint32_t)(E.ld / 2) | ((uint32_t)k << 2) | ((uint32_t)(a - b) << 11) | ((uint32_t)off << 18));
+							H->at.push_back((uint32_t)(E.ld / 2) | ((uint32_t)own_k[j] << 2) | ((uint32_t)(a - b) << 11) | ((uint32_t)off << 18));
 							H->asm_terms_total++;
 							if (H->at.size() % 32 == 0) in_step.clear();
 						}
-					}
 				}
 				close_step();
 				H->at_ptr.push_back((int)H->at.size());

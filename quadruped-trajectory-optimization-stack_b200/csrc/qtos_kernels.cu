@@ -292,7 +292,9 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
 /* Assembly of one block row of the condensed KKT matrix A = sigma I + J' D J, one CTA per (problem, block row):
  * stage A_a = D J[:, a] for every (element, column a) of the block row in shared memory, then every warp walks its
  * flat term stream, one term per lane: panel[i(a)][perm(b)] += A_a . J[:, b].  Warp w owns the panel rows
- * i % 4 == w and the targets inside one step are distinct, so the sums are race-free and their order is fixed.
+ * 4 w .. 4 w + 3 and the targets inside one step are distinct, so the sums are race-free and their order is fixed
+ * (elements ascending per target).  Terms of an element run in (b, a) order: a step of 32 lanes touches ~8 J columns
+ * and the warp's <= 4 staged columns, a third of the L1 wavefronts of the (a, b) order.
  * Block rows are independent, so the grid is problems x block rows and no CTA carries a serial chain; the finished
  * panel (16 x 16 w_I, row-major) goes to the block row's slot of M, where k_factor picks it up. */
 __global__ void __launch_bounds__(FT, ASM_MINB)
@@ -309,11 +311,23 @@ k_asm(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 	const int fI = T.fb[I], wI = I - fI + 1, wcols = wI * 16;
 	{
 		const int s0 = T.as_ptr[I], nst = T.as_ptr[I + 1] - s0;
-		for (int q = tid; q < nst * 6; q += FT) {
-			const int k = q / 6, r = q - 6 * k;
+		/* one thread per staged column: its (up to) six values are three 128-bit loads, all in flight together */
+		for (int k = tid; k < nst; k += FT) {
 			const AsmCol C = T.as_col[s0 + k];
-			As[q] = r < C.nrows ? Sig[C.row0 + r] * Jv[C.voff + r] : 0.0;
-			if (r == 0) av[k] = C.voff;
+			const double2 *src = reinterpret_cast<const double2 *>(Jv + C.voff);
+			const int n2 = (C.nrows + 1) >> 1;
+			double2 v0 = src[0], v1 = make_double2(0.0, 0.0), v2 = v1;
+			if (n2 > 1) v1 = src[1];
+			if (n2 > 2) v2 = src[2];
+			const double *sg = Sig + C.row0;
+			double s6[6];
+#pragma unroll
+			for (int r = 0; r < 6; ++r) s6[r] = r < C.nrows ? sg[r] : 0.0;
+			double2 *dst = reinterpret_cast<double2 *>(As + 6 * k);
+			dst[0] = make_double2(s6[0] * v0.x, s6[1] * v0.y);
+			dst[1] = make_double2(s6[2] * v1.x, s6[3] * v1.y);
+			dst[2] = make_double2(s6[4] * v2.x, s6[5] * v2.y);
+			av[k] = C.voff;
 		}
 		for (int r = warp; r < 16; r += FT / 32)
 			for (int c = lane; c < wcols; c += 32) rp[r * rp_ld + c] = 0.0;
@@ -321,12 +335,17 @@ k_asm(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 	__syncthreads();
 	{
 		const int t0 = T.at_ptr[I * 4 + warp], t1 = T.at_ptr[I * 4 + warp + 1];
-		/* four steps in flight: descriptors, then the J columns of all four, then the sums in step order */
+		/* four steps in flight: the J columns of all four, then the sums in step order; the descriptors of the NEXT four
+		 * steps are fetched one round trip ahead (the loop is bound by its dependent round trips descriptor -> J column,
+		 * not by the L1 data pipe: deeper register pipelines cost occupancy and lose) */
+		uint32_t dn[4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) dn[u] = t0 + lane + 32 * u < t1 ? __ldg(T.at + t0 + lane + 32 * u) : 0u;
 		for (int t = t0 + lane; t < t1; t += 128) {
 			uint32_t d[4];
 			double2 b[4][3];
 #pragma unroll
-			for (int u = 0; u < 4; ++u) d[u] = t + 32 * u < t1 ? __ldg(T.at + t + 32 * u) : 0u;
+			for (int u = 0; u < 4; ++u) { d[u] = dn[u]; dn[u] = t + 128 + 32 * u < t1 ? __ldg(T.at + t + 128 + 32 * u) : 0u; }
 #pragma unroll
 			for (int u = 0; u < 4; ++u) {
 				const int n2 = d[u] & 3;
