@@ -671,10 +671,22 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 			H->as_ptr.push_back((int)H->as_col.size());
 			H->as_max = std::max(H->as_max, (int)H->as_col.size() - s0);
 		}
-		H->jt_ptr.assign(1, 0);
-		for (int i = 0; i < npad; ++i) {
-			H->jt_terms.insert(H->jt_terms.end(), jt[i].begin(), jt[i].end());
-			H->jt_ptr.push_back((int)H->jt_terms.size());
+		H->jg_ptr.assign(1, 0); H->jg.clear();
+		for (int g = 0; g * 32 < npad; ++g) {
+			size_t ns = 0;
+			for (int l = 0; l < 32 && g * 32 + l < npad; ++l) ns = std::max(ns, jt[g * 32 + l].size());
+			for (size_t st = 0; st < ns; ++st)
+				for (int l = 0; l < 32; ++l) {
+					const int i = g * 32 + l;
+					uint2_t d; d.x = d.y = 0;
+					if (i < npad && st < jt[i].size()) {
+						const Element &E = H->elems[jt[i][st] >> 8];
+						d.x = (uint32_t)(E.valoff + (int)(jt[i][st] & 255u) * E.ld) | ((uint32_t)E.nrows << 20);
+						d.y = (uint32_t)E.row0;
+					}
+					H->jg.push_back(d);
+				}
+			H->jg_ptr.push_back((int)H->jg.size());
 		}
 	}
 

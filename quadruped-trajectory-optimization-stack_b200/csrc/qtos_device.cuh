@@ -39,7 +39,7 @@ struct DevTables {
 	const int *ter_row; const int16_t *ter_var;
 	const int *fb, *blkptr, *diag_off;
 	const int *as_ptr, *at_ptr; const AsmCol *as_col; const uint32_t *at;
-	const int *jt_ptr; const uint32_t *jt_terms;
+	const int *jg_ptr; const uint2_t *jg;
 	const double *csv_t, *csv_tl; const uint8_t *csv_id;
 	const double *dur; int dur_ld;          /* [10][dur_ld] */
 	double nominal[QTOS_NEE][3];

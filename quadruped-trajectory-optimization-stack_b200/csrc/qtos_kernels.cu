@@ -179,20 +179,45 @@ k_jac_rom(DevTables T, DevWork W, int n)
 
 /* ------------------------------------------------------------------ k_prepare */
 
+#ifndef JG_U
+#define JG_U 2          /* terms in flight per lane of the J' v gather: more costs the fourth resident CTA and loses */
+#endif
+#ifndef PREP_MINB
+#define PREP_MINB 4
+#endif
+#ifndef STEP_MINB
+#define STEP_MINB 4      /* four CTAs per SM: the line search is latency-bound, the fourth CTA pays for ~1.7 KB of spills */
+#endif
+/* (J' v)_i for variable i (all 32 lanes of a warp call it together, i = 32 g + lane): self-contained term descriptors,
+ * read coalesced, four terms in flight; the sum runs in term order, rows ascending */
 __device__ __forceinline__ double jt_gather(const DevTables &T, const double *Jv, const double *wrow, int i)
 {
+	const int g = i >> 5, base = T.jg_ptr[g], ns = (T.jg_ptr[g + 1] - base) >> 5;
+	const uint2 *tk = reinterpret_cast<const uint2 *>(T.jg) + base + (i & 31);
 	double acc = 0.0;
-	for (int q = T.jt_ptr[i]; q < T.jt_ptr[i + 1]; ++q) {
-		const uint32_t t = T.jt_terms[q];
-		const Element &E = T.elems[t >> 8];
-		const double *col = Jv + E.valoff + (t & 255u) * E.ld;
-		const double *wr = wrow + E.row0;
-		for (int rr = 0; rr < E.nrows; ++rr) acc += col[rr] * wr[rr];
+	for (int s = 0; s < ns; s += JG_U) {
+		uint2 d[JG_U];
+		double c[JG_U][6], w[JG_U][6];
+#pragma unroll
+		for (int u = 0; u < JG_U; ++u) d[u] = s + u < ns ? __ldg(tk + 32 * (s + u)) : make_uint2(0u, 0u);
+#pragma unroll
+		for (int u = 0; u < JG_U; ++u) {
+			const int nr = d[u].x >> 20;
+			const double *col = Jv + (d[u].x & 0xfffffu), *wr = wrow + d[u].y;
+#pragma unroll
+			for (int rr = 0; rr < 6; ++rr) { c[u][rr] = rr < nr ? col[rr] : 0.0; w[u][rr] = rr < nr ? wr[rr] : 0.0; }
+		}
+#pragma unroll
+		for (int u = 0; u < JG_U; ++u) {
+			const int nr = d[u].x >> 20;
+#pragma unroll
+			for (int rr = 0; rr < 6; ++rr) if (rr < nr) acc += c[u][rr] * w[u][rr];
+		}
 	}
 	return acc;
 }
 
-__global__ void __launch_bounds__(QTOS_THREADS)
+__global__ void __launch_bounds__(QTOS_THREADS, PREP_MINB)
 k_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 {
 	const int pid = blockIdx.x;
@@ -203,7 +228,7 @@ k_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 	double *y = WS(y, T.m), *Sig = WS(Sig, T.m), *w = WS(w, T.m), *dy = WS(dy, T.m), *vec = WS(vec, T.npad), *scal = WS(scal, 16);
 	/* v: 0 dual_inf(max) 1 theta_inf(max) 2 compl max 3 compl min 4 sum|y| 5 sum z 6 viol(max) */
 	double v[7] = {0, 0, 0, 1e300, 0, 0, 0};
-	for (int i = threadIdx.x; i < T.n_free; i += blockDim.x) v[0] = fmax(v[0], fabs(jt_gather(T, Jv, y, i)));
+	for (int i = threadIdx.x; i < T.npad; i += blockDim.x) v[0] = fmax(v[0], fabs(jt_gather(T, Jv, y, i)));   /* padding variables have no terms */
 	for (int i = threadIdx.x; i < T.m; i += blockDim.x) {
 		const int fl = T.row_flags[i];
 		v[4] += fabs(y[i]);
@@ -251,7 +276,10 @@ k_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 		w[i] = y[i] + sg * (r[i] - s[i]) + rsm;
 	}
 	__syncthreads();
-	for (int i = threadIdx.x; i < T.npad; i += blockDim.x) vec[i] = i < T.n_free ? -jt_gather(T, Jv, w, i) : 0.0;
+	for (int i = threadIdx.x; i < ((T.npad + 31) & ~31); i += blockDim.x) {
+		const double gi = jt_gather(T, Jv, w, i);
+		if (i < T.npad) vec[i] = i < T.n_free ? -gi : 0.0;
+	}
 }
 
 /* ------------------------------------------------------------------ k_factor */
@@ -594,7 +622,7 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 
 /* three CTAs per SM (<= 85 registers): the evaluation inside the line search is latency-bound, occupancy pays more
  * than the 24 bytes of spill cost (17.8 -> 9.1 ms per bench step) */
-__global__ void __launch_bounds__(QTOS_THREADS, 3)
+__global__ void __launch_bounds__(QTOS_THREADS, STEP_MINB)
 k_step(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *hfs, int n_hf, qtos_options opt)
 {
 	const int pid = blockIdx.x;

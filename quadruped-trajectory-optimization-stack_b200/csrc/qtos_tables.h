@@ -66,6 +66,8 @@ struct AsmCol {                    /* one staged column (element e, local column
 	uint8_t  nrows, i;             /* rows of the element; panel row (variable perm % 16) the column adds into */
 };
 
+struct uint2_t { uint32_t x, y; };   /* 64-bit table entry, read as uint2 on the device */
+
 struct HostTables {
 	qtos_shape shape;
 	/* dimensions */
@@ -118,8 +120,11 @@ struct HostTables {
 	int as_max = 0;                                      /* most staged columns of one block row */
 	int max_w = 0, rp_ld = 0;                            /* widest block row (blocks); leading dimension of the shared-memory panel */
 	long long asm_terms_total = 0;                       /* (a, b) pairs summed = scalar dot products per assembly */
-	std::vector<int>     jt_ptr;                         /* [npad+1] */
-	std::vector<uint32_t> jt_terms;                      /* e<<8 | a */
+	/* J' v gather (k_prepare), one thread per variable: the (element, column) terms of 32 neighbouring variables are
+	 * interleaved (term s of lane l at jg_ptr[g] + 32 s + l, zero = none) so a warp reads its descriptors coalesced and
+	 * keeps several columns in flight: lo = value offset of the column | rows << 20, hi = first constraint row */
+	std::vector<int>     jg_ptr;                         /* [ceil(npad/32)+1], multiples of 32 */
+	std::vector<uint2_t> jg;
 	/* 1 kHz sampler */
 	std::vector<double>  csv_t;                          /* [csv_rows] accumulated sample times */
 	std::vector<uint8_t> csv_id;                         /* [csv_rows][10] */
