@@ -592,25 +592,44 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 			}
 		}
 		diag_done_wait();                              /* last diagonal block */
-		/* ---- backward substitution: L' x = z ---- */
+		/* ---- backward substitution: L' x = z.  The factor left L2 long ago (888 resident problems x 0.5 MB), so row I-1
+		 *      (inv(L_II) and its off-diagonal blocks, fragment-major, <= max_w blocks = one panel buffer) is copied
+		 *      asynchronously into the idle panel buffers while row I is solved ---- */
+		auto row_fetch = [&](int I) {
+			double *dst = rp0 + (I & 1) * 16 * rp_ld;
+			const int nch = (I - T.fb[I] + 1) * 128;                 /* 16-byte chunks: block 0 = inv(L_II), then the row */
+			const double2 *srow = reinterpret_cast<const double2 *>(M + (size_t)T.blkptr[I] * 256) - 128;
+			const double2 *sinv = reinterpret_cast<const double2 *>(Dinv + (size_t)I * 256);
+			for (int q = tid; q < nch; q += 128) {
+				const unsigned d = (unsigned)__cvta_generic_to_shared(reinterpret_cast<double2 *>(dst) + q);
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(q < 128 ? sinv + q : srow + q) : "memory");
+			}
+		};
+		tile_sync();                                   /* every warp is done with both panel buffers */
+		row_fetch(T.nb - 1);
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		tile_sync();
 		for (int I = T.nb - 1; I >= 0; --I) {
 			const int fI = T.fb[I];
-			const double *rowg = M + (size_t)T.blkptr[I] * 256;
+			const double *buf = rp0 + (I & 1) * 16 * rp_ld;
+			if (I > 0) row_fetch(I - 1);               /* its buffer was last read two rows ago */
+			asm volatile("cp.async.commit_group;" ::: "memory");
 			if (tid < 16) {
 				double v = 0.0;
-				const double *iv = Dinv + (size_t)I * 256;
-				for (int q = tid; q < 16; ++q) v += iv[frag_off(q, tid)] * zs[I * 16 + q];
+				for (int q = tid; q < 16; ++q) v += buf[frag_off(q, tid)] * zs[I * 16 + q];
 				part[tid] = v;
 			}
 			tile_sync();
 			if (tid < 16) zs[I * 16 + tid] = part[tid];
 			for (int c = tid; c < (I - fI) * 16; c += 128) {
-				const double *blk = rowg + (size_t)(c >> 4) * 256 + frag_off(0, c & 15);
+				const double *blk = buf + 256 + (c >> 4) * 256 + frag_off(0, c & 15);
 				double acc = 0.0;
 #pragma unroll
 				for (int q = 0; q < 16; ++q) acc += blk[((q >> 3) << 7) + ((q & 7) << 3)] * part[q];
 				zs[fI * 16 + c] -= acc;
 			}
+			asm volatile("cp.async.wait_group 0;" ::: "memory");
 			tile_sync();
 		}
 		for (int i = tid; i < T.npad; i += 128) W.vec[(size_t)pid * T.npad + i] = zs[i];
