@@ -34,9 +34,9 @@ WORKLOAD = ("batched multi-start: %d start/goal pairs per GPU on a 256x256 rough
 # (n_free = 605, RCM envelope 50 728 entries): sum_i w_i^2 = 6.3e6 FP64 flop
 ALG_FLOP_PER_FACTORIZATION = 6.3e6
 # DRAM traffic of k_factor per factorization, from the ncu --set full capture of one launch with all 4096 problems
-# active (profiles/r01d_summary.md: dram__bytes_read.sum + dram__bytes_write.sum over 4096 factorizations); the
+# active (profiles/r01e_summary.md: dram__bytes_read.sum + dram__bytes_write.sum over 4096 factorizations); the
 # algorithmic bytes are the assembled matrix read once and the factor written once: 2 x 59 648 doubles = 0.954 MB
-NCU_DRAM_BYTES_PER_FACTORIZATION = 1.337e6
+NCU_DRAM_BYTES_PER_FACTORIZATION = 1.345e6
 ALG_BYTES_PER_FACTORIZATION = 2 * 59648 * 8
 
 
