@@ -28,13 +28,34 @@ def make_records(results, global_idx, groups):
     return rec
 
 
-def argmin_per_group(rec):
-    """rec [n, 5] (any order) -> {group: winning global id}; deterministic lexicographic key."""
+def argmin_per_group_sorted(rec):
+    """reference implementation: one lexicographic sort of all records (O(n log n), ~20 ms for 32768 records)."""
     order = np.lexsort((rec[:, 4], rec[:, 3], rec[:, 2], rec[:, 1], rec[:, 0]))
     srt = rec[order]
     first = np.ones(len(srt), dtype=bool)
     first[1:] = srt[1:, 0] != srt[:-1, 0]
     return {int(g): int(i) for g, i in zip(srt[first, 0], srt[first, 4])}
+
+
+def argmin_per_group(rec):
+    """rec [n, 5] (any order) -> {group: winning global id}; deterministic lexicographic key
+    (not converged, cost, violation, global id).  Segmented minimum, one key after the other over the still-tied
+    candidates: a radix sort of the integer group ids plus O(n) passes (the selection sits inside the timed step at
+    every GPU count, and the gathered record count grows with the number of ranks)."""
+    if len(rec) == 0:
+        return {}
+    order = np.argsort(rec[:, 0].astype(np.int64), kind="stable")
+    srt = rec[order]
+    grp = srt[:, 0]
+    starts = np.flatnonzero(np.concatenate(([True], grp[1:] != grp[:-1])))
+    counts = np.diff(np.concatenate((starts, [len(srt)])))
+    tied = np.ones(len(srt), dtype=bool)
+    best = None
+    for col in (1, 2, 3, 4):
+        key = np.where(tied, srt[:, col], np.inf)
+        best = np.minimum.reduceat(key, starts)
+        tied &= key == np.repeat(best, counts)
+    return dict(zip(grp[starts].astype(np.int64).tolist(), best.astype(np.int64).tolist()))
 
 
 def select_best(rec_local, device=None):

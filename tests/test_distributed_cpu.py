@@ -54,3 +54,19 @@ def test_shards_partition_the_batch():
         assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(4096 * world))
         for p in parts:                                      # every group of 8 candidates is split evenly
             assert np.all(np.bincount(p // 8) == 8 // world if world <= 8 else True)
+
+
+def test_segmented_selection_equals_the_sorted_reference():
+    """argmin_per_group (radix sort of group ids + segmented minima) against the one-sort reference, with heavy ties on
+    every key, ragged groups, singleton groups and one group holding everything."""
+    rng = np.random.default_rng(7)
+    for n, gs in ((4096, 8), (1000, 7), (64, 1), (500, 500), (1, 1)):
+        rec = np.empty((n, 5))
+        rec[:, 0] = np.arange(n) // gs
+        rec[:, 1] = rng.random(n) < 0.3
+        rec[:, 2] = np.round(rng.random(n) * 3)
+        rec[:, 3] = np.round(rng.random(n) * 2) * 1e-5
+        rec[:, 4] = np.arange(n)
+        rec = rec[rng.permutation(n)]
+        assert parallel.argmin_per_group(rec) == parallel.argmin_per_group_sorted(rec)
+    assert parallel.argmin_per_group(np.empty((0, 5))) == {}
