@@ -58,9 +58,25 @@ def argmin_per_group(rec):
     return dict(zip(grp[starts].astype(np.int64).tolist(), best.astype(np.int64).tolist()))
 
 
+def argmin_per_group_torch(rec):
+    """the same selection on a torch tensor [n, 5] (device-resident after the all-gather): dense group index by
+    torch.unique, then one segmented minimum (scatter_reduce amin) per key over the still-tied candidates.
+    Returns (groups int64 [G], winning global ids int64 [G]) on the tensor's device."""
+    grp, inv = torch.unique(rec[:, 0].to(torch.int64), return_inverse=True)
+    tied = torch.ones(rec.shape[0], dtype=torch.bool, device=rec.device)
+    inf = torch.tensor(float("inf"), dtype=rec.dtype, device=rec.device)
+    best = None
+    for col in (1, 2, 3, 4):
+        key = torch.where(tied, rec[:, col], inf)
+        best = torch.full((grp.shape[0],), float("inf"), dtype=rec.dtype, device=rec.device).scatter_reduce(0, inv, key, "amin")
+        tied &= key == best[inv]
+    return grp, best.to(torch.int64)
+
+
 def select_best(rec_local, device=None):
     """all-gather the records of every rank (equal counts per rank) and pick the winner of each group
-    on every rank identically.  Returns (winners dict, gathered records)."""
+    on every rank identically.  Returns (winners dict, gathered records or None).  With a process group the
+    selection runs on the gathered tensor where it lands (on the GPU under NCCL): only the winners come back."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return argmin_per_group(rec_local), rec_local
     world = dist.get_world_size()
@@ -69,5 +85,6 @@ def select_best(rec_local, device=None):
         t = t.to(device)
     out = torch.empty((world * t.shape[0], t.shape[1]), dtype=t.dtype, device=t.device)
     dist.all_gather_into_tensor(out, t)
-    allrec = out.cpu().numpy()
-    return argmin_per_group(allrec), allrec
+    grp, win = argmin_per_group_torch(out)
+    gw = torch.stack((grp, win)).cpu().numpy()
+    return dict(zip(gw[0].tolist(), gw[1].tolist())), out

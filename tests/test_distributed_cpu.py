@@ -70,3 +70,18 @@ def test_segmented_selection_equals_the_sorted_reference():
         rec = rec[rng.permutation(n)]
         assert parallel.argmin_per_group(rec) == parallel.argmin_per_group_sorted(rec)
     assert parallel.argmin_per_group(np.empty((0, 5))) == {}
+
+
+def test_torch_selection_equals_numpy():
+    """the tensor version used on the gathered records (GPU under NCCL, CPU under gloo)."""
+    rng = np.random.default_rng(11)
+    for n, gs in ((4096, 8), (999, 13), (32, 1)):
+        rec = np.empty((n, 5))
+        rec[:, 0] = 5 + 3 * (np.arange(n) // gs)            # sparse group ids
+        rec[:, 1] = rng.random(n) < 0.3
+        rec[:, 2] = np.round(rng.random(n) * 3)
+        rec[:, 3] = np.round(rng.random(n) * 2) * 1e-5
+        rec[:, 4] = np.arange(n)
+        rec = rec[rng.permutation(n)]
+        grp, win = parallel.argmin_per_group_torch(torch.from_numpy(rec))
+        assert dict(zip(grp.tolist(), win.tolist())) == parallel.argmin_per_group(rec)
