@@ -533,6 +533,13 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 			if (I > 0 && fI == I) diag_done_wait();    /* no off-diagonal block: keep the hand-off in step */
 			for (int J = fI; J <= I; ++J) {
 				const int K0 = max(fI, T.fb[J]), nK = J - K0;
+				/* inv(L[J,J]) for the second product, requested before the sweep of the block so its latency hides under
+				 * it (J = I-1 has to wait for the diagonal warp first) */
+				double2 i01 = make_double2(0.0, 0.0), i23 = i01;
+				if (J < I - 1) {
+					const double2 *bi = reinterpret_cast<const double2 *>(Dinv + (size_t)J * 256 + tn * 128) + lane;
+					i01 = bi[0]; i23 = bi[32];
+				}
 				tile_sync();
 				/* four independent accumulator chains (one per k-step of a block) instead of one chain of 4 nK MMAs;
 				 * DMMA step kk of lane (fr, fc) contracts k = 4 fc + kk, so both operands are 128-bit loads */
@@ -566,9 +573,11 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 				else *reinterpret_cast<double2 *>(dS + (tm * 8 + fr) * TLD + tn * 8 + 2 * fc) = sij;   /* plain layout for the diagonal warp */
 				if (J < I) {
 					/* L[I,J] = S * inv(L[J,J])' : second DMMA product, B = inv(L[J,J]) in fragment order from global */
-					if (J == I - 1) diag_done_wait();  /* inv(L[I-1,I-1]) and z_{I-1} are needed from here on, not earlier */
-					const double2 *bi = reinterpret_cast<const double2 *>(Dinv + (size_t)J * 256 + tn * 128) + lane;
-					const double2 i01 = bi[0], i23 = bi[32];
+					if (J == I - 1) {                  /* inv(L[I-1,I-1]) and z_{I-1} are needed from here on, not earlier */
+						diag_done_wait();
+						const double2 *bi = reinterpret_cast<const double2 *>(Dinv + (size_t)J * 256 + tn * 128) + lane;
+						i01 = bi[0]; i23 = bi[32];
+					}
 					tile_sync();
 					const double2 *ta = reinterpret_cast<const double2 *>(tmp + (tm * 8 + fr) * TLT + 4 * fc);
 					const double2 t01 = ta[odd], t23 = ta[odd ^ 1];
