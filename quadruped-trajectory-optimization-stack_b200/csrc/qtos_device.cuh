@@ -224,6 +224,16 @@ __device__ __forceinline__ void dyn_state(const DevTables &T, const DynSample &D
 		S.Iw[3 * i + j] = RI[3 * i] * S.E.R[3 * j] + RI[3 * i + 1] * S.E.R[3 * j + 1] + RI[3 * i + 2] * S.E.R[3 * j + 2];
 }
 
+/* column descriptor through the read-only path: the loop that consumes it also stores Jacobian values, and a plain
+ * load could alias those stores as far as the compiler knows -- every iteration would wait for its own descriptor */
+__device__ __forceinline__ JCol ldg_jcol(const JCol *p)
+{
+	static_assert(sizeof(JCol) == 32, "JCol is two 16-byte words");
+	union { int4 q[2]; JCol c; } u;
+	u.q[0] = __ldg(reinterpret_cast<const int4 *>(p)); u.q[1] = __ldg(reinterpret_cast<const int4 *>(p) + 1);
+	return u.c;
+}
+
 /* 6 rows [AX AY AZ LX LY LZ] (ref: single_rigid_body_dynamics.cc:76-103) */
 __device__ __forceinline__ void dyn_rows(const DevTables &T, const DynState &S, double *g6)
 {
@@ -299,7 +309,7 @@ __device__ __forceinline__ void dyn_jac(const DevTables &T, const DynSample &D, 
 	const double s0 = sc6[0], s1 = sc6[1], s2 = sc6[2], s3 = sc6[3], s4 = sc6[4], s5 = sc6[5];
 	const JCol *cols = T.jcols + D.col0;
 	for (int sl = 0; sl < ncols; ++sl) {
-		const JCol C = cols[sl];
+		const JCol C = ldg_jcol(cols + sl);
 		const int k = C.dim;
 		double a0, a1, a2, l0 = 0.0, l1 = 0.0, l2 = 0.0;
 		if (C.kind == 1) {
@@ -349,15 +359,16 @@ __device__ __forceinline__ void rom_jac(const DevTables &T, const RomSample &R, 
 		for (int r = 0; r < 3; ++r) Gp[3 * r + k] = col[r];
 	}
 	const JCol *cols = T.jcols + R.col0;
+	const double s0 = sc3[0], s1 = sc3[1], s2 = sc3[2];     /* before the stores below: no reload per column */
 	for (int sl = 0; sl < ncols; ++sl) {          /* column stride 4: 3 rows + zero pad */
-		const JCol C = cols[sl];
+		const JCol C = ldg_jcol(cols + sl);
 		const int k = C.dim;
 		const double w = C.kind == 0 ? -C.w[0] : C.w[0];
 		double v0, v1, v2;
 		if (C.kind == 1) { v0 = Gp[k]; v1 = Gp[3 + k]; v2 = Gp[6 + k]; }
 		else { v0 = S.E.R[3 * k]; v1 = S.E.R[3 * k + 1]; v2 = S.E.R[3 * k + 2]; }
 		double2 *o = reinterpret_cast<double2 *>(blk + 4 * sl);
-		o[0] = make_double2(sc3[0] * v0 * w, sc3[1] * v1 * w); o[1] = make_double2(sc3[2] * v2 * w, 0.0);
+		o[0] = make_double2(s0 * v0 * w, s1 * v1 * w); o[1] = make_double2(s2 * v2 * w, 0.0);
 	}
 }
 
