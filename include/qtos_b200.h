@@ -30,6 +30,7 @@ enum {
 	QTOS_SOLVE_SUCCEEDED = 0,         /* Ipopt Solve_Succeeded */
 	QTOS_MAX_ITER = -1,               /* Ipopt Maximum_Iterations_Exceeded */
 	QTOS_STEP_FAILED = -2,            /* line search could not make progress */
+	QTOS_INVALID_NUMBER = -13,        /* Ipopt Invalid_Number_Detected: NaN/Inf in the constraints (bad inputs) */
 	QTOS_RUNNING = 99
 };
 

@@ -226,20 +226,30 @@ k_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 	const double *Jv = WS(Jv, T.nJ), *r = WS(r, T.m), *s = WS(s, T.m), *zL = WS(zL, T.m), *zU = WS(zU, T.m);
 	const double *dL = WS(dL, T.m), *dU = WS(dU, T.m), *sc = WS(sc, T.m);
 	double *y = WS(y, T.m), *Sig = WS(Sig, T.m), *w = WS(w, T.m), *dy = WS(dy, T.m), *vec = WS(vec, T.npad), *scal = WS(scal, 16);
-	/* v: 0 dual_inf(max) 1 theta_inf(max) 2 compl max 3 compl min 4 sum|y| 5 sum z 6 viol(max) */
-	double v[7] = {0, 0, 0, 1e300, 0, 0, 0};
+	/* v: 0 dual_inf(max) 1 theta_inf(max) 2 compl max 3 compl min 4 sum|y| 5 sum z 6 viol(max) 7 sum 0*r (NaN/Inf probe:
+	 * fmax/fmin drop NaN operands, so a non-finite constraint value would otherwise pass for feasible) */
+	double v[8] = {0, 0, 0, 1e300, 0, 0, 0, 0};
 	for (int i = threadIdx.x; i < T.npad; i += blockDim.x) v[0] = fmax(v[0], fabs(jt_gather(T, Jv, y, i)));   /* padding variables have no terms */
 	for (int i = threadIdx.x; i < T.m; i += blockDim.x) {
 		const int fl = T.row_flags[i];
 		v[4] += fabs(y[i]);
+		v[7] += 0.0 * r[i];
 		if (fl & ROW_EQ) { v[1] = fmax(v[1], fabs(r[i])); v[6] = fmax(v[6], fabs(r[i]) / sc[i]); continue; }
 		v[1] = fmax(v[1], fabs(r[i] - s[i]));
 		v[0] = fmax(v[0], fabs(-y[i] - zL[i] + zU[i]));
 		if (fl & ROW_HASL) { const double c = zL[i] * (s[i] - dL[i]); v[2] = fmax(v[2], c); v[3] = fmin(v[3], c); v[5] += zL[i]; v[6] = fmax(v[6], T.gl[i] - r[i] / sc[i]); }
 		if (fl & ROW_HASU) { const double c = zU[i] * (dU[i] - s[i]); v[2] = fmax(v[2], c); v[3] = fmin(v[3], c); v[5] += zU[i]; v[6] = fmax(v[6], r[i] / sc[i] - T.gu[i]); }
 	}
-	const int ops[7] = {1, 1, 1, 2, 0, 0, 1};
-	block_reduce<7>(v, ops, red);
+	const int ops[8] = {1, 1, 1, 2, 0, 0, 1, 0};
+	block_reduce<8>(v, ops, red);
+	if (!(v[7] == 0.0) || !(v[4] == v[4])) {            /* non-finite constraints or multipliers: stop this window */
+		if (threadIdx.x == 0) {
+			const double qnan = v[7] - v[7] + (v[4] - v[4]);       /* NaN without a literal */
+			scal[SC_DUAL] = scal[SC_THETA] = scal[SC_COMPL] = scal[SC_VIOL] = scal[SC_E0] = qnan;
+			W.iters[pid] = it; W.status[pid] = QTOS_INVALID_NUMBER; atomicSub(W.n_running, 1);
+		}
+		return;
+	}
 	const double dual_inf = v[0], theta_inf = v[1], cmax = v[2], cmin = T.n_bounds > 0 ? v[3] : 0.0;
 	const double s_d = fmax(100.0, (v[4] + v[5]) / (double)(T.m + T.n_bounds)) / 100.0;
 	const double s_c = fmax(100.0, v[5] / (double)(T.n_bounds > 0 ? T.n_bounds : 1)) / 100.0;

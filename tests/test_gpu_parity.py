@@ -283,3 +283,18 @@ def test_chunking_and_argument_errors(solvers):
     with pytest.raises(Q.QtosError):
         S8.solve(p8[:0])
     S8.close()
+
+
+def test_bad_window_does_not_poison_the_batch(solvers):
+    """independent windows stay independent: a NaN start and an absurd goal end with a non-zero status inside the
+    iteration cap while every other window of the batch returns exactly what it returns alone."""
+    S = solvers["S2"]
+    p, grid, res = _rough(S, 16)
+    r0, x0, _ = S.solve(p)
+    q = p.copy()
+    q["start_pos"][3, 0] = np.nan
+    q["goal"][7] = (1e6, -1e6, 0.24)
+    r, x, _ = S.solve(q)
+    assert r["status"][3] != 0 and r["status"][7] != 0 and r["iters"].max() <= 200
+    keep = np.ones(16, bool); keep[[3, 7]] = False
+    assert np.array_equal(x[keep], x0[keep]) and np.array_equal(r["status"][keep], r0["status"][keep])

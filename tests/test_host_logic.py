@@ -132,3 +132,22 @@ def test_csv_free_handoff_equals_the_text_detour(tmp_path):
     assert st["CoM"] == [float(v) for v in r7[1:4]] and st["HR_FOOT"] == [float(v) for v in r7[16:19]]
     assert st["CoM_vel_ang"] == [float(v) for v in r7[22:25]] and sorted(st) == sorted(
         ["CoM", "orientation", "FL_FOOT", "FR_FOOT", "HL_FOOT", "HR_FOOT", "CoM_vel", "CoM_vel_ang"])
+
+
+def test_heightfield_file_edge_cases(tmp_path):
+    """parser of towr_heightfield.txt (ref: custom_terrain.cpp:22-49): trailing commas and blank tail lines are fine,
+    ragged or empty files fail loudly instead of the reference's undefined behaviour."""
+    good = tmp_path / "ok.txt"; good.write_text("0.0, 0.5, 1.0,\n0.25, 0.0, 0.0,\n\n")
+    g = HF.read_towr_heightfield(str(good))
+    assert g.shape == (2, 3) and g[0, 1] == 0.5 and g[1, 0] == 0.25
+    ragged = tmp_path / "ragged.txt"; ragged.write_text("0, 1, 2,\n0, 1,\n")
+    with pytest.raises(ValueError, match="ragged"):
+        HF.read_towr_heightfield(str(ragged))
+    empty = tmp_path / "empty.txt"; empty.write_text("\n\n")
+    with pytest.raises(ValueError, match="empty"):
+        HF.read_towr_heightfield(str(empty))
+    # write -> read round trip of the reference's file format, incl. the missing final newline
+    m = np.round(np.random.default_rng(3).uniform(0, 0.2, (7, 5)), 4)
+    HF.write_heightfield(str(tmp_path / "rt.txt"), m)
+    assert not open(tmp_path / "rt.txt").read().endswith("\n")
+    assert np.array_equal(HF.read_towr_heightfield(str(tmp_path / "rt.txt")), m)
