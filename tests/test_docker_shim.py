@@ -63,6 +63,9 @@ def test_ps_cp_rm_verbs(tmp_path, golden_hf):
 
 @pytest.mark.gpu
 def test_exec_main_through_the_shim(tmp_path, golden_hf):
+    pkg = os.path.join(ROOT, "quadruped-trajectory-optimization-stack_b200")
+    if not os.path.exists(os.path.join(pkg, "main")):          # normally built by __graft_entry__.build(); host C++ only
+        subprocess.check_call(["make", "-s", "-C", os.path.join(pkg, "csrc"), "qtos_main"])
     env = _env(tmp_path)
     cid = _docker_info(env)
     s = {k: v.replace("<id>", cid) for k, v in SCRIPTS.items()}
