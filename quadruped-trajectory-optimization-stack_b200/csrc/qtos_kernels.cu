@@ -454,14 +454,16 @@ __device__ __forceinline__ void diag_done_wait() { asm volatile("bar.sync 3, 160
  * Row I+1 needs inv(L[I,I]) and z_I only for its LAST off-diagonal block, so the serial 16x16 factorization -- a third
  * of the kernel's critical path when it sat between barriers of all warps -- runs under the sweep of the next row.
  * Then the backward substitution over the finished factor -> dx (tile warps). */
+template <int nbuf>
 __global__ void __launch_bounds__(FTT, FACTOR_MINB)
 k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 {
 	const int pid = blockIdx.x;
 	if (W.status[pid] != QTOS_RUNNING) return;
 	extern __shared__ __align__(16) double sm[];
-	double *rp0 = sm;                              /* [2][16][rp_ld]  block rows I (being swept) and I+1 (arriving), row-major panels */
-	double *zs = rp0 + 2 * 16 * rp_ld;             /* [npad] rhs -> z -> dx */
+	double *rp0 = sm;                              /* [nbuf][16][rp_ld]  block rows I (being swept) and I+1 (arriving), row-major panels;
+	                                                  nbuf = 1 where two buffers would cost resident CTAs (wide shapes): no prefetch then */
+	double *zs = rp0 + nbuf * 16 * rp_ld;          /* [npad] rhs -> z -> dx */
 	double *tmp = zs + T.npad;                     /* [16][TLT] S of an off-diagonal block (tile warps) */
 	double *dS = tmp + 16 * TLT;                   /* [16][TLD] S of the diagonal block -> inv(L_II) (hand-off buffer) */
 	double *part = dS + 16 * TLD;                  /* [16] rhs of the diagonal solves */
@@ -527,19 +529,27 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 		const int tm = warp >> 1, tn = warp & 1;       /* 8x8 tile of the 16x16 block owned by this warp */
 		const int fr = lane >> 2, fc = lane & 3;       /* fragment row / column */
 		const int odd = fr & 1;
-		panel_fetch(rp0, rp_ld, M, (T.blkptr[1] - T.blkptr[0]) * 8, warp, lane);
-		asm volatile("cp.async.commit_group;" ::: "memory");
+		if (nbuf == 2) {
+			panel_fetch(rp0, rp_ld, M, (T.blkptr[1] - T.blkptr[0]) * 8, warp, lane);
+			asm volatile("cp.async.commit_group;" ::: "memory");
+		}
 		for (int I = 0; I < T.nb; ++I) {
 			const int fI = T.fb[I], wI = I - fI + 1;
 			const int rowbase = T.blkptr[I] * 256;
 			double pacc = 0.0;                         /* this lane's share of L[I,<I] z (forward substitution) */
-			double *rp = rp0 + (I & 1) * 16 * rp_ld;
+			double *rp = rp0 + (nbuf == 2 ? (I & 1) * 16 * rp_ld : 0);
 			tile_sync();                               /* row I-1 has left the other panel buffer */
-			/* next row's assembled panel (k_asm) starts its way from HBM now and lands under this row's sweep:
-			 * asynchronous 16-byte copies, no register staging; this row's copies were issued one row ago */
-			if (I + 1 < T.nb) panel_fetch(rp0 + ((I + 1) & 1) * 16 * rp_ld, rp_ld, M + (size_t)T.blkptr[I + 1] * 256, (T.blkptr[I + 2] - T.blkptr[I + 1]) * 8, warp, lane);
-			asm volatile("cp.async.commit_group;" ::: "memory");
-			asm volatile("cp.async.wait_group 1;" ::: "memory");
+			if (nbuf == 2) {
+				/* next row's assembled panel (k_asm) starts its way from HBM now and lands under this row's sweep:
+				 * asynchronous 16-byte copies, no register staging; this row's copies were issued one row ago */
+				if (I + 1 < T.nb) panel_fetch(rp0 + ((I + 1) & 1) * 16 * rp_ld, rp_ld, M + (size_t)T.blkptr[I + 1] * 256, (T.blkptr[I + 2] - T.blkptr[I + 1]) * 8, warp, lane);
+				asm volatile("cp.async.commit_group;" ::: "memory");
+				asm volatile("cp.async.wait_group 1;" ::: "memory");
+			} else {
+				panel_fetch(rp0, rp_ld, M + (size_t)T.blkptr[I] * 256, wI * 8, warp, lane);
+				asm volatile("cp.async.commit_group;" ::: "memory");
+				asm volatile("cp.async.wait_group 0;" ::: "memory");
+			}
 			if (I > 0 && fI == I) diag_done_wait();    /* no off-diagonal block: keep the hand-off in step */
 			for (int J = fI; J <= I; ++J) {
 				const int K0 = max(fI, T.fb[J]), nK = J - K0;
@@ -615,7 +625,7 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 		 *      (inv(L_II) and its off-diagonal blocks, fragment-major, <= max_w blocks = one panel buffer) is copied
 		 *      asynchronously into the idle panel buffers while row I is solved ---- */
 		auto row_fetch = [&](int I) {
-			double *dst = rp0 + (I & 1) * 16 * rp_ld;
+			double *dst = rp0 + (nbuf == 2 ? (I & 1) * 16 * rp_ld : 0);
 			const int nch = (I - T.fb[I] + 1) * 128;                 /* 16-byte chunks: block 0 = inv(L_II), then the row */
 			const double2 *srow = reinterpret_cast<const double2 *>(M + (size_t)T.blkptr[I] * 256) - 128;
 			const double2 *sinv = reinterpret_cast<const double2 *>(Dinv + (size_t)I * 256);
@@ -631,9 +641,11 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 		tile_sync();
 		for (int I = T.nb - 1; I >= 0; --I) {
 			const int fI = T.fb[I];
-			const double *buf = rp0 + (I & 1) * 16 * rp_ld;
-			if (I > 0) row_fetch(I - 1);               /* its buffer was last read two rows ago */
-			asm volatile("cp.async.commit_group;" ::: "memory");
+			const double *buf = rp0 + (nbuf == 2 ? (I & 1) * 16 * rp_ld : 0);
+			if (nbuf == 2) {
+				if (I > 0) row_fetch(I - 1);           /* its buffer was last read two rows ago */
+				asm volatile("cp.async.commit_group;" ::: "memory");
+			}
 			if (tid < 16) {
 				double v = 0.0;
 				for (int q = tid; q < 16; ++q) v += buf[frag_off(q, tid)] * zs[I * 16 + q];
@@ -647,6 +659,11 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 #pragma unroll
 				for (int q = 0; q < 16; ++q) acc += blk[((q >> 3) << 7) + ((q & 7) << 3)] * part[q];
 				zs[fI * 16 + c] -= acc;
+			}
+			if (nbuf == 1 && I > 0) {                  /* one buffer: the next row can only be fetched once this one is done */
+				tile_sync();
+				row_fetch(I - 1);
+				asm volatile("cp.async.commit_group;" ::: "memory");
 			}
 			asm volatile("cp.async.wait_group 0;" ::: "memory");
 			tile_sync();
