@@ -298,3 +298,16 @@ def test_bad_window_does_not_poison_the_batch(solvers):
     assert r["status"][3] != 0 and r["status"][7] != 0 and r["iters"].max() <= 200
     keep = np.ones(16, bool); keep[[3, 7]] = False
     assert np.array_equal(x[keep], x0[keep]) and np.array_equal(r["status"][keep], r0["status"][keep])
+
+
+def test_contexts_of_different_shapes_coexist():
+    """the dynamic shared-memory cap is per kernel function, not per context: a narrow shape created after a wide one
+    (and the other way round) must still launch."""
+    for order in (("S5", "S2"), ("S2", "S5")):
+        ctxs = [Q.Solver(Q.default_shape(*SHAPES[k]), max_batch=2) for k in order]
+        for S in ctxs:
+            p, _, _ = _rough(S, 2)
+            r, _, _ = S.solve(p)
+            assert set(r["status"]) <= {0, -1, -2}
+        for S in ctxs:
+            S.close()
