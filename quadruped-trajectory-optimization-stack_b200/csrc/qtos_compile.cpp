@@ -169,7 +169,9 @@ std::vector<double> sample_times(double T, double dt)
 
 /* ------------------------------------------------------------------ ordering */
 
-std::vector<int> rcm(int n, const std::vector<std::set<int>> &adj)
+/* reverse Cuthill-McKee; start < 0: pseudo-peripheral start node of every component (the classic choice),
+ * start >= 0: that node starts the first component */
+std::vector<int> rcm(int n, const std::vector<std::set<int>> &adj, int start = -1)
 {
 	std::vector<int> order; order.reserve(n);
 	std::vector<char> seen(n, 0);
@@ -185,7 +187,8 @@ std::vector<int> rcm(int n, const std::vector<std::set<int>> &adj)
 	while ((int)order.size() < n) {
 		int s = -1;
 		for (int i = 0; i < n; ++i) if (!seen[i] && (s < 0 || adj[i].size() < adj[s].size())) s = i;
-		for (int rep = 0; rep < 4; ++rep) { int f = bfs_far(s); if (f == s) break; s = f; }
+		if (start >= 0 && order.empty()) s = start;
+		else for (int rep = 0; rep < 4; ++rep) { int f = bfs_far(s); if (f == s) break; s = f; }
 		size_t head = order.size();
 		order.push_back(s); seen[s] = 1;
 		while (head < order.size()) {
@@ -531,11 +534,55 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 	/* ---- ordering of the condensed KKT matrix ---- */
 	std::vector<std::set<int>> adj(n_free);
 	for (auto &c : ecols) for (int a : c) for (int b : c) if (a != b) adj[a].insert(b);
-	std::vector<int> order = rcm(n_free, adj);           /* order[new] = old free index */
-	std::vector<int> pos(n_free);
-	for (int i = 0; i < n_free; ++i) pos[order[i]] = i;
 	const int NB = QTOS_NB;
 	const int npad = ((n_free + NB - 1) / NB) * NB, nb = npad / NB;
+	/* the factorization pays per 16x16 block (barriers, second product) and per block product of the left-looking
+	 * sweep, not per scalar of the envelope: among the RCM orderings from every start node keep the one with the
+	 * cheapest BLOCK skyline (ties: the classic pseudo-peripheral start, then the lowest node) */
+	auto block_cost = [&](const std::vector<int> &ord) {
+		std::vector<int> ps(n_free), fst(npad);
+		for (int i = 0; i < n_free; ++i) ps[ord[i]] = i;
+		for (int i = 0; i < npad; ++i) fst[i] = i;
+		for (auto &c : ecols) {
+			int mn = npad;
+			for (int a : c) mn = std::min(mn, ps[a]);
+			for (int a : c) fst[ps[a]] = std::min(fst[ps[a]], mn);
+		}
+		std::vector<int> fbk(nb);
+		long blocks = 0, macs = 0;
+		for (int I = 0; I < nb; ++I) {
+			int mn = npad;
+			for (int i = I * NB; i < (I + 1) * NB; ++i) mn = std::min(mn, fst[i]);
+			fbk[I] = mn / NB; blocks += I - fbk[I] + 1;
+			for (int J = fbk[I]; J <= I; ++J) macs += J - std::max(fbk[I], fbk[J]);
+		}
+		return macs + 2 * blocks;
+	};
+	std::vector<int> order = rcm(n_free, adj);           /* order[new] = old free index */
+	{
+		long best = block_cost(order);
+		/* neighbours pre-sorted by (degree, index): a Cuthill-McKee sweep from a given start is then a plain BFS, the
+		 * same visiting order rcm() produces.  Every fourth node is tried (the nodes of one spline node share their
+		 * neighbourhood and give the same skyline) */
+		std::vector<std::vector<int>> nbrs(n_free);
+		for (int u = 0; u < n_free; ++u) {
+			nbrs[u].assign(adj[u].begin(), adj[u].end());
+			std::stable_sort(nbrs[u].begin(), nbrs[u].end(), [&](int a, int b) { return adj[a].size() < adj[b].size(); });
+		}
+		std::vector<int> cand; std::vector<char> seen;
+		for (int st = 0; st < n_free; st += 4) {
+			cand.clear(); seen.assign(n_free, 0);
+			cand.push_back(st); seen[st] = 1;
+			for (size_t head = 0; head < cand.size(); ++head)
+				for (int v : nbrs[cand[head]]) if (!seen[v]) { seen[v] = 1; cand.push_back(v); }
+			if ((int)cand.size() != n_free) continue;            /* disconnected pattern: keep the default ordering */
+			std::reverse(cand.begin(), cand.end());
+			const long c = block_cost(cand);
+			if (c < best) { best = c; order = cand; }
+		}
+	}
+	std::vector<int> pos(n_free);
+	for (int i = 0; i < n_free; ++i) pos[order[i]] = i;
 	H->npad = npad; H->nb = nb;
 	H->perm_of_var.assign(n_all, -1); H->var_of_perm.assign(npad, -1);
 	for (int f = 0; f < n_free; ++f) { H->perm_of_var[var_of_free[f]] = (int16_t)pos[f]; H->var_of_perm[pos[f]] = (int16_t)var_of_free[f]; }
