@@ -581,6 +581,33 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 			if (c < best) { best = c; order = cand; }
 		}
 	}
+	/* refinement at block granularity: the nodes of two neighbouring blocks are re-dealt so that those whose leftmost
+	 * connection lies further left come first (only moves ACROSS a block boundary change the block skyline); a re-deal
+	 * is kept when the block cost drops.  Deterministic, a few passes. */
+	{
+		long best = block_cost(order);
+		for (int pass = 0; pass < 8; ++pass) {
+			bool improved = false;
+			for (int I = 0; I + 1 < nb; ++I) {
+				const int lo = I * NB, hi = std::min(n_free, (I + 2) * NB);
+				if (hi - lo <= NB) continue;
+				std::vector<int> ps(n_free);
+				for (int i = 0; i < n_free; ++i) ps[order[i]] = i;
+				std::vector<int> left(n_free, n_free);
+				for (auto &c : ecols) {
+					int mn = n_free;
+					for (int a : c) mn = std::min(mn, ps[a]);
+					for (int a : c) left[a] = std::min(left[a], mn);
+				}
+				std::vector<int> win(order.begin() + lo, order.begin() + hi), cand = order;
+				std::stable_sort(win.begin(), win.end(), [&](int a, int b) { return std::min(left[a], lo) < std::min(left[b], lo); });
+				std::copy(win.begin(), win.end(), cand.begin() + lo);
+				const long c = block_cost(cand);
+				if (c < best) { best = c; order.swap(cand); improved = true; }
+			}
+			if (!improved) break;
+		}
+	}
 	std::vector<int> pos(n_free);
 	for (int i = 0; i < n_free; ++i) pos[order[i]] = i;
 	H->npad = npad; H->nb = nb;
