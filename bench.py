@@ -34,10 +34,10 @@ WORKLOAD = ("batched multi-start: %d start/goal pairs per GPU on a 256x256 rough
 # (n_free = 605, RCM envelope 50 728 entries): sum_i w_i^2 = 6.3e6 FP64 flop
 ALG_FLOP_PER_FACTORIZATION = 6.3e6
 # DRAM traffic of k_factor per factorization, from the ncu --set full capture of one launch with all 4096 problems
-# active (profiles/r01e_summary.md: dram__bytes_read.sum + dram__bytes_write.sum over 4096 factorizations); the
-# algorithmic bytes are the assembled matrix read once and the factor written once: 2 x 59 648 doubles = 0.954 MB
-NCU_DRAM_BYTES_PER_FACTORIZATION = 1.345e6
-ALG_BYTES_PER_FACTORIZATION = 2 * 59648 * 8
+# active (profiles/r01g_factor_summary.md: dram__bytes_read.sum + dram__bytes_write.sum over 4096 factorizations); the
+# algorithmic bytes are the assembled matrix read once and the factor written once: 2 x 214 blocks x 256 doubles
+# = 0.877 MB (taken from the compiled shape at run time)
+NCU_DRAM_BYTES_PER_FACTORIZATION = 1.2465e6
 
 
 def build_workload(n_total, seed=1234):
@@ -289,7 +289,7 @@ def run_gpu(args):
                      "avg_launch_ms": fact_ms / max(1, fact_launches),
                      "traffic": NCU_DRAM_BYTES_PER_FACTORIZATION * fact / max(1, fact_launches),
                      "traffic_unit": "bytes per average launch (ncu dram bytes per factorization x factorizations per launch)",
-                     "algorithmic_bytes": ALG_BYTES_PER_FACTORIZATION * fact / max(1, fact_launches),
+                     "algorithmic_bytes": 2.0 * dims.kkt_blocks * dims.kkt_block * dims.kkt_block * 8 * fact / max(1, fact_launches),
                      "hbm_peak_gbs": peaks.get("hbm_gbs")},
         "cpu_baseline": {"value": cpu_v, "unit": "solves/s", "cores": cpu_cores, "kind": "port",
                          "sample": "128 windows of the same workload, one process per core, oracle/towr_ipm.c",
