@@ -57,6 +57,7 @@ struct DevWork {
 	double *Dinv;                           /* [nb*256] inverses of the diagonal blocks of L */
 	int *status, *iters, *flags;            /* [1] each */
 	int *n_running;                         /* single counter */
+	int *active, *n_active;                 /* [n] problems that go on to assemble / factor / step in this iteration, and their count */
 };
 
 enum { SC_MU = 0, SC_NU, SC_SD, SC_SC, SC_DUAL, SC_THETA, SC_COMPL, SC_VIOL, SC_E0, SC_NFAIL, SC_N };

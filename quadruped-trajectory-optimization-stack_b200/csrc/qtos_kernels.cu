@@ -274,7 +274,7 @@ k_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 		if (Emu <= kappa_eps * mu && mu > mu_min) mu = fmax(mu_min, fmin(0.2 * mu, mu * sqrt(mu)));
 		else break;
 	}
-	if (threadIdx.x == 0) scal[SC_MU] = mu;
+	if (threadIdx.x == 0) { scal[SC_MU] = mu; W.active[atomicAdd(W.n_active, 1)] = pid; }   /* order is irrelevant: the CTAs of k_asm are independent */
 	const double rho = 1.0 / opt.delta_c;
 	for (int i = threadIdx.x; i < T.m; i += blockDim.x) {
 		const int fl = T.row_flags[i];
@@ -338,8 +338,9 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
 __global__ void __launch_bounds__(FT, ASM_MINB)
 k_asm(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 {
-	const int pid = blockIdx.x / T.nb, I = blockIdx.x - pid * T.nb;
-	if (W.status[pid] != QTOS_RUNNING) return;
+	const int slot = blockIdx.x / T.nb, I = blockIdx.x - slot * T.nb;
+	if (slot >= *W.n_active) return;               /* the grid is an upper bound of the active count */
+	const int pid = W.active[slot];
 	extern __shared__ __align__(16) double sm[];
 	double *rp = sm;                               /* [16][rp_ld]  the block row, row-major over the whole panel */
 	double *As = rp + 16 * rp_ld;                  /* [as_max][6] staged D J columns of the block row */
