@@ -678,7 +678,8 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 
 /* three CTAs per SM (<= 85 registers): the evaluation inside the line search is latency-bound, occupancy pays more
  * than the 24 bytes of spill cost (17.8 -> 9.1 ms per bench step) */
-__global__ void __launch_bounds__(QTOS_THREADS, STEP_MINB)
+template <int MINB>
+__global__ void __launch_bounds__(QTOS_THREADS, MINB)
 k_step(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *hfs, int n_hf, qtos_options opt)
 {
 	const int pid = blockIdx.x;
