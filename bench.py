@@ -180,9 +180,13 @@ def run_gpu(args):
         winners, _ = parallel.select_best(rec, device=dev)
         return r, winners
 
+    h_res = torch.empty(n * Q.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    h_x = torch.empty((n, S.n_vars), dtype=torch.float64).pin_memory()
+
     def step_e2e():
         pp = h_p.numpy().view(Q.PROBLEM_DTYPE).reshape(n)
-        r, x, _ = S.solve(pp, opts)                                   # host buffers: H2D problems, D2H results + node values
+        # host buffers through the public API: H2D problems from pinned memory, D2H results + node values into pinned memory
+        r, x, _ = S.solve(pp, opts, out=(h_res.numpy().view(Q.RESULT_DTYPE).reshape(n), h_x.numpy()))
         rec = parallel.make_records(r, idx, p["group"])
         winners, _ = parallel.select_best(rec, device=dev)
         return r, x

@@ -246,13 +246,23 @@ class Solver:
         self._ck(self._L.qtos_eval(self._h, pp, n, _dp(xx), _dp(g), _dp(J)))
         return (g, J) if jac else g
 
-    def solve(self, problems, options=None, csv=False):
-        """Solve a batch of windows.  Returns (results[RESULT_DTYPE], x[n, n_vars], csv or None)."""
+    def solve(self, problems, options=None, csv=False, out=None):
+        """Solve a batch of windows.  Returns (results[RESULT_DTYPE], x[n, n_vars], csv or None).
+        `out` = (results, x) lets the caller supply the host buffers the C ABI writes into -- e.g. page-locked
+        memory, which the device-to-host copies then reach at full PCIe speed (a fresh pageable array is faulted in
+        page by page under the copy)."""
         p, pp = self._probs(problems)
         n = len(p)
         o = options if options is not None else default_options()
-        res = np.zeros(n, dtype=RESULT_DTYPE)
-        x = np.zeros((n, self.n_vars))
+        if out is not None:
+            res, x = out
+            if res.dtype != RESULT_DTYPE or res.shape != (n,) or not res.flags.c_contiguous:
+                raise ValueError("out[0] must be a C-contiguous RESULT_DTYPE array of length %d" % n)
+            if x.dtype != np.float64 or x.shape != (n, self.n_vars) or not x.flags.c_contiguous:
+                raise ValueError("out[1] must be a C-contiguous float64 array of shape (%d, %d)" % (n, self.n_vars))
+        else:
+            res = np.zeros(n, dtype=RESULT_DTYPE)
+            x = np.zeros((n, self.n_vars))
         rows = np.zeros((n, self.csv_rows, CSV_COLS)) if csv else None
         self._ck(self._L.qtos_solve_batch(self._h, pp, n, C.byref(o), res.ctypes.data_as(C.c_void_p), _dp(x), _dp(rows)))
         return res, x, rows

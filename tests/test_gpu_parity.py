@@ -311,3 +311,18 @@ def test_contexts_of_different_shapes_coexist():
             assert set(r["status"]) <= {0, -1, -2}
         for S in ctxs:
             S.close()
+
+
+def test_caller_supplied_output_buffers(solvers):
+    """solve(out=...) writes into the caller's (e.g. page-locked) buffers and returns them; wrong shapes are refused."""
+    import torch
+    S = solvers["S2"]
+    p, _, _ = _rough(S, 8)
+    r0, x0, _ = S.solve(p)
+    h_res = torch.empty(8 * Q.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    h_x = torch.empty((8, S.n_vars), dtype=torch.float64).pin_memory()
+    res, x = h_res.numpy().view(Q.RESULT_DTYPE).reshape(8), h_x.numpy()
+    r1, x1, _ = S.solve(p, out=(res, x))
+    assert r1 is res and x1 is x and np.array_equal(x1, x0) and np.array_equal(r1["iters"], r0["iters"])
+    with pytest.raises(ValueError):
+        S.solve(p, out=(res, x[:4]))
