@@ -619,6 +619,8 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 		for (int i = 0; i < n_free; ++i) xs[order[i]] = (double)i;
 		double degsum = 0.0;
 		for (int u = 0; u < n_free; ++u) degsum += (double)adj[u].size();
+		std::vector<std::vector<double>> snaps;              /* the embedding after 50 (settled), 1 and 3 sweeps */
+		std::vector<double> snap1, snap3;
 		for (int it = 0; it < 50 && degsum > 0.0; ++it) {
 			double wm = 0.0, mx = 0.0;
 			for (int u = 0; u < n_free; ++u) {
@@ -631,13 +633,22 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 			for (int u = 0; u < n_free; ++u) { ys[u] -= wm; mx = std::max(mx, std::fabs(ys[u])); }
 			if (!(mx > 0.0)) break;
 			for (int u = 0; u < n_free; ++u) xs[u] = ys[u] / mx;
+			if (it == 0) snap1 = xs;
+			if (it == 2) snap3 = xs;
 		}
-		for (int dir = 0; dir < 2; ++dir) {
-			std::vector<int> cand(n_free);
-			for (int i = 0; i < n_free; ++i) cand[i] = i;
-			std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return dir ? xs[a] > xs[b] : xs[a] < xs[b]; });
-			const long c = refine(cand);
-			if (c < best) { best = c; order = cand; }
+		snaps.push_back(xs); snaps.push_back(snap1); snaps.push_back(snap3);
+		const long rcm_best = best;
+		for (size_t k = 0; k < snaps.size(); ++k) {
+			if (snaps[k].empty()) continue;
+			if (k > 0 && best == rcm_best) break;              /* the settled embedding lost to RCM (wide shapes): the half-settled ones are not tried */
+			const std::vector<double> &xv = snaps[k];
+			for (int dir = 0; dir < 2; ++dir) {
+				std::vector<int> cand(n_free);
+				for (int i = 0; i < n_free; ++i) cand[i] = i;
+				std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return dir ? xv[a] > xv[b] : xv[a] < xv[b]; });
+				const long c = refine(cand);
+				if (c < best) { best = c; order = cand; }
+			}
 		}
 	}
 	std::vector<int> pos(n_free);
