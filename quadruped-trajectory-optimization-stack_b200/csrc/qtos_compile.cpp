@@ -586,24 +586,27 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 	 * is kept when the block cost drops.  Deterministic, a few passes. */
 	auto refine = [&](std::vector<int> &ord) {
 		long best = block_cost(ord);
+		std::vector<int> ps(n_free), left(n_free);
+		auto leftmost = [&]() {                                  /* leftmost connection of every node under ord */
+			for (int i = 0; i < n_free; ++i) ps[ord[i]] = i;
+			std::fill(left.begin(), left.end(), n_free);
+			for (auto &c : ecols) {
+				int mn = n_free;
+				for (int a : c) mn = std::min(mn, ps[a]);
+				for (int a : c) left[a] = std::min(left[a], mn);
+			}
+		};
+		leftmost();
 		for (int pass = 0; pass < 8; ++pass) {
 			bool improved = false;
 			for (int I = 0; I + 1 < nb; ++I) {
 				const int lo = I * NB, hi = std::min(n_free, (I + 2) * NB);
 				if (hi - lo <= NB) continue;
-				std::vector<int> ps(n_free);
-				for (int i = 0; i < n_free; ++i) ps[ord[i]] = i;
-				std::vector<int> left(n_free, n_free);
-				for (auto &c : ecols) {
-					int mn = n_free;
-					for (int a : c) mn = std::min(mn, ps[a]);
-					for (int a : c) left[a] = std::min(left[a], mn);
-				}
 				std::vector<int> win(ord.begin() + lo, ord.begin() + hi), cand = ord;
 				std::stable_sort(win.begin(), win.end(), [&](int a, int b) { return std::min(left[a], lo) < std::min(left[b], lo); });
 				std::copy(win.begin(), win.end(), cand.begin() + lo);
 				const long c = block_cost(cand);
-				if (c < best) { best = c; ord.swap(cand); improved = true; }
+				if (c < best) { best = c; ord.swap(cand); improved = true; leftmost(); }
 			}
 			if (!improved) break;
 		}
@@ -646,6 +649,7 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 				std::vector<int> cand(n_free);
 				for (int i = 0; i < n_free; ++i) cand[i] = i;
 				std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return dir ? xv[a] > xv[b] : xv[a] < xv[b]; });
+				if (block_cost(cand) * 100 > best * 115) continue;   /* hopeless before refinement (wide shapes): not refined */
 				const long c = refine(cand);
 				if (c < best) { best = c; order = cand; }
 			}

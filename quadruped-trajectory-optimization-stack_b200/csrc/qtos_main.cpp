@@ -9,6 +9,7 @@
  *   output     traj.csv, 37 columns at 1 kHz                             (ref: main.cpp:15,92-131,470)
  */
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -69,6 +70,14 @@ bool read_grid(const std::string &path, std::vector<double> &h, int &nx, int &ny
 
 int main(int argc, char **argv)
 {
+	const bool timing = getenv("QTOS_TIMING") != nullptr;      /* development: phase times on stderr */
+	auto t_prev = std::chrono::steady_clock::now();
+	auto lap = [&](const char *what) {
+		if (!timing) return;
+		auto t = std::chrono::steady_clock::now();
+		std::cerr << "[qtos timing] " << what << " " << std::chrono::duration<double, std::milli>(t - t_prev).count() << " ms" << std::endl;
+		t_prev = t;
+	};
 	qtos_shape shape; qtos_default_shape(&shape);
 	qtos_problem p; memset(&p, 0, sizeof(p));
 	double goal[3] = {0.5, 0.0, 0.24}, start[3] = {0.0, 0.0, 0.24}, runtime = 15.0, res = 0.1, duration = 5.0, t0 = 0.0;
@@ -101,8 +110,10 @@ int main(int argc, char **argv)
 		std::cerr << "Could not open file " << hf_path << std::endl;   /* the reference carries on into UB here */
 		return 2;
 	}
+	lap("flags + heightfield file");
 	qtos_ctx *ctx = nullptr;
 	if (qtos_create(0, &shape, 1, &ctx) != QTOS_OK) { std::cerr << "qtos_create: " << qtos_last_error(nullptr) << std::endl; return 3; }
+	lap("qtos_create (CUDA context, shape compile, workspace)");
 	int rc = qtos_upload_heightfield(ctx, grid.data(), nx, ny, res, &p.hf_id);
 	qtos_dims d; qtos_get_dims(ctx, &d);
 	std::vector<double> x(d.n_vars), rows((size_t)d.csv_rows * QTOS_CSV_COLS);
@@ -111,10 +122,13 @@ int main(int argc, char **argv)
 	(void)runtime;   /* max_cpu_time has no deterministic GPU analogue: the iteration cap (200) bounds the solve */
 	if (rc == QTOS_OK) rc = qtos_solve_batch(ctx, &p, 1, &o, &r, x.data(), rows.data());
 	if (rc != QTOS_OK) { std::cerr << "qtos: " << qtos_last_error(ctx) << std::endl; qtos_destroy(ctx); return 3; }
+	lap("upload + solve + 1 kHz sampling");
 	std::cout << "Number of Iterations....: " << r.iters << std::endl;
 	std::cout << "Constraint violation....: " << r.constr_viol << std::endl;
 	std::cout << "status -> " << r.status << std::endl;
 	qtos_write_csv(rows.data(), d.csv_rows, "traj.csv");
+	lap("traj.csv");
 	qtos_destroy(ctx);
+	lap("qtos_destroy");
 	return r.status;
 }
