@@ -126,6 +126,7 @@ def problem_from_args(a, hf_id=0):
 
 
 _SOLVERS = {}
+_HEIGHTFIELDS = {}
 
 
 def _solver(combo, duration, device=0):
@@ -147,9 +148,15 @@ def towr_main(argv, cwd=".", device=0, quiet=False):
         # the reference prints and then reads an empty grid (UB); the replacement fails loudly
         sys.stderr.write("Could not open file %s\n" % hf_path)
         return 2
-    grid = read_towr_heightfield(hf_path)
     S = _solver(a["combo"], a["duration"], device)
-    hid = S.upload_heightfield(grid, a["resolution"])
+    st = os.stat(hf_path)
+    key = (id(S), os.path.abspath(hf_path), st.st_mtime_ns, st.st_size, float(a["resolution"]))
+    hid = _HEIGHTFIELDS.get(key)
+    if hid is None:                 # a long-lived process (serve.py) re-reads and re-uploads only a CHANGED terrain file
+        if len(_HEIGHTFIELDS) >= 256:
+            raise RuntimeError("more than 256 distinct heightfields uploaded by one process: restart the daemon")
+        grid = read_towr_heightfield(hf_path)
+        hid = _HEIGHTFIELDS[key] = S.upload_heightfield(grid, a["resolution"])
     p = problem_from_args(a, hid)
     res, x, rows = S.solve(p, default_options(), csv=True)
     write_csv(rows[0], os.path.join(cwd, TRAJ_FILE))

@@ -84,3 +84,50 @@ def test_exec_main_through_the_shim(tmp_path, golden_hf):
     args["-t"] = 0.0
     p = subprocess.run(shlex.split(s['run'] + " " + towr_cli.cmd_args(args)), env=env, cwd=host, capture_output=True, text=True)
     assert p.returncode != 0
+
+
+@pytest.mark.gpu
+def test_daemon_behind_the_same_command_line(tmp_path, golden_hf):
+    """`python -m qtos_b200.serve` keeps the CUDA context, the compiled shape and the uploaded terrain; the docker
+    stand-in asks it when its socket answers.  Same traj.csv as the native ./main, a fraction of its latency."""
+    import sys
+    import time
+    from qtos_b200 import serve
+    pkg = os.path.join(ROOT, "quadruped-trajectory-optimization-stack_b200")
+    if not os.path.exists(os.path.join(pkg, "main")):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(pkg, "csrc"), "qtos_main"])
+    env = _env(tmp_path)
+    cid = _docker_info(env)
+    s = {k: v.replace("<id>", cid) for k, v in SCRIPTS.items()}
+    host = _host_tree(tmp_path, golden_hf["exp_1_towr"])
+    subprocess.run(shlex.split(s['heightfield_copy']), env=env, cwd=host, check=True)
+    args = {"-s": [0, 0, 0.24], "-g": [0.5, 0, 0.24], "-e1": [0.21, 0.19, 0.0], "-e2": [0.21, -0.19, 0.0],
+            "-e3": [-0.21, 0.19, 0.0], "-e4": [-0.21, -0.19, 0.0], "-s_ang": [0, 0, 0], "-t": 1.0, "-r": 15.0, "-resolution": 0.1}
+    cmd = shlex.split(s['run'] + " " + towr_cli.cmd_args(args))
+    # native process first (no daemon yet): the reference csv
+    t0 = time.perf_counter(); p = subprocess.run(cmd, env=env, cwd=host, capture_output=True, text=True); t_native = time.perf_counter() - t0
+    assert p.returncode == 0, p.stdout + p.stderr
+    build = tmp_path / "container" / "build"
+    native_csv = open(build / "traj.csv").read()
+    os.remove(build / "traj.csv")
+    sock = str(tmp_path / "container" / "qtos.sock")
+    env_d = dict(env, PYTHONPATH=ROOT + os.pathsep + env.get("PYTHONPATH", ""))
+    d = subprocess.Popen([sys.executable, "-m", "qtos_b200.serve", "--socket", sock], env=env_d, cwd=ROOT, stdout=subprocess.PIPE, text=True)
+    try:
+        assert "ready" in d.stdout.readline()
+        times = []
+        for _ in range(3):
+            t0 = time.perf_counter(); p = subprocess.run(cmd, env=env, cwd=host, capture_output=True, text=True); times.append(time.perf_counter() - t0)
+            assert p.returncode == 0 and "status -> 0" in p.stdout, p.stdout + p.stderr
+        assert open(build / "traj.csv").read() == native_csv            # byte-identical plan file
+        # a blocked probe still reports a non-zero exit code through the daemon
+        HF.write_heightfield(str(host / "data" / "heightfields" / "from_pybullet" / "towr_heightfield.txt"), golden_hf["exp_3_towr"])
+        subprocess.run(shlex.split(s['heightfield_copy']), env=env, cwd=host, check=True)
+        args["-t"] = 0.0
+        p = subprocess.run(shlex.split(s['run'] + " " + towr_cli.cmd_args(args)), env=env, cwd=host, capture_output=True, text=True)
+        assert p.returncode != 0
+        print("native ./main %.3f s; through the daemon %s s" % (t_native, ["%.3f" % t for t in times]))
+        assert min(times[1:]) < 0.5 * t_native
+    finally:
+        serve.request(sock, {"cmd": "shutdown"}, timeout=10.0)
+        d.wait(timeout=30)
