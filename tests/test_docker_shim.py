@@ -131,3 +131,33 @@ def test_daemon_behind_the_same_command_line(tmp_path, golden_hf):
     finally:
         serve.request(sock, {"cmd": "shutdown"}, timeout=10.0)
         d.wait(timeout=30)
+
+
+def test_daemon_protocol_without_a_device(tmp_path):
+    """host side of the resident solver (no GPU needed): the stand-in routes `exec <id> ./main` to the socket when it
+    answers, exit code and stderr come back through it, a bad request does not end the daemon, shutdown removes the socket."""
+    import sys
+    from qtos_b200 import serve
+    env = _env(tmp_path)
+    cid = _docker_info(env)
+    (tmp_path / "container" / "build").mkdir(parents=True)
+    sock = str(tmp_path / "container" / "qtos.sock")
+    assert serve.request(sock, {"cmd": "ping"}) is None              # nobody there: the client says so, no exception
+    env_d = dict(env, PYTHONPATH=ROOT + os.pathsep + env.get("PYTHONPATH", ""))
+    d = subprocess.Popen([sys.executable, "-m", "qtos_b200.serve", "--socket", sock], env=env_d, cwd=ROOT, stdout=subprocess.PIPE, text=True)
+    try:
+        assert "ready" in d.stdout.readline()
+        assert serve.request(sock, {"cmd": "ping"}) == {"rc": 0, "out": "pong"}
+        with pytest.raises(RuntimeError):                            # a second daemon refuses the socket of a live one
+            serve.serve(sock)
+        # no heightfield in the container tree: the clone's loud exit code 2 (main.cpp:364 reads the file; missing -> UB there)
+        p = subprocess.run(shlex.split(SCRIPTS['run'].replace("<id>", cid) + " -t 0.0"), env=env, capture_output=True, text=True)
+        assert p.returncode == 2 and "Could not open file" in p.stderr
+        import socket as _s
+        c = _s.socket(_s.AF_UNIX, _s.SOCK_STREAM); c.connect(sock); c.sendall(b"not json\n")
+        assert b"bad request" in c.recv(4096); c.close()
+        assert serve.request(sock, {"cmd": "ping"})["out"] == "pong"
+    finally:
+        serve.request(sock, {"cmd": "shutdown"}, timeout=10.0)
+        d.wait(timeout=30)
+    assert not os.path.exists(sock)
