@@ -64,37 +64,48 @@ def serve(sock_path=None, device=0, ready=None):
         while True:
             conn, _ = srv.accept()
             with conn:
-                buf = b""
-                while not buf.endswith(b"\n"):
-                    chunk = conn.recv(65536)
-                    if not chunk:
-                        break
-                    buf += chunk
+                conn.settimeout(10.0)                        # a silent or vanished client must not stall the queue
                 try:
-                    req = json.loads(buf.decode())
-                except ValueError:
-                    conn.sendall(b'{"rc": 3, "out": "bad request"}\n')
+                    if _serve_one(conn, towr_cli, device):
+                        return
+                except OSError:
                     continue
-                if req.get("cmd") == "shutdown":
-                    conn.sendall(b'{"rc": 0, "out": "bye"}\n')
-                    return
-                if req.get("cmd") == "ping":
-                    conn.sendall(b'{"rc": 0, "out": "pong"}\n')
-                    continue
-                out, err = io.StringIO(), io.StringIO()
-                try:
-                    with redirect_stdout(out), redirect_stderr(err):
-                        rc = towr_cli.towr_main(list(req.get("argv", [])), cwd=req.get("cwd", "."), device=device)
-                except Exception as e:                       # the daemon outlives a bad request
-                    rc = 3
-                    err.write("qtos: %s\n" % e)
-                conn.sendall((json.dumps({"rc": int(rc), "out": out.getvalue(), "err": err.getvalue()}) + "\n").encode())
     finally:
         srv.close()
         try:
             os.remove(sock_path)
         except OSError:
             pass
+
+
+def _serve_one(conn, towr_cli, device):
+    """one request on an accepted connection; True when it was the shutdown command."""
+    buf = b""
+    while not buf.endswith(b"\n"):
+        chunk = conn.recv(65536)
+        if not chunk:
+            break
+        buf += chunk
+    try:
+        req = json.loads(buf.decode())
+    except ValueError:
+        conn.sendall(b'{"rc": 3, "out": "bad request"}\n')
+        return False
+    if req.get("cmd") == "shutdown":
+        conn.sendall(b'{"rc": 0, "out": "bye"}\n')
+        return True
+    if req.get("cmd") == "ping":
+        conn.sendall(b'{"rc": 0, "out": "pong"}\n')
+        return False
+    out, err = io.StringIO(), io.StringIO()
+    try:
+        with redirect_stdout(out), redirect_stderr(err):
+            rc = towr_cli.towr_main(list(req.get("argv", [])), cwd=req.get("cwd", "."), device=device)
+    except Exception as e:                       # the daemon outlives a bad request
+        rc = 3
+        err.write("qtos: %s\n" % e)
+    conn.sendall((json.dumps({"rc": int(rc), "out": out.getvalue(), "err": err.getvalue()}) + "\n").encode())
+    return False
 
 
 if __name__ == "__main__":
