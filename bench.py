@@ -34,10 +34,10 @@ WORKLOAD = ("batched multi-start: %d start/goal pairs per GPU on a 256x256 rough
 # (n_free = 605, RCM envelope 50 728 entries): sum_i w_i^2 = 6.3e6 FP64 flop
 ALG_FLOP_PER_FACTORIZATION = 6.3e6
 # DRAM traffic of k_factor per factorization, from the ncu --set full capture of one launch with all 4096 problems
-# active (profiles/r01i_factor_summary.md: dram__bytes_read.sum + dram__bytes_write.sum over 4096 factorizations); the
-# algorithmic bytes are the assembled matrix read once and the factor written once: 2 x 206 blocks x 256 doubles
-# = 0.844 MB (taken from the compiled shape at run time)
-NCU_DRAM_BYTES_PER_FACTORIZATION = 1.1932e6
+# active (profiles/r01k_summary.md: dram__bytes_read.sum + dram__bytes_write.sum over 4096 factorizations); the
+# algorithmic bytes are the assembled matrix read once and the factor written once: 2 x 202 blocks x 256 doubles
+# = 0.827 MB (taken from the compiled shape at run time)
+NCU_DRAM_BYTES_PER_FACTORIZATION = 1.1702e6
 
 
 def build_workload(n_total, seed=1234):
