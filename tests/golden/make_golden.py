@@ -59,13 +59,65 @@ np.savez_compressed(os.path.join(HERE, "heightfields.npz"), **out)
 
 gait = np.loadtxt(os.path.join(REF, "test/data/traj/gait.csv"), delimiter=",")
 towr = np.loadtxt(os.path.join(REF, "data/traj/towr.csv"), delimiter=",")
+# towr_g4 = rows t = 2.502 .. 3.755 of the plan the FIRST logged solve wrote (the head of towr.csv before the
+# splice at t = 3.756): with towr_g2 these are the input -> output pairs of the logged solves #1 and #2
 np.savez_compressed(os.path.join(HERE, "gait_csv.npz"), gait=gait[::10], towr_g2=towr[1254:6255][::10],
+                    towr_g4=towr[:1254][::10],
                     gait_rows=np.array(gait.shape[0]), towr_rows=np.array(towr.shape[0]))
+
+import re  # noqa: E402
+
+
+def iteration_tables(path):
+    """the three Ipopt iteration tables (logs/towr_log.out:54-62,191-199,328-337) as printed strings"""
+    tabs, cur = [], None
+    for line in open(path).read().split("\n"):
+        if line.startswith("iter    objective"):
+            cur = []
+            continue
+        if cur is None:
+            continue
+        m = re.match(r"\s*(\d+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+?)([a-zA-Z]?)\s+(\d+)\s*$", line)
+        if m:
+            cur.append({"iter": int(m.group(1)), "inf_pr": m.group(3), "inf_du": m.group(4), "lg_mu": m.group(5),
+                        "dnorm": m.group(6), "lg_rg": m.group(7), "alpha_du": m.group(8), "alpha_pr": m.group(9),
+                        "tag": m.group(10), "ls": int(m.group(11))})
+        elif not line.strip() and cur:
+            tabs.append(cur)
+            cur = None
+    return tabs
+
+
+def logged_inputs(path):
+    """the argument echo in front of each solve (logs/towr_log.out:8-29,140-166,278-304): goal, start, start_ang,
+    four feet; then (solves 2, 3) t_start ... resolution"""
+    lines = open(path).read().split("\n")
+    out = []
+    for i, line in enumerate(lines):
+        if line.startswith("This is Ipopt version"):
+            j = i
+            while not lines[j].startswith("****") or "TOWR" not in lines[j - 3]:
+                j -= 1
+            nums, replan = [], False
+            for t in lines[j + 1:i]:
+                try:
+                    nums.append(float(t))
+                except ValueError:
+                    if nums and len(nums) >= 21:
+                        replan = t.strip() == "s_vel"   # "<t_start> s_vel ..." follows the feet only on replans
+                        break
+            out.append({"goal": nums[0:3], "start_pos": nums[3:6], "start_ang": nums[6:9],
+                        "ee": [nums[9:12], nums[12:15], nums[15:18], nums[18:21]],
+                        "t_start": nums[21] if replan else 0.0})
+    return out
+
 
 log = {"n_vars_free": 1005, "n_vars_total": 1040, "n_fixed": 35, "n_eq": 706, "n_ineq": 1024,
        "nnz_eq": 11557, "nnz_ineq": 20605, "ineq_lower_only": 112, "ineq_both": 816, "ineq_upper_only": 96,
        "inf_pr_iter0": 19.4, "iters": [7, 7, 8],
-       "source": "logs/towr_log.out:40-52,55,64,98-129,192,201,329,339"}
+       "iteration_tables": iteration_tables(os.path.join(REF, "logs/towr_log.out")),
+       "inputs": logged_inputs(os.path.join(REF, "logs/towr_log.out")),
+       "source": "logs/towr_log.out:8-29,40-64,98-129,140-166,191-201,278-304,328-339"}
 json.dump(log, open(os.path.join(HERE, "towr_log.json"), "w"), indent=1)
 
 samples = [
