@@ -5,7 +5,7 @@ plans solves #1 and #2 wrote).  The emulator reproduces the tables to the printe
 CSV's 6-digit rounding -- which also identifies the build that produced them: mass 3.0 kg and
 max_dev_from_nominal = (0.08, 0.08, 0.10) instead of the vendored (0.10, 0.08, 0.10)
 (solver/towr/include/towr/models/examples/solo12_model.h:26,35); with the vendored x-deviation the very first
-step (alpha_pr, inf_du of iteration 1) is off by more than 10 %.
+step is visibly different (alpha_pr of iteration 1 off by 11 %, inf_pr / inf_du print differently).
 """
 import numpy as np
 import pytest
@@ -89,4 +89,5 @@ def test_vendored_constants_do_not_reproduce_the_log(oracle, towr_log):
     o.max_iter = 1
     t = IpoptEmulator(p, o).solve().trace[1]
     g = towr_log["iteration_tables"][0][1]
-    assert abs(t["alpha_pr"] / float(g["alpha_pr"]) - 1.0) > 0.05 and abs(t["inf_du"] / float(g["inf_du"]) - 1.0) > 0.05
+    assert abs(t["alpha_pr"] / float(g["alpha_pr"]) - 1.0) > 0.05
+    assert "%.2e" % t["inf_du"] != g["inf_du"] and "%.2e" % t["inf_pr"] != g["inf_pr"]
