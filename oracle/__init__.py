@@ -57,6 +57,22 @@ class IpmResult(C.Structure):
                 ("tr_ls", C.c_int * 256), ("chol_fix", C.c_int)]
 
 
+class IpoptOptions(C.Structure):
+    _fields_ = [("tol", C.c_double), ("constr_viol_tol", C.c_double), ("compl_inf_tol", C.c_double),
+                ("dual_inf_tol", C.c_double), ("max_iter", C.c_int), ("delta_c", C.c_double),
+                ("n_refine", C.c_int), ("lm_history", C.c_int), ("verbose", C.c_int), ("sigma_floor", C.c_double)]
+
+
+class IpoptResult(C.Structure):
+    _fields_ = [("status", C.c_int), ("iters", C.c_int),
+                ("constr_viol", C.c_double), ("dual_inf", C.c_double), ("compl_inf", C.c_double),
+                ("nlp_error", C.c_double), ("mu", C.c_double), ("n_trace", C.c_int),
+                ("tr_inf_pr", C.c_double * 256), ("tr_inf_du", C.c_double * 256), ("tr_mu", C.c_double * 256),
+                ("tr_dnorm", C.c_double * 256), ("tr_alpha_pr", C.c_double * 256), ("tr_alpha_du", C.c_double * 256),
+                ("tr_ls", C.c_int * 256), ("tr_pairs", C.c_int * 256), ("tr_free", C.c_int * 256),
+                ("tr_tag", C.c_char * 256), ("chol_fix", C.c_int)]
+
+
 def build(force=False):
     """Compile oracle/liboracle.so with the committed Makefile (gcc)."""
     so = os.path.join(_HERE, "liboracle.so")
@@ -91,6 +107,8 @@ def lib():
         L.orc_default_shape.argtypes = [C.POINTER(Shape)]
         L.orc_ipm_default_options.argtypes = [C.POINTER(IpmOptions)]
         L.orc_ipm_solve.argtypes = [C.c_void_p, C.POINTER(IpmOptions), dp, C.POINTER(IpmResult)]
+        L.orc_ipopt_default_options.argtypes = [C.POINTER(IpoptOptions)]
+        L.orc_ipopt_solve.argtypes = [C.c_void_p, C.POINTER(IpoptOptions), dp, C.POINTER(IpoptResult)]
         _LIB = L
     return _LIB
 
@@ -206,6 +224,17 @@ class Problem:
     def write_csv(self, x, path, dt=0.001):
         x = np.ascontiguousarray(x, dtype=np.float64)
         return lib().orc_write_csv(self.h, _dp(x), dt, path.encode())
+
+    def solve_ipopt(self, x0=None, **opts):
+        """the reference's Ipopt 3.11.9 algorithm in the form the CUDA kernels implement (towr_ipopt.c)"""
+        o = IpoptOptions()
+        lib().orc_ipopt_default_options(C.byref(o))
+        for k, v in opts.items():
+            setattr(o, k, v)
+        x = self.x0() if x0 is None else np.array(x0, dtype=np.float64)
+        res = IpoptResult()
+        lib().orc_ipopt_solve(self.h, C.byref(o), _dp(x), C.byref(res))
+        return x, res
 
     def solve(self, x0=None, **opts):
         o = IpmOptions()

@@ -238,6 +238,7 @@ class IpoptEmulator:
                     sigma_w = min(max(sTy / float(s_new @ s_new), o.lm_init_val_min), o.lm_init_val_max)
             last = (x.copy(), Jc, Jd)
             W = sigma_w * np.eye(n)
+            self._sigma_w, self._Bl, self._Mid = sigma_w, None, None
             if S:
                 Sm, Ym = np.array(S).T, np.array(Y).T
                 StY = Sm.T @ Ym
@@ -246,6 +247,7 @@ class IpoptEmulator:
                 Mid = np.block([[sigma_w * Sm.T @ Sm, Lm], [Lm.T, -Dm]])
                 Bl = np.hstack([sigma_w * Sm, Ym])
                 W = W - Bl @ np.linalg.solve(Mid, Bl.T)
+                self._Bl, self._Mid = Bl, Mid
 
             # ---- error measures (IpoptCalculatedQuantities)
             glx = Jc.T @ yc + Jd.T @ yd

@@ -51,15 +51,7 @@ void orc_ipm_default_options(orc_ipm_options *o)
 
 /* ---------------------------------------------------------------- structure */
 
-typedef struct {
-	int n, m;              /* free variables, rows */
-	int *free_of;          /* [n_all] -> free index or -1 */
-	int *var_of;           /* [n] -> full index */
-	int *rowptr, *col;     /* CSR over free columns (structure = reference mask) */
-	int *perm, *iperm;     /* RCM: perm[new] = old free index */
-	int *first;            /* skyline: first column of row i (permuted) */
-	long *skyptr;          /* [n+1] */
-} ipm_struct;
+#include "towr_sparse.h"
 
 static void rcm_order(int n, const unsigned char *adj /* n*n */, int *perm)
 {
@@ -109,7 +101,7 @@ static void rcm_order(int n, const unsigned char *adj /* n*n */, int *perm)
 	free(deg); free(visited); free(queue); free(nb);
 }
 
-static ipm_struct *build_struct(orc_problem *p, const double *x0)
+ipm_struct *orc_build_struct(orc_problem *p, const double *x0)
 {
 	ipm_struct *S = (ipm_struct *)calloc(1, sizeof(ipm_struct));
 	const int na = p->n, m = p->m;
@@ -160,14 +152,14 @@ static ipm_struct *build_struct(orc_problem *p, const double *x0)
 	return S;
 }
 
-static void free_struct(ipm_struct *S)
+void orc_free_struct(ipm_struct *S)
 {
 	free(S->free_of); free(S->var_of); free(S->rowptr); free(S->col);
 	free(S->perm); free(S->iperm); free(S->first); free(S->skyptr); free(S);
 }
 
 /* skyline Cholesky, row oriented: A[i][j], first[i] <= j <= i at sky[skyptr[i] + j - first[i]] */
-static int sky_chol(const ipm_struct *S, double *A)
+int orc_sky_chol(const ipm_struct *S, double *A)
 {
 	const int n = S->n; int bad = 0;
 	for (int i = 0; i < n; ++i) {
@@ -187,7 +179,7 @@ static int sky_chol(const ipm_struct *S, double *A)
 	return bad;
 }
 
-static void sky_solve(const ipm_struct *S, const double *L, double *b)
+void orc_sky_solve(const ipm_struct *S, const double *L, double *b)
 {
 	const int n = S->n;
 	for (int i = 0; i < n; ++i) {
@@ -214,7 +206,7 @@ int orc_ipm_solve(orc_problem *p, const orc_ipm_options *o, double *x, orc_ipm_r
 	const int na = p->n, m = p->m;
 	memset(res, 0, sizeof(*res));
 	for (int i = 0; i < na; ++i) if (p->xl[i] == p->xu[i]) x[i] = p->xl[i];
-	ipm_struct *S = build_struct(p, x);
+	ipm_struct *S = orc_build_struct(p, x);
 	const int n = S->n, nnz = S->rowptr[m];
 	const double *gl = p->gl, *gu = p->gu;
 
@@ -352,8 +344,8 @@ int orc_ipm_solve(orc_problem *p, const orc_ipm_options *o, double *x, orc_ipm_r
 				}
 			}
 		}
-		if (sky_chol(S, M)) res->chol_fix++;
-		sky_solve(S, M, dx);                               /* dx in permuted order */
+		if (orc_sky_chol(S, M)) res->chol_fix++;
+		orc_sky_solve(S, M, dx);                               /* dx in permuted order */
 		/* recover ds, dy, dz */
 		double a_pr = 1.0, a_du = 1.0, theta1 = 0, gphi_d = 0, quad = 0, dxmax = 0;
 		for (int i = 0; i < n; ++i) { quad += sigma * dx[i] * dx[i]; dxmax = dmax(dxmax, fabs(dx[i])); }
@@ -434,6 +426,6 @@ int orc_ipm_solve(orc_problem *p, const orc_ipm_options *o, double *x, orc_ipm_r
 	free(Jd); free(jv); free(sc); free(g); free(gt); free(r); free(rt); free(s); free(st); free(y);
 	free(zL); free(zU); free(dL); free(dU); free(Sig); free(w); free(ds); free(dy); free(dzL); free(dzU);
 	free(iseq); free(hasL); free(hasU); free(rx); free(dx); free(xt); free(M);
-	free_struct(S);
+	orc_free_struct(S);
 	return status;
 }

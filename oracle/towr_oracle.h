@@ -156,6 +156,33 @@ void orc_ipm_default_options(orc_ipm_options *o);
 int  orc_ipm_solve(orc_problem *p, const orc_ipm_options *o, double *x /* n, out */,
                    orc_ipm_result *res);
 
+/* ---- the Ipopt 3.11.9 algorithm of the reference path (towr_ipopt.c; see its header) ---- */
+#define ORC_TRACE_MAX 256
+#define ORC_FILTER_MAX 32
+typedef struct {
+	double tol, constr_viol_tol, compl_inf_tol, dual_inf_tol;   /* 1e-3 (ifopt), 1e-4, 1e-4, 1 */
+	int    max_iter;          /* 200 (main.cpp:461) */
+	double delta_c;           /* penalty 1/delta_c on the equality block of the condensed system */
+	int    n_refine;          /* multiplier-method passes that remove the penalty's bias */
+	int    lm_history;        /* limited_memory_max_history 6 */
+	int    verbose;
+	double sigma_floor;       /* lower bound of the limited-memory scalar sigma_w (0: Ipopt's 1e-8) */
+} orc_ipopt_options;
+
+typedef struct {
+	int status, iters;
+	double constr_viol, dual_inf, compl_inf, nlp_error, mu;
+	int n_trace;
+	double tr_inf_pr[ORC_TRACE_MAX], tr_inf_du[ORC_TRACE_MAX], tr_mu[ORC_TRACE_MAX], tr_dnorm[ORC_TRACE_MAX],
+	       tr_alpha_pr[ORC_TRACE_MAX], tr_alpha_du[ORC_TRACE_MAX];
+	int tr_ls[ORC_TRACE_MAX], tr_pairs[ORC_TRACE_MAX], tr_free[ORC_TRACE_MAX];
+	char tr_tag[ORC_TRACE_MAX];
+	int chol_fix;
+} orc_ipopt_result;
+
+void orc_ipopt_default_options(orc_ipopt_options *o);
+int  orc_ipopt_solve(orc_problem *p, const orc_ipopt_options *o, double *x /* n, in: x0, out */, orc_ipopt_result *res);
+
 #ifdef __cplusplus
 }
 #endif

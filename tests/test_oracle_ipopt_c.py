@@ -1,0 +1,53 @@
+"""CPU tier: oracle/towr_ipopt.c (the Ipopt algorithm in the form the CUDA kernels implement: condensed SPD system,
+penalty + multiplier passes on the equality block, Woodbury for the limited-memory term) against
+ (a) the reference's golden iteration tables and plans, and
+ (b) oracle/ipopt_emul.py (dense, exact KKT solve) on rough-terrain windows of the batched shape."""
+import numpy as np
+import pytest
+
+from test_ipopt_emulation import logged_problem
+
+
+def test_c_port_reproduces_golden_tables_and_plans(oracle, towr_log, golden_csv):
+    its, plans = [], []
+    for k, inp in enumerate(towr_log["inputs"]):
+        p = logged_problem(oracle, inp)
+        x, r = p.solve_ipopt()
+        assert r.status == 0
+        its.append(r.iters)
+        plans.append((p, x))
+        table = towr_log["iteration_tables"][k]
+        assert r.n_trace == len(table)
+        for g in table[:5]:                                   # iterations 0-4 print identically
+            i = g["iter"]
+            got = {"inf_pr": r.tr_inf_pr[i], "inf_du": r.tr_inf_du[i], "dnorm": r.tr_dnorm[i],
+                   "alpha_du": r.tr_alpha_du[i], "alpha_pr": r.tr_alpha_pr[i]}
+            for key, v in got.items():
+                assert abs(v - float(g[key])) <= 6e-3 * abs(float(g[key])), (k, i, key, v, g[key])
+            assert abs(np.log10(r.tr_mu[i]) - float(g["lg_mu"])) <= 0.051
+            assert r.tr_ls[i] == g["ls"] and (i == 0 or r.tr_tag[i:i + 1].decode() == g["tag"])
+    assert its == towr_log["iters"]
+    for (p, x), G, row0 in ((plans[0], golden_csv["towr_g4"], 2502), (plans[1], golden_csv["towr_g2"], 0)):
+        rows = p.csv(x)[row0::10][:len(G)]
+        assert np.abs(rows[:, 1:4] - G[:, 1:4]).max() < 2e-5          # CoM within 0.02 mm of TOWR + Ipopt (north_star: 1 mm)
+        assert np.abs(rows[:, 7:19] - G[:, 7:19]).max() < 2e-5        # feet
+        assert np.abs(rows[:, 4:7] - G[:, 4:7]).max() < 1e-4
+
+
+def test_c_port_matches_dense_emulator_on_rough_terrain(oracle):
+    from oracle.ipopt_emul import IpoptEmulator
+    rng = np.random.default_rng(7)
+    grid = np.kron(np.round(rng.uniform(0, 0.075, (32, 32)), 4), np.ones((8, 8)))
+    ter = oracle.Terrain(grid, 0.02)
+    sh = oracle.default_shape("C1", 2.0)
+    worst = 0.0
+    for k in range(3):
+        sx, sy = rng.uniform(0.3, 2.0, 2)
+        feet = [(sx + a, sy + b, ter.height(sx + a, sy + b)) for a, b in ((0.21, 0.19), (0.21, -0.19), (-0.21, 0.19), (-0.21, -0.19))]
+        inst = oracle.make_instance(start_pos=(sx, sy, ter.height(sx, sy) + 0.24), goal=(sx + 0.4, sy + 0.05, 0.24), ee=feet)
+        p = oracle.Problem(sh, inst, ter)
+        x, r = p.solve_ipopt()
+        e = IpoptEmulator(p).solve()
+        assert r.status == 0 and e.status == 0 and r.iters == e.iters
+        worst = max(worst, np.abs(p.csv(x)[:, 1:19] - p.csv(e.x)[:, 1:19]).max())
+    assert worst < 1e-4, worst            # measured ~1e-6 m
