@@ -29,7 +29,7 @@ enum { QTOS_C0 = 0, QTOS_C1, QTOS_C2, QTOS_C3, QTOS_C4, QTOS_CUSTOM };
 enum {
 	QTOS_SOLVE_SUCCEEDED = 0,         /* Ipopt Solve_Succeeded */
 	QTOS_MAX_ITER = -1,               /* Ipopt Maximum_Iterations_Exceeded */
-	QTOS_STEP_FAILED = -2,            /* line search could not make progress */
+	QTOS_STEP_FAILED = -2,            /* line search could not make progress (Ipopt: Restoration_Failed) */
 	QTOS_INVALID_NUMBER = -13,        /* Ipopt Invalid_Number_Detected: NaN/Inf in the constraints (bad inputs) */
 	QTOS_RUNNING = 99
 };
@@ -76,9 +76,21 @@ typedef struct {
 	double mu_init;                   /* 0.1 */
 	double sigma_w;                   /* Hessian model sigma_w * I */
 	double delta_c;                   /* equality-block regularisation */
-	int    feas_exit;                 /* 1: f == 0 on this path, so any point with violation <= constr_viol_tol is
+	int    feas_exit;                 /* FAST only. 1: f == 0 on this path, so any point with violation <= constr_viol_tol is
 	                                     optimal with zero multipliers and terminates the solve (default) */
+	int    algorithm;                 /* QTOS_ALG_IPOPT (default) or QTOS_ALG_FAST */
+	int    n_refine;                  /* IPOPT: multiplier-method passes on the equality block per direction (2) */
+	int    lm_history;                /* IPOPT: limited_memory_max_history (6, the maximum) */
 } qtos_options;
+
+/* QTOS_ALG_IPOPT: the algorithm the reference runs (Ipopt 3.11.9 as configured by ifopt, ref: solver/towr/src/main.cpp:444-463,
+ *   logs/towr_log.out:37-64): limited-memory BFGS Hessian (history 6), adaptive quality-function barrier update, filter line
+ *   search; reproduces the reference's logged iteration tables and plans (tests/test_gpu_parity.py).  mu_init, sigma_w and
+ *   feas_exit are ignored.
+ * QTOS_ALG_FAST: Hessian model sigma_w I, monotone barrier update, l1-merit line search: a feasible plan, not Ipopt's plan. */
+enum { QTOS_ALG_IPOPT = 0, QTOS_ALG_FAST = 1 };
+#define QTOS_TRACE_ITERS 48       /* iterations kept by qtos_get_trace */
+#define QTOS_TRACE_COLS 8         /* inf_pr, inf_du, mu, ||d||, alpha_du, alpha_pr, line-search trials, step tag ('f' / 'h' as a number) */
 
 typedef struct {
 	int    status;
@@ -134,6 +146,9 @@ int  qtos_solve_batch(qtos_ctx *ctx, const qtos_problem *p, int n, const qtos_op
 /* same with device-resident buffers (problems, results, x) on the context's stream */
 int  qtos_solve_batch_device(qtos_ctx *ctx, const qtos_problem *d_p, int n, const qtos_options *o,
                              qtos_result *d_res, double *d_x_out);
+/* IPOPT algorithm: the per-iteration table Ipopt prints (ref: logs/towr_log.out:55-62), for the first n problems of the
+ * last solve: trace_out = n * QTOS_TRACE_ITERS * QTOS_TRACE_COLS doubles; rows past a problem's last iteration are zero */
+int  qtos_get_trace(qtos_ctx *ctx, int n, double *trace_out);
 /* 1 kHz sampler (ref: main.cpp:92-131): rows_out = n * csv_rows * 37 */
 int  qtos_sample_csv(qtos_ctx *ctx, const qtos_problem *p, int n, const double *x, double *rows_out);
 /* write one trajectory as the reference's traj.csv text ("%g", comma separated) */
@@ -142,7 +157,7 @@ int  qtos_write_csv(const double *rows, int n_rows, const char *path);
 /* instrumentation.  With profiling on, CUDA events are recorded between the kernels of every iteration
  * on the context's stream (no extra synchronisation) and resolved when the solve ends. */
 typedef struct {
-	float ms[8];                      /* device time of the last solve: init, jac, prepare, assemble, factor, step, 0, 0 */
+	float ms[8];                      /* device time of the last solve: init, jac, prepare, assemble, factor, step, solve (IPOPT), 0 */
 	long long factorizations;         /* problems factored, summed over the iterations of the last solve */
 	long long factor_launches;        /* k_factor launches of the last solve */
 	int iterations;                   /* batch iterations of the last solve */

@@ -179,7 +179,7 @@ int orc_sky_chol(const ipm_struct *S, double *A)
 	return bad;
 }
 
-void orc_sky_solve(const ipm_struct *S, const double *L, double *b)
+void orc_sky_fwd(const ipm_struct *S, const double *L, double *b)
 {
 	const int n = S->n;
 	for (int i = 0; i < n; ++i) {
@@ -188,12 +188,23 @@ void orc_sky_solve(const ipm_struct *S, const double *L, double *b)
 		for (int k = fi; k < i; ++k) s -= ri[k - fi] * b[k];
 		b[i] = s / ri[i - fi];
 	}
+}
+
+void orc_sky_bwd(const ipm_struct *S, const double *L, double *b)
+{
+	const int n = S->n;
 	for (int i = n - 1; i >= 0; --i) {
 		const double *ri = L + S->skyptr[i]; const int fi = S->first[i];
 		b[i] /= ri[i - fi];
 		const double bi = b[i];
 		for (int k = fi; k < i; ++k) b[k] -= ri[k - fi] * bi;
 	}
+}
+
+void orc_sky_solve(const ipm_struct *S, const double *L, double *b)
+{
+	orc_sky_fwd(S, L, b);
+	orc_sky_bwd(S, L, b);
 }
 
 /* ---------------------------------------------------------------- the loop */

@@ -17,7 +17,9 @@
  *         M = sigma_w I + Jd' Sigma Jd + rho Jc' Jc          (SPD, skyline Cholesky in RCM order)
  *         dx_{k+1} = Mf^-1 (b1 + Jc' (rho b2 - dy_k)),  dy_{k+1} = dy_k + rho (Jc dx_{k+1} - b2)
  *   - the limited-memory term  W = sigma_w I - Bl Mid^-1 Bl'  (compact BFGS, Bl = [sigma_w S, Y]) enters by the
- *     Woodbury identity: Mf^-1 v = u + Z (Mid - Bl' Z)^-1 Bl' u,  u = M^-1 v,  Z = M^-1 Bl;
+ *     Woodbury identity, written between the two triangular solves of M = L L' (the kernels get Q = L^-1 Bl as
+ *     extra right-hand sides of the factorization's forward substitution, and never need M^-1 Bl):
+ *         Mf^-1 v = L'^-1 (p + Q (Mid - Q'Q)^-1 Q' p),   p = L^-1 v,   Q = L^-1 Bl;
  *   - the affine-scaling and centering directions of the quality-function mu oracle are two right-hand sides
  *     of the same factorization; the search direction is aff + (mu / avg_compl) cen (exact: the KKT
  *     right-hand side is affine in mu).
@@ -77,31 +79,28 @@ typedef struct {
 	const unsigned char *iseq, *hasL, *hasU;
 	double *Lsky;                     /* factor of M */
 	int nlr;                          /* columns of Bl (2 x stored pairs) */
-	double *Bl, *Z;                   /* [nlr][n] */
+	double *Bl, *Z;                   /* [nlr][n]; Z = Q = L^-1 Bl in permuted order */
 	double Clu[4 * LM_MAX * LM_MAX]; int Cpiv[2 * LM_MAX];
 	double rho;
 	int n_refine;
 	double *tmp;                      /* [n] */
 } kkt_t;
 
-/* u = M^-1 v (free order in, free order out) */
-static void m_solve(const kkt_t *K, const double *v, double *u)
-{
-	const ipm_struct *S = K->S;
-	for (int i = 0; i < K->n; ++i) K->tmp[S->iperm[i]] = v[i];
-	orc_sky_solve(S, K->Lsky, K->tmp);
-	for (int i = 0; i < K->n; ++i) u[i] = K->tmp[S->iperm[i]];
-}
-
-/* u = Mf^-1 v with the limited-memory term (Woodbury) */
+/* u = Mf^-1 v with the limited-memory term (Woodbury between the triangular solves); free order in and out */
 static void mf_solve(const kkt_t *K, const double *v, double *u)
 {
-	m_solve(K, v, u);
-	if (!K->nlr) return;
-	double t[2 * LM_MAX];
-	for (int a = 0; a < K->nlr; ++a) { double s = 0; for (int i = 0; i < K->n; ++i) s += K->Bl[(size_t)a * K->n + i] * u[i]; t[a] = s; }
-	lu_solve(K->nlr, K->Clu, K->Cpiv, t);
-	for (int a = 0; a < K->nlr; ++a) for (int i = 0; i < K->n; ++i) u[i] += K->Z[(size_t)a * K->n + i] * t[a];
+	const ipm_struct *S = K->S;
+	const int n = K->n;
+	for (int i = 0; i < n; ++i) K->tmp[S->iperm[i]] = v[i];
+	orc_sky_fwd(S, K->Lsky, K->tmp);                              /* p = L^-1 v (permuted order, like Q) */
+	if (K->nlr) {
+		double t[2 * LM_MAX];
+		for (int a = 0; a < K->nlr; ++a) { double s = 0; for (int i = 0; i < n; ++i) s += K->Z[(size_t)a * n + i] * K->tmp[i]; t[a] = s; }
+		lu_solve(K->nlr, K->Clu, K->Cpiv, t);
+		for (int a = 0; a < K->nlr; ++a) for (int i = 0; i < n; ++i) K->tmp[i] += K->Z[(size_t)a * n + i] * t[a];
+	}
+	orc_sky_bwd(S, K->Lsky, K->tmp);
+	for (int i = 0; i < n; ++i) u[i] = K->tmp[S->iperm[i]];
 }
 
 /* One primal-dual solve (PDFullSpaceSolver::SolveOnce in condensed form).  Row-indexed inputs: rc_d[i] = rhs of the
@@ -323,9 +322,12 @@ int orc_ipopt_solve(orc_problem *p, const orc_ipopt_options *o, double *x, orc_i
 				Mid[(n_pairs + b) * q + a] = a > b ? sy : 0.0;           /* L' */
 				Mid[(n_pairs + a) * q + n_pairs + b] = a == b ? -sy : 0.0;   /* -D */
 			}
-			for (int a = 0; a < q; ++a) m_solve(&K, Bl + (size_t)a * n, Z + (size_t)a * n);
+			for (int a = 0; a < q; ++a) {
+				for (int i = 0; i < n; ++i) Z[(size_t)a * n + S->iperm[i]] = Bl[(size_t)a * n + i];
+				orc_sky_fwd(S, M, Z + (size_t)a * n);                 /* Q = L^-1 Bl */
+			}
 			for (int a = 0; a < q; ++a) for (int b = 0; b < q; ++b) {
-				double t = 0; for (int i = 0; i < n; ++i) t += Bl[(size_t)a * n + i] * Z[(size_t)b * n + i];
+				double t = 0; for (int i = 0; i < n; ++i) t += Z[(size_t)a * n + i] * Z[(size_t)b * n + i];
 				K.Clu[a * q + b] = Mid[a * q + b] - t;
 			}
 			if (getenv("ORC_DEBUG_LM")) { printf("  Mid:"); for (int a = 0; a < q * q; ++a) printf(" %.6e", Mid[a]); printf("\n  C:"); for (int a = 0; a < q * q; ++a) printf(" %.6e", K.Clu[a]); printf("\n"); }

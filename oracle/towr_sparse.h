@@ -23,5 +23,8 @@ void orc_free_struct(ipm_struct *S);
 int  orc_sky_chol(const ipm_struct *S, double *A);
 /* solves L L' x = b in place (b in permuted order) */
 void orc_sky_solve(const ipm_struct *S, const double *L, double *b);
+/* the two halves: L z = b and L' x = z */
+void orc_sky_fwd(const ipm_struct *S, const double *L, double *b);
+void orc_sky_bwd(const ipm_struct *S, const double *L, double *b);
 
 #endif

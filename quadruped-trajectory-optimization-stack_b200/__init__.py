@@ -67,7 +67,12 @@ class Shape(C.Structure):
 class Options(C.Structure):
     _fields_ = [("tol", C.c_double), ("constr_viol_tol", C.c_double), ("compl_inf_tol", C.c_double),
                 ("dual_inf_tol", C.c_double), ("max_iter", C.c_int), ("mu_init", C.c_double),
-                ("sigma_w", C.c_double), ("delta_c", C.c_double), ("feas_exit", C.c_int)]
+                ("sigma_w", C.c_double), ("delta_c", C.c_double), ("feas_exit", C.c_int),
+                ("algorithm", C.c_int), ("n_refine", C.c_int), ("lm_history", C.c_int)]
+
+
+ALG_IPOPT, ALG_FAST = 0, 1          # qtos_options.algorithm
+TRACE_ITERS, TRACE_COLS = 48, 8
 
 
 class Dims(C.Structure):
@@ -92,7 +97,7 @@ assert PROBLEM_DTYPE.itemsize == 8 * 28 + 8 and RESULT_DTYPE.itemsize == 56
 
 EXPORTS = ["qtos_default_shape", "qtos_default_options", "qtos_create", "qtos_destroy", "qtos_last_error",
            "qtos_get_dims", "qtos_upload_heightfield", "qtos_heightfield_query", "qtos_heightfield_cells",
-           "qtos_get_initial", "qtos_eval", "qtos_solve_batch", "qtos_solve_batch_device", "qtos_sample_csv",
+           "qtos_get_initial", "qtos_eval", "qtos_solve_batch", "qtos_solve_batch_device", "qtos_get_trace", "qtos_sample_csv",
            "qtos_write_csv", "qtos_launch_count", "qtos_set_profiling", "qtos_last_stats", "qtos_stream",
            "qtos_measure_fp64_peak"]
 
@@ -120,6 +125,7 @@ def lib():
         L.qtos_eval.argtypes = [vp, vp, C.c_int, dp, dp, dp]
         L.qtos_solve_batch.argtypes = [vp, vp, C.c_int, C.POINTER(Options), vp, dp, dp]
         L.qtos_solve_batch_device.argtypes = [vp, vp, C.c_int, C.POINTER(Options), vp, vp]
+        L.qtos_get_trace.argtypes = [vp, C.c_int, dp]
         L.qtos_sample_csv.argtypes = [vp, vp, C.c_int, dp, dp]
         L.qtos_write_csv.argtypes = [dp, C.c_int, C.c_char_p]
         L.qtos_launch_count.argtypes = [vp]
@@ -274,6 +280,13 @@ class Solver:
                                                  C.c_void_p(d_results_ptr) if d_results_ptr else None,
                                                  C.c_void_p(d_x_ptr) if d_x_ptr else None))
 
+    def trace(self, n):
+        """Ipopt-style iteration table of the first n problems of the last solve (algorithm IPOPT):
+        [n, TRACE_ITERS, (inf_pr, inf_du, mu, ||d||, alpha_du, alpha_pr, ls, tag)]."""
+        t = np.zeros((n, TRACE_ITERS, TRACE_COLS))
+        self._ck(self._L.qtos_get_trace(self._h, int(n), _dp(t)))
+        return t
+
     def sample_csv(self, problems, x):
         p, pp = self._probs(problems)
         n = len(p)
@@ -292,8 +305,8 @@ class Solver:
         """device ms per phase of the last solve (profiling on), problems factored, iterations."""
         st = Stats()
         self._L.qtos_last_stats(self._h, C.byref(st))
-        names = ["init", "jac", "prepare", "assemble", "factor", "step"]
-        return {"ms": dict(zip(names, list(st.ms)[:6])), "factorizations": st.factorizations,
+        names = ["init", "jac", "prepare", "assemble", "factor", "step", "solve"]
+        return {"ms": dict(zip(names, list(st.ms)[:7])), "factorizations": st.factorizations,
                 "factor_launches": st.factor_launches, "iterations": st.iterations}
 
     def fp64_peak_tflops(self):

@@ -58,7 +58,23 @@ struct DevWork {
 	int *status, *iters, *flags;            /* [1] each */
 	int *n_running;                         /* single counter */
 	int *active, *n_active;                 /* [n] problems that go on to assemble / factor / step in this iteration, and their count */
+	/* QTOS_ALG_IPOPT (qtos_ipopt.cuh) */
+	double *ipst;                           /* [IP_N] algorithm state */
+	double *glx, *lastx, *gJold, *adx, *cdx;/* [npad] J'y, previous x, J(x_k)'y_{k+1}, affine / centering dx (permuted order) */
+	double *lmS, *lmY;                      /* [6][npad] limited-memory pairs (ring) */
+	double *RB, *PB;                        /* [nb][16][16] right-hand sides of the factorization's forward substitution, and L^-1 of them */
+	double *wA, *wC;                        /* [m] first-pass row weights of the affine / centering right-hand side */
+	double *ads, *ady, *advL, *advU, *cds, *cdy, *cdvL, *cdvU;   /* [m] the two directions, row part */
+	double *trace;                          /* [QTOS_TRACE_ITERS][QTOS_TRACE_COLS] */
 };
+
+/* IPOPT algorithm state per problem (doubles) */
+enum { IP_MU = 0, IP_TAU, IP_FREE, IP_MU_MAX, IP_AMU_THMIN, IP_TH_MAX, IP_TH_MIN, IP_SIGMA_W, IP_NPAIRS, IP_SKIPPED, IP_HAVE_LAST,
+       IP_NFILTER, IP_SIGMA_F, IP_AVRG, IP_ERR, IP_THETA, IP_GL2, IP_PR2, IP_ALPHA_PR, IP_ALPHA_DU, IP_DNORM, IP_LS, IP_TAG,
+       IP_HEAD, IP_FPHI = 32, IP_FTH = 64, IP_MID = 96, IP_N = 256 };
+#define IP_FILTER_MAX 32
+#define IP_LM 6                             /* limited-memory history capacity */
+#define IP_NRHS 16                          /* right-hand sides of the factorization: 6 S + 6 Y columns, affine, centering, 2 spare */
 
 enum { SC_MU = 0, SC_NU, SC_SD, SC_SC, SC_DUAL, SC_THETA, SC_COMPL, SC_VIOL, SC_E0, SC_NFAIL, SC_N };
 

@@ -1,0 +1,707 @@
+/*
+ * qtos_ipopt.cuh -- kernels of QTOS_ALG_IPOPT: the interior-point algorithm the reference runs (Ipopt 3.11.9 as configured
+ * by ifopt: limited-memory BFGS Hessian with history 6, adaptive quality-function barrier update, filter line search;
+ * ref: solver/towr/src/main.cpp:444-463, logs/towr_log.out:37-64).  Ipopt's source is not under /root/reference; the
+ * algorithm is the published one (Waechter & Biegler, Math. Prog. 106, 2006; Nocedal, Waechter & Waltz, SIAM J. Optim. 19,
+ * 2009), restated for one thread block per problem.  The test oracle of exactly this form is oracle/towr_ipopt.c, which is
+ * pinned to the reference's logged iteration tables and plans.
+ *
+ * One batch iteration = k_jac_dyn | k_jac_rom -> kip_prepare -> k_asm -> k_factor<.,1> -> kip_solve -> kip_step:
+ *   kip_prepare  J'y, limited-memory update (pairs s = x+ - x, y = (J+ - J)'lambda+), error measures and termination,
+ *                barrier-update bookkeeping (free / fixed mode), Sigma, the right-hand sides of the affine-scaling and
+ *                centering directions and the limited-memory columns Bl = [sigma S, Y] as 16 right-hand sides (W.RB)
+ *   k_asm        M = sigma I + Jd' Sigma Jd + rho Jc' Jc
+ *   k_factor     M = L L' and P = L^-1 RB (one more block row of the factorization)
+ *   kip_solve    Woodbury term between the triangular solves: Mf^-1 v = L'^-1 (p + Q (Mid - Q'Q)^-1 Q'p), Q = L^-1 Bl;
+ *                n_refine multiplier-method passes on the equality block; both directions at once (two right-hand sides
+ *                through every sweep over L, the rows of L streamed by bulk asynchronous copies)
+ *   kip_step     quality-function barrier oracle (golden section over sigma), search direction aff + sigma cen,
+ *                fraction to the boundary, filter line search with in-kernel g(x), iterate and multiplier update
+ */
+#ifndef QTOS_IPOPT_CUH_
+#define QTOS_IPOPT_CUH_
+
+#define IP_EPS 2.220446049250313e-16
+
+/* ------------------------------------------------------------------ kip_prepare */
+
+__global__ void __launch_bounds__(QTOS_THREADS, PREP_MINB)
+kip_prepare(DevTables T, DevWork W, qtos_options opt, int it)
+{
+	const int pid = blockIdx.x;
+	if (W.status[pid] != QTOS_RUNNING) return;
+	__shared__ double red[15 * 32];
+	__shared__ double sdots[2 * IP_LM * IP_LM];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const double *Jv = WS(Jv, T.nJ), *r = WS(r, T.m), *s = WS(s, T.m), *vL = WS(zL, T.m), *vU = WS(zU, T.m);
+	const double *dL = WS(dL, T.m), *dU = WS(dU, T.m), *sc = WS(sc, T.m), *y = WS(y, T.m), *x = WS(x, T.n_all);
+	double *Sig = WS(Sig, T.m), *wA = WS(wA, T.m), *wC = WS(wC, T.m), *scal = WS(scal, 16), *ip = WS(ipst, IP_N);
+	double *glx = WS(glx, T.npad), *lastx = WS(lastx, T.npad), *gJold = WS(gJold, T.npad);
+	double *tS = WS(adx, T.npad), *tY = WS(cdx, T.npad);          /* candidate pair (the direction buffers are free here) */
+	double *lmS = WS(lmS, IP_LM * T.npad), *lmY = WS(lmY, IP_LM * T.npad), *RB = WS(RB, T.npad * IP_NRHS);
+	const int hist = opt.lm_history < 1 ? 1 : (opt.lm_history > IP_LM ? IP_LM : opt.lm_history);
+	/* state of the previous iteration (every thread reads it before thread 0 rewrites it at the end) */
+	double mu = ip[IP_MU], tau = ip[IP_TAU], sigma_w = ip[IP_SIGMA_W], mu_max = ip[IP_MU_MAX], amu_thmin = ip[IP_AMU_THMIN];
+	int free_mode = (int)ip[IP_FREE], n_pairs = (int)ip[IP_NPAIRS], skipped = (int)ip[IP_SKIPPED], head = (int)ip[IP_HEAD];
+	int nfilter = (int)ip[IP_NFILTER];
+	const int have_last = (int)ip[IP_HAVE_LAST];
+	/* v: 0 dual_inf (max) 1 primal_inf (max) 2 compl (max) 3 sum|y| 4 sum z 5 viol (max) 6 theta (sum) 7 sum s z 8 sum 0*r
+	 *    9 |grad L|^2 10 |c|^2 11 max |s z - mu| 12 s'y 13 s's 14 y'y */
+	double v[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	for (int i = tid; i < T.npad; i += blockDim.x) {
+		const double g = jt_gather(T, Jv, y, i);
+		const int var = T.var_of_perm[i];
+		const double xi = var >= 0 ? x[var] : 0.0;
+		glx[i] = g;
+		v[0] = fmax(v[0], fabs(g)); v[9] += g * g;
+		if (have_last) {
+			const double sn = xi - lastx[i], yn = g - gJold[i];
+			tS[i] = sn; tY[i] = yn;
+			v[12] += sn * yn; v[13] += sn * sn; v[14] += yn * yn;
+		}
+		lastx[i] = xi;
+	}
+	for (int i = tid; i < T.m; i += blockDim.x) {
+		const int fl = T.row_flags[i];
+		v[3] += fabs(y[i]);
+		v[8] += 0.0 * r[i];
+		if (fl & ROW_EQ) { const double a = fabs(r[i]); v[1] = fmax(v[1], a); v[6] += a; v[5] = fmax(v[5], a / sc[i]); v[10] += r[i] * r[i]; continue; }
+		const double c = r[i] - s[i], gs = -y[i] - vL[i] + vU[i];
+		v[1] = fmax(v[1], fabs(c)); v[6] += fabs(c); v[10] += c * c;
+		v[0] = fmax(v[0], fabs(gs)); v[9] += gs * gs;
+		if (fl & ROW_HASL) { const double p = (s[i] - dL[i]) * vL[i]; v[2] = fmax(v[2], p); v[7] += p; v[4] += vL[i]; v[11] = fmax(v[11], fabs(p - mu)); v[5] = fmax(v[5], T.gl[i] - r[i] / sc[i]); }
+		if (fl & ROW_HASU) { const double p = (dU[i] - s[i]) * vU[i]; v[2] = fmax(v[2], p); v[7] += p; v[4] += vU[i]; v[11] = fmax(v[11], fabs(p - mu)); v[5] = fmax(v[5], r[i] / sc[i] - T.gu[i]); }
+	}
+	{ const int ops[15] = {1, 1, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1, 0, 0, 0}; block_reduce<15>(v, ops, red); }
+	const double dual_inf = v[0], primal_inf = v[1], compl_ = v[2], viol = v[5], theta = v[6];
+	const int nbnd = T.n_bounds > 0 ? T.n_bounds : 1;
+	const double s_d = fmax(100.0, (v[3] + v[4]) / (double)(T.m + T.n_bounds)) / 100.0;
+	const double s_c = fmax(100.0, v[4] / (double)nbnd) / 100.0;
+	const double nlp_error = fmax(fmax(dual_inf / s_d, primal_inf), compl_ / s_c);
+	const double avrg_compl = v[7] / (double)nbnd;
+	const bool invalid = !(v[8] == 0.0) || !(nlp_error == nlp_error) || !(theta == theta);
+	const bool conv = !invalid && nlp_error <= opt.tol && dual_inf <= opt.dual_inf_tol && viol <= opt.constr_viol_tol && compl_ <= opt.compl_inf_tol;
+	const bool stop = invalid || conv || it >= opt.max_iter;
+	if (tid == 0) {
+		scal[SC_DUAL] = dual_inf; scal[SC_THETA] = primal_inf; scal[SC_COMPL] = compl_; scal[SC_VIOL] = viol; scal[SC_E0] = nlp_error; scal[SC_MU] = mu;
+		W.iters[pid] = it;
+		if (it < QTOS_TRACE_ITERS) {
+			double *tr = WS(trace, QTOS_TRACE_ITERS * QTOS_TRACE_COLS) + it * QTOS_TRACE_COLS;
+			tr[0] = viol; tr[1] = dual_inf; tr[2] = mu; tr[3] = ip[IP_DNORM]; tr[4] = ip[IP_ALPHA_DU]; tr[5] = ip[IP_ALPHA_PR]; tr[6] = ip[IP_LS]; tr[7] = ip[IP_TAG];
+		}
+		if (stop) {
+			if (invalid) { const double qnan = v[8] - v[8] + (nlp_error - nlp_error); scal[SC_VIOL] = scal[SC_E0] = qnan; }
+			W.status[pid] = invalid ? QTOS_INVALID_NUMBER : (conv ? QTOS_SOLVE_SUCCEEDED : QTOS_MAX_ITER);
+			atomicSub(W.n_running, 1);
+		}
+	}
+	if (stop) return;
+
+	/* ---- limited-memory update (LimMemQuasiNewtonUpdater::UpdateHessian) */
+	int new_slot = -1;
+	if (have_last) {
+		const double sTy = v[12], sTs = v[13], yTy = v[14];
+		const bool skipping = sTy <= sqrt(IP_EPS) * sqrt(sTs) * sqrt(yTy);
+		if (skipping) { if (++skipped >= 2) { n_pairs = 0; head = 0; sigma_w = 1.0; skipped = 0; } }
+		else {
+			skipped = 0;
+			if (n_pairs == hist) { head = (head + 1) % hist; n_pairs--; }
+			new_slot = (head + n_pairs) % hist;
+			n_pairs++;
+			sigma_w = fmin(fmax(sTy / sTs, 1e-8), 1e8);
+		}
+	}
+	if (new_slot >= 0) {
+		for (int i = tid; i < T.npad; i += blockDim.x) { lmS[(size_t)new_slot * T.npad + i] = tS[i]; lmY[(size_t)new_slot * T.npad + i] = tY[i]; }
+	}
+	const double sigma_f = sigma_w;
+
+	/* ---- barrier parameter, part one (AdaptiveMuUpdate::UpdateBarrierParameter): mode switches and the fixed-mode update;
+	 *      the free-mode oracle needs the two directions and runs in kip_step */
+	const double mu_min = fmin(1e-11, 0.5 * fmin(opt.tol, opt.compl_inf_tol));
+	if (mu_max < 0.0) mu_max = 1e3 * avrg_compl;
+	const bool acceptable = theta <= amu_thmin;
+	if (!free_mode) {
+		if (acceptable) free_mode = 1;
+		else {
+			const double berr = fmax(fmax(dual_inf / s_d, primal_inf), v[11] / s_c);
+			if (berr <= 10.0 * mu) {
+				double nm = fmin(0.2 * mu, pow(mu, 1.5));
+				nm = fmax(nm, fmin(opt.compl_inf_tol, opt.tol) / 11.0);
+				mu = nm; tau = fmax(0.99, 1.0 - mu); nfilter = 0;
+			}
+		}
+	} else if (!acceptable) {
+		free_mode = 0;
+		mu = fmin(fmax(0.8 * avrg_compl, mu_min), mu_max);
+		tau = fmax(0.99, 1.0 - mu); nfilter = 0;
+	}
+	if (free_mode && acceptable) {                        /* RememberCurrentPointAsAccepted */
+		const double mg = 1e-5 * fmin(1.0, theta);
+		if (mg > 0.0 && theta - mg < amu_thmin) amu_thmin = theta - mg;
+	}
+
+	/* ---- Sigma and the first-pass row weights of the two right-hand sides (PDFullSpaceSolver in condensed form) */
+	const double rho = 1.0 / opt.delta_c;
+	for (int i = tid; i < T.m; i += blockDim.x) {
+		const int fl = T.row_flags[i];
+		if (fl & ROW_EQ) { Sig[i] = rho; wA[i] = rho * -r[i]; wC[i] = 0.0; continue; }
+		double sg = 0.0, augA = -(-y[i] - vL[i] + vU[i]), augC = 0.0;
+		if (fl & ROW_HASL) { const double sl = s[i] - dL[i]; sg += vL[i] / sl; augA += (-sl * vL[i]) / sl; augC += avrg_compl / sl; }
+		if (fl & ROW_HASU) { const double su = dU[i] - s[i]; sg += vU[i] / su; augA -= (-su * vU[i]) / su; augC -= avrg_compl / su; }
+		Sig[i] = sg;
+		wA[i] = sg * -(r[i] - s[i]) + augA;
+		wC[i] = augC;
+	}
+	__syncthreads();
+	/* ---- right-hand-side block: columns 0..5 sigma S, 6..11 Y (chronological, unused ones zero), 12 affine, 13 centering */
+	for (int i = tid; i < T.npad; i += blockDim.x) {
+		const double va = -glx[i] + jt_gather(T, Jv, wA, i), vc = jt_gather(T, Jv, wC, i);
+		double *o = RB + (size_t)(i >> 4) * 256 + (i & 15);
+#pragma unroll
+		for (int a = 0; a < IP_LM; ++a) {
+			const int sl = (head + a) % hist;
+			o[a * 16] = a < n_pairs ? sigma_f * lmS[(size_t)sl * T.npad + i] : 0.0;
+			o[(IP_LM + a) * 16] = a < n_pairs ? lmY[(size_t)sl * T.npad + i] : 0.0;
+		}
+		o[12 * 16] = i < T.n_free ? va : 0.0; o[13 * 16] = i < T.n_free ? vc : 0.0; o[14 * 16] = 0.0; o[15 * 16] = 0.0;
+	}
+	/* ---- middle matrix of the compact representation: [[sigma S'S, L], [L', -D]], L = strictly lower part of S'Y */
+	for (int q = warp; q < n_pairs * n_pairs; q += blockDim.x >> 5) {
+		const int a = q / n_pairs, b = q - a * n_pairs;
+		const double *Sa = lmS + (size_t)((head + a) % hist) * T.npad, *Sb = lmS + (size_t)((head + b) % hist) * T.npad, *Yb = lmY + (size_t)((head + b) % hist) * T.npad;
+		double ss = 0.0, sy = 0.0;
+		for (int i = lane; i < T.npad; i += 32) { const double sa = Sa[i]; ss += sa * Sb[i]; sy += sa * Yb[i]; }
+		for (int o = 16; o > 0; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+		if (lane == 0) { sdots[a * IP_LM + b] = ss; sdots[IP_LM * IP_LM + a * IP_LM + b] = sy; }
+	}
+	__syncthreads();
+	if (tid < 4 * IP_LM * IP_LM) {
+		const int q2 = 2 * IP_LM, ra = tid / q2, cb = tid - ra * q2;
+		const int a = ra % IP_LM, b = cb % IP_LM;
+		double val = 0.0;
+		if (a < n_pairs && b < n_pairs) {
+			if (ra < IP_LM && cb < IP_LM) val = sigma_f * sdots[a * IP_LM + b];
+			else if (ra < IP_LM) val = a > b ? sdots[IP_LM * IP_LM + a * IP_LM + b] : 0.0;              /* L[a][b] */
+			else if (cb < IP_LM) val = b > a ? sdots[IP_LM * IP_LM + b * IP_LM + a] : 0.0;              /* L'[a][b] = L[b][a] */
+			else val = a == b ? -sdots[IP_LM * IP_LM + a * IP_LM + a] : 0.0;
+		}
+		ip[IP_MID + tid] = val;
+	}
+	if (tid == 0) {
+		ip[IP_MU] = mu; ip[IP_TAU] = tau; ip[IP_FREE] = free_mode; ip[IP_MU_MAX] = mu_max; ip[IP_AMU_THMIN] = amu_thmin;
+		ip[IP_SIGMA_W] = sigma_w; ip[IP_SIGMA_F] = sigma_f; ip[IP_NPAIRS] = n_pairs; ip[IP_SKIPPED] = skipped; ip[IP_HEAD] = head;
+		ip[IP_HAVE_LAST] = 1.0; ip[IP_NFILTER] = nfilter; ip[IP_AVRG] = avrg_compl; ip[IP_ERR] = nlp_error; ip[IP_THETA] = theta;
+		ip[IP_GL2] = v[9]; ip[IP_PR2] = v[10];
+		W.active[atomicAdd(W.n_active, 1)] = pid;
+	}
+}
+
+/* ------------------------------------------------------------------ kip_solve */
+
+#define KS_T 128
+#ifndef KS_MINB
+#define KS_MINB 3
+#endif
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+	asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra WAIT_%=;\n}\n"
+	             :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+/* 1-D bulk asynchronous copy global -> shared (TMA unit, no tensor map), completion counted on the mbarrier */
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+struct SweepCtx {
+	const int *fb, *blkptr;
+	int nb, npad;
+	const double *M, *Dinv;
+	double *z;              /* [2][npad] */
+	double *lb;             /* [2][max_w * 256] */
+	double *part;           /* [4][16][2] */
+	double *xi;             /* [2][16] */
+	uint64_t *mbar;         /* [2] */
+	int lbsz;               /* doubles per row buffer */
+	unsigned phase[2];
+};
+
+/* row I of L into buffer b: block 0 = inv(L_II), then the off-diagonal blocks fI..I-1, all fragment-major (see frag_off) */
+__device__ __forceinline__ void sweep_fetch(SweepCtx &C, int I, int b)
+{
+	const SweepCtx &T = C;
+	const int nbk = I - T.fb[I];
+	mbar_expect_tx(&C.mbar[b], (unsigned)((nbk + 1) * 2048));
+	bulk_g2s(C.lb + (size_t)b * C.lbsz, C.Dinv + (size_t)I * 256, 2048u, &C.mbar[b]);
+	if (nbk) bulk_g2s(C.lb + (size_t)b * C.lbsz + 256, C.M + (size_t)T.blkptr[I] * 256, (unsigned)(nbk * 2048), &C.mbar[b]);
+}
+
+/* L' x = z for the two right-hand sides in C.z, in place; all KS_T threads */
+__device__ __forceinline__ void sweep_backward(SweepCtx &C)
+{
+	const SweepCtx &T = C;
+	const int tid = threadIdx.x, npad = T.npad;
+	if (tid == 0) sweep_fetch(C, T.nb - 1, 0);
+	for (int I = T.nb - 1, b = 0; I >= 0; --I, b ^= 1) {
+		if (tid == 0 && I > 0) sweep_fetch(C, I - 1, b ^ 1);       /* that buffer was released by the barrier ending row I+1 */
+		mbar_wait(&C.mbar[b], C.phase[b]); C.phase[b] ^= 1;
+		const double *buf = C.lb + (size_t)b * C.lbsz;
+		const int fI = T.fb[I];
+		if (tid < 32) {
+			const int k = tid >> 4, c = tid & 15;
+			const double *zI = C.z + k * npad + I * 16;
+			double acc = 0.0;
+			for (int q = c; q < 16; ++q) acc += buf[frag_off(q, c)] * zI[q];
+			C.xi[tid] = acc;
+		}
+		__syncthreads();
+		if (tid < 32) C.z[(tid >> 4) * npad + I * 16 + (tid & 15)] = C.xi[tid];
+		for (int c = tid; c < (I - fI) * 16; c += KS_T) {
+			const double *blk = buf + 256 + (c >> 4) * 256 + frag_off(0, c & 15);
+			double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+			for (int q = 0; q < 16; ++q) { const double l = blk[((q >> 3) << 7) + ((q & 7) << 3)]; a0 += l * C.xi[q]; a1 += l * C.xi[16 + q]; }
+			C.z[fI * 16 + c] -= a0; C.z[npad + fI * 16 + c] -= a1;
+		}
+		__syncthreads();
+	}
+}
+
+/* L z = v for the two right-hand sides in C.z, in place */
+__device__ __forceinline__ void sweep_forward(SweepCtx &C)
+{
+	const SweepCtx &T = C;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, npad = T.npad;
+	const int fr = lane >> 2, fc = lane & 3;
+	if (tid == 0) sweep_fetch(C, 0, 0);
+	for (int I = 0, b = 0; I < T.nb; ++I, b ^= 1) {
+		if (tid == 0 && I + 1 < T.nb) sweep_fetch(C, I + 1, b ^ 1);
+		mbar_wait(&C.mbar[b], C.phase[b]); C.phase[b] ^= 1;
+		const double *buf = C.lb + (size_t)b * C.lbsz;
+		const int fI = T.fb[I], nbk = I - fI;
+		/* every warp takes every fourth block of the row; a lane reads its operand-fragment chunks (conflict-free 128-bit
+		 * loads): rows fr and 8 + fr, columns 4 fc + 2 h + {0, 1} */
+		double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};      /* [row half][right-hand side] */
+		for (int jb = warp; jb < nbk; jb += KS_T / 32) {
+			const double2 *blk = reinterpret_cast<const double2 *>(buf + 256 + jb * 256) + lane;
+			const double *z0 = C.z + (fI + jb) * 16 + 4 * fc, *z1 = z0 + npad;
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				const double2 za = *reinterpret_cast<const double2 *>(z0 + 2 * h), zb = *reinterpret_cast<const double2 *>(z1 + 2 * h);
+#pragma unroll
+				for (int tn = 0; tn < 2; ++tn) {
+					const double2 l = blk[tn * 64 + h * 32];
+					acc[tn][0] += l.x * za.x + l.y * za.y;
+					acc[tn][1] += l.x * zb.x + l.y * zb.y;
+				}
+			}
+		}
+#pragma unroll
+		for (int tn = 0; tn < 2; ++tn)
+#pragma unroll
+			for (int k = 0; k < 2; ++k) {
+				double a = acc[tn][k];
+				a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
+				if (fc == 0) C.part[(warp * 16 + tn * 8 + fr) * 2 + k] = a;
+			}
+		__syncthreads();
+		if (tid < 32) {
+			const int k = tid >> 4, q = tid & 15;
+			double sacc = 0.0;
+#pragma unroll
+			for (int w = 0; w < KS_T / 32; ++w) sacc += C.part[(w * 16 + q) * 2 + k];
+			C.xi[tid] = C.z[k * npad + I * 16 + q] - sacc;
+		}
+		__syncthreads();
+		if (tid < 32) {
+			const int k = tid >> 4, rr = tid & 15;
+			double a = 0.0;
+			for (int q = 0; q <= rr; ++q) a += buf[frag_off(rr, q)] * C.xi[k * 16 + q];
+			C.z[k * npad + I * 16 + rr] = a;
+		}
+		__syncthreads();
+	}
+}
+
+/* dense LU with partial pivoting of the 12 x 12 Woodbury matrix (one thread; row-major, in place) */
+__device__ inline int lu12_factor(double *A, int *piv)
+{
+	const int n = 2 * IP_LM;
+	for (int k = 0; k < n; ++k) {
+		int p = k;
+		for (int i = k + 1; i < n; ++i) if (fabs(A[i * n + k]) > fabs(A[p * n + k])) p = i;
+		piv[k] = p;
+		if (A[p * n + k] == 0.0) return 0;
+		if (p != k) for (int j = 0; j < n; ++j) { const double t = A[k * n + j]; A[k * n + j] = A[p * n + j]; A[p * n + j] = t; }
+		for (int i = k + 1; i < n; ++i) {
+			A[i * n + k] /= A[k * n + k];
+			for (int j = k + 1; j < n; ++j) A[i * n + j] -= A[i * n + k] * A[k * n + j];
+		}
+	}
+	return 1;
+}
+__device__ inline void lu12_solve(const double *A, const int *piv, double *b)
+{
+	const int n = 2 * IP_LM;
+	for (int k = 0; k < n; ++k) { const double t = b[k]; b[k] = b[piv[k]]; b[piv[k]] = t; }
+	for (int k = 0; k < n; ++k) for (int i = k + 1; i < n; ++i) b[i] -= A[i * n + k] * b[k];
+	for (int k = n - 1; k >= 0; --k) { for (int j = k + 1; j < n; ++j) b[k] -= A[k * n + j] * b[j]; b[k] /= A[k * n + k]; }
+}
+
+__global__ void __launch_bounds__(KS_T, KS_MINB)
+kip_solve(DevTables T, DevWork W, qtos_options opt, int max_w)
+{
+	const int pid = blockIdx.x;
+	if (W.status[pid] != QTOS_RUNNING) return;
+	extern __shared__ __align__(16) double sm[];
+	const int npad = T.npad, q12 = 2 * IP_LM;
+	double *z = sm;                                /* [2][npad] */
+	double *lb = z + 2 * npad;                     /* [2][max_w * 256] */
+	double *G = lb + 2 * max_w * 256;              /* [12][14]  Q'[Q, p_aff, p_cen] */
+	double *Clu = G + q12 * 14;                    /* [12][12] */
+	double *tt = Clu + q12 * q12;                  /* [2][12] */
+	double *part = tt + 2 * q12;                   /* [4][16][2] */
+	double *xi = part + 128;                       /* [2][16] */
+	uint64_t *mbar = reinterpret_cast<uint64_t *>(xi + 32);   /* [2] */
+	int *piv = reinterpret_cast<int *>(mbar + 2);  /* [12] + flag */
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const double *Jv = WS(Jv, T.nJ), *r = WS(r, T.m), *s = WS(s, T.m), *vL = WS(zL, T.m), *vU = WS(zU, T.m);
+	const double *dL = WS(dL, T.m), *dU = WS(dU, T.m), *y = WS(y, T.m), *Sig = WS(Sig, T.m);
+	const double *RB = WS(RB, npad * IP_NRHS), *PB = WS(PB, npad * IP_NRHS);
+	double *ip = WS(ipst, IP_N);
+	double *ady = WS(ady, T.m), *cdy = WS(cdy, T.m), *eA = WS(rt, T.m), *eC = WS(st, T.m);
+	const int n_pairs = (int)ip[IP_NPAIRS];
+	const double avrg_compl = ip[IP_AVRG], rho = 1.0 / opt.delta_c;
+	if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+	SweepCtx C; C.fb = T.fb; C.blkptr = T.blkptr; C.nb = T.nb; C.npad = npad; C.M = WS(M, T.nM); C.Dinv = WS(Dinv, T.nb * 256); C.z = z; C.lb = lb; C.part = part; C.xi = xi; C.mbar = mbar;
+	C.lbsz = max_w * 256; C.phase[0] = C.phase[1] = 0;
+	for (int i = tid; i < npad; i += KS_T) {
+		const double *o = PB + (size_t)(i >> 4) * 256 + (i & 15);
+		z[i] = o[12 * 16]; z[npad + i] = o[13 * 16];
+	}
+	for (int i = tid; i < T.m; i += KS_T) { ady[i] = 0.0; cdy[i] = 0.0; eA[i] = 0.0; eC[i] = 0.0; }
+	__syncthreads();
+	int nlr = 2 * n_pairs;
+	for (int pass = 0; pass <= opt.n_refine; ++pass) {
+		if (nlr) {
+			/* G[a][b] = Q_a' [Q_b | p_aff | p_cen]: a warp takes column a and keeps all partial sums of its row of G */
+			for (int a = warp; a < q12; a += KS_T / 32) {
+				if ((a % IP_LM) >= n_pairs) continue;
+				double acc[14];
+#pragma unroll
+				for (int b = 0; b < 14; ++b) acc[b] = 0.0;
+				for (int i = lane; i < npad; i += 32) {
+					const double *o = PB + (size_t)(i >> 4) * 256 + (i & 15);
+					const double qa = o[a * 16];
+					if (pass == 0) {
+#pragma unroll
+						for (int b = 0; b < q12; ++b) acc[b] += qa * o[b * 16];
+					}
+					acc[12] += qa * z[i]; acc[13] += qa * z[npad + i];
+				}
+#pragma unroll
+				for (int b = 0; b < 14; ++b) {
+					if (pass > 0 && b < q12) continue;
+					double t = acc[b];
+					for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+					if (lane == 0) G[a * 14 + b] = t;
+				}
+			}
+			__syncthreads();
+			if (pass == 0) {
+				if (tid == 0) {
+					/* C = Mid - Q'Q on the slots in use, identity on the others */
+					for (int a = 0; a < q12; ++a) for (int b = 0; b < q12; ++b) {
+						const bool used = (a % IP_LM) < n_pairs && (b % IP_LM) < n_pairs;
+						Clu[a * q12 + b] = used ? ip[IP_MID + a * q12 + b] - G[a * 14 + b] : (a == b ? 1.0 : 0.0);
+					}
+					piv[q12] = lu12_factor(Clu, piv);
+					if (!piv[q12]) { ip[IP_NPAIRS] = 0.0; ip[IP_HEAD] = 0.0; ip[IP_SIGMA_W] = 1.0; }     /* singular: drop the pairs */
+				}
+				__syncthreads();
+				if (!piv[q12]) nlr = 0;
+			}
+			if (nlr) {
+				if (tid < 2) {
+					double *t = tt + tid * q12;
+					for (int a = 0; a < q12; ++a) t[a] = (a % IP_LM) < n_pairs ? G[a * 14 + 12 + tid] : 0.0;
+					lu12_solve(Clu, piv, t);
+				}
+				__syncthreads();
+				for (int i = tid; i < npad; i += KS_T) {
+					const double *o = PB + (size_t)(i >> 4) * 256 + (i & 15);
+					double a0 = 0.0, a1 = 0.0;
+					for (int a = 0; a < q12; ++a) {
+						if ((a % IP_LM) >= n_pairs) continue;
+						const double qa = o[a * 16];
+						a0 += qa * tt[a]; a1 += qa * tt[q12 + a];
+					}
+					z[i] += a0; z[npad + i] += a1;
+				}
+			}
+			__syncthreads();
+		}
+		sweep_backward(C);                         /* z = dx of both directions, permuted order */
+		/* multiplier-method update on the equality rows: dy += rho (Jc dx - b2) */
+		for (int i = tid; i < T.m; i += KS_T) {
+			if (!(T.row_flags[i] & ROW_EQ)) continue;
+			const Element &E = T.elems[T.row_elem[i]];
+			const int rr = i - E.row0;
+			const int16_t *cols = T.elem_cols + E.coloff;
+			double j0 = 0.0, j1 = 0.0;
+			for (int a = 0; a < E.ncols; ++a) { const double jv = Jv[E.valoff + a * E.ld + rr]; j0 += jv * z[cols[a]]; j1 += jv * z[npad + cols[a]]; }
+			const double da = ady[i] + rho * (j0 + r[i]), dc = cdy[i] + rho * j1;      /* b2 = -r (affine), 0 (centering) */
+			ady[i] = da; cdy[i] = dc; eA[i] = da; eC[i] = dc;
+		}
+		if (pass == opt.n_refine) break;
+		__syncthreads();
+		/* next right-hand side: v = v0 - Jc' dy, then p = L^-1 v */
+		for (int i = tid; i < ((npad + 31) & ~31); i += KS_T) {
+			if (i >= npad) continue;
+			const double *o = RB + (size_t)(i >> 4) * 256 + (i & 15);
+			const double ga = jt_gather(T, Jv, eA, i), gc = jt_gather(T, Jv, eC, i);
+			z[i] = i < T.n_free ? o[12 * 16] - ga : 0.0; z[npad + i] = i < T.n_free ? o[13 * 16] - gc : 0.0;
+		}
+		__syncthreads();
+		sweep_forward(C);
+	}
+	__syncthreads();
+	/* ---- expansion of the condensed rows: ds, dy, dvL, dvU of both directions; dx out */
+	double *adx = WS(adx, npad), *cdx = WS(cdx, npad);
+	for (int i = tid; i < npad; i += KS_T) { adx[i] = z[i]; cdx[i] = z[npad + i]; }
+	double *ads = WS(ads, T.m), *advL = WS(advL, T.m), *advU = WS(advU, T.m), *cds = WS(cds, T.m), *cdvL = WS(cdvL, T.m), *cdvU = WS(cdvU, T.m);
+	for (int i = tid; i < T.m; i += KS_T) {
+		const int fl = T.row_flags[i];
+		if (fl & ROW_EQ) continue;
+		const Element &E = T.elems[T.row_elem[i]];
+		const int rr = i - E.row0;
+		const int16_t *cols = T.elem_cols + E.coloff;
+		double j0 = 0.0, j1 = 0.0;
+		for (int a = 0; a < E.ncols; ++a) { const double jv = Jv[E.valoff + a * E.ld + rr]; j0 += jv * z[cols[a]]; j1 += jv * z[npad + cols[a]]; }
+		double augA = -(-y[i] - vL[i] + vU[i]), augC = 0.0, sl = 1.0, su = 1.0;
+		if (fl & ROW_HASL) { sl = s[i] - dL[i]; augA += (-sl * vL[i]) / sl; augC += avrg_compl / sl; }
+		if (fl & ROW_HASU) { su = dU[i] - s[i]; augA -= (-su * vU[i]) / su; augC -= avrg_compl / su; }
+		const double dsa = j0 + (r[i] - s[i]), dsc = j1;                     /* ds = Jd dx - b2, b2 = -(d - s) / 0 */
+		ads[i] = dsa; cds[i] = dsc;
+		ady[i] = Sig[i] * dsa - augA; cdy[i] = Sig[i] * dsc - augC;
+		advL[i] = (fl & ROW_HASL) ? (-sl * vL[i] - vL[i] * dsa) / sl : 0.0;
+		cdvL[i] = (fl & ROW_HASL) ? (avrg_compl - vL[i] * dsc) / sl : 0.0;
+		advU[i] = (fl & ROW_HASU) ? (-su * vU[i] + vU[i] * dsa) / su : 0.0;
+		cdvU[i] = (fl & ROW_HASU) ? (avrg_compl + vU[i] * dsc) / su : 0.0;
+	}
+}
+
+/* ------------------------------------------------------------------ kip_step */
+
+/* QualityFunctionMuOracle::CalculateQualityFunction (2-norm squared, no centrality term) at sigma */
+__device__ __forceinline__ double ip_quality(const DevTables &T, const DevWork &W, int pid, double sg, double tau, double gl2, double pr2, double *red)
+{
+	const double *s = WS(s, T.m), *vL = WS(zL, T.m), *vU = WS(zU, T.m), *dL = WS(dL, T.m), *dU = WS(dU, T.m);
+	const double *ads = WS(ads, T.m), *advL = WS(advL, T.m), *advU = WS(advU, T.m), *cds = WS(cds, T.m), *cdvL = WS(cdvL, T.m), *cdvU = WS(cdvU, T.m);
+	double a[2] = {1.0, 1.0};
+	for (int i = threadIdx.x; i < T.m; i += blockDim.x) {
+		const int fl = T.row_flags[i];
+		if (fl & ROW_EQ) continue;
+		const double d = ads[i] + sg * cds[i];
+		if (fl & ROW_HASL) { const double uL = advL[i] + sg * cdvL[i]; if (d < 0) a[0] = fmin(a[0], -tau * (s[i] - dL[i]) / d); if (uL < 0) a[1] = fmin(a[1], -tau * vL[i] / uL); }
+		if (fl & ROW_HASU) { const double uU = advU[i] + sg * cdvU[i]; if (-d < 0) a[0] = fmin(a[0], -tau * (dU[i] - s[i]) / -d); if (uU < 0) a[1] = fmin(a[1], -tau * vU[i] / uU); }
+	}
+	{ const int ops[2] = {2, 2}; block_reduce<2>(a, ops, red); }
+	const double ap = a[0], ad = a[1];
+	double cc[1] = {0.0};
+	for (int i = threadIdx.x; i < T.m; i += blockDim.x) {
+		const int fl = T.row_flags[i];
+		if (fl & ROW_EQ) continue;
+		const double d = ads[i] + sg * cds[i];
+		if (fl & ROW_HASL) { const double t = ((s[i] - dL[i]) + ap * d) * (vL[i] + ad * (advL[i] + sg * cdvL[i])); cc[0] += t * t; }
+		if (fl & ROW_HASU) { const double t = ((dU[i] - s[i]) + ap * -d) * (vU[i] + ad * (advU[i] + sg * cdvU[i])); cc[0] += t * t; }
+	}
+	{ const int ops[1] = {0}; block_reduce<1>(cc, ops, red); }
+	const double n_dual = T.n_free + T.n_ineq, n_pri = T.m, n_comp = T.n_bounds;
+	return (1 - ad) * (1 - ad) * gl2 / n_dual + (1 - ap) * (1 - ap) * pr2 / n_pri + cc[0] / n_comp;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(QTOS_THREADS, MINB)
+kip_step(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *hfs, int n_hf, qtos_options opt)
+{
+	const int pid = blockIdx.x;
+	if (W.status[pid] != QTOS_RUNNING) return;
+	extern __shared__ __align__(16) double sm[];
+	double *b = sm;                       /* [npad] dx (permuted order) */
+	double *red = b + T.npad;             /* [8*32] */
+	__shared__ double sfphi[IP_FILTER_MAX], sfth[IP_FILTER_MAX];
+	const int tid = threadIdx.x;
+	const double *Jv = WS(Jv, T.nJ), *sc = WS(sc, T.m), *dLb = WS(dL, T.m), *dUb = WS(dU, T.m);
+	const double *adx = WS(adx, T.npad), *cdx = WS(cdx, T.npad);
+	const double *ads = WS(ads, T.m), *ady = WS(ady, T.m), *advL = WS(advL, T.m), *advU = WS(advU, T.m);
+	const double *cds = WS(cds, T.m), *cdy = WS(cdy, T.m), *cdvL = WS(cdvL, T.m), *cdvU = WS(cdvU, T.m);
+	double *s = WS(s, T.m), *y = WS(y, T.m), *vL = WS(zL, T.m), *vU = WS(zU, T.m), *r = WS(r, T.m);
+	double *rt = WS(rt, T.m), *st = WS(st, T.m), *x = WS(x, T.n_all), *xt = WS(xt, T.n_all), *ip = WS(ipst, IP_N);
+	double mu = ip[IP_MU], tau = ip[IP_TAU];
+	const int free_mode = (int)ip[IP_FREE];
+	int nfilter = (int)ip[IP_NFILTER];
+	const double avrg_compl = ip[IP_AVRG], nlp_error = ip[IP_ERR], theta = ip[IP_THETA], gl2 = ip[IP_GL2], pr2 = ip[IP_PR2], mu_max = ip[IP_MU_MAX];
+	double theta_max = ip[IP_TH_MAX], theta_min = ip[IP_TH_MIN];
+	if (tid < IP_FILTER_MAX) { sfphi[tid] = ip[IP_FPHI + tid]; sfth[tid] = ip[IP_FTH + tid]; }
+	__syncthreads();
+	const double mu_min = fmin(1e-11, 0.5 * fmin(opt.tol, opt.compl_inf_tol));
+	double sigma = mu / avrg_compl;
+	if (free_mode) {
+		tau = fmax(0.99, 1.0 - nlp_error);
+		/* QualityFunctionMuOracle::CalculateMu: golden section on sigma (linear scale), at most 8 steps */
+#define QF(sig_) ip_quality(T, W, pid, (sig_), tau, gl2, pr2, red)
+		const double s_1m = 1.0 - 1e-2;
+		const double qf_1 = QF(1.0), qf_1m = QF(s_1m);
+		double s_up, s_lo, q_up, q_lo; bool search = true;
+		if (qf_1m > qf_1) { s_up = fmin(100.0, mu_max / avrg_compl); s_lo = 1.0; q_up = -100.0; q_lo = qf_1; if (s_lo >= s_up) { sigma = s_up; search = false; } }
+		else { s_lo = fmax(1e-6, mu_min / avrg_compl); s_up = fmin(fmax(s_lo, s_1m), mu_max / avrg_compl); q_up = qf_1m; q_lo = -100.0; if (s_lo >= s_up) { sigma = s_lo; search = false; } }
+		if (search) {
+			const double s_up0 = s_up, s_lo0 = s_lo, gfac = (3.0 - sqrt(5.0)) / 2.0;
+			double m1 = s_lo + gfac * (s_up - s_lo), m2 = s_lo + (1 - gfac) * (s_up - s_lo);
+			double q1 = QF(m1), q2 = QF(m2);
+			int k = 0;
+			while ((s_up - s_lo) >= 1e-2 * s_up && k < 8) {
+				k++;
+				if (q1 > q2) { s_lo = m1; q_lo = q1; m1 = m2; q1 = q2; m2 = s_lo + (1 - gfac) * (s_up - s_lo); q2 = QF(m2); }
+				else { s_up = m2; q_up = q2; m2 = m1; q2 = q1; m1 = s_lo + gfac * (s_up - s_lo); q1 = QF(m1); }
+			}
+			double q;
+			if (q1 < q2) { sigma = m1; q = q1; } else { sigma = m2; q = q2; }
+			if (s_up == s_up0) { double qt = q_up; if (qt < 0) qt = QF(s_up); if (qt < q) { sigma = s_up; q = qt; } }
+			else if (s_lo == s_lo0) { double qt = q_lo; if (qt < 0) qt = QF(s_lo); if (qt < q) { sigma = s_lo; q = qt; } }
+		}
+#undef QF
+		mu = fmax(fmin(fmax(sigma * avrg_compl, mu_min), mu_max), mu_min);
+		sigma = mu / avrg_compl;
+		nfilter = 0;
+	}
+	/* ---- search direction aff + sigma cen; fraction to the boundary; barrier objective and its directional derivative */
+	/* v: 0 dnorm (max) 1 alpha_max (min) 2 alpha_du (min) 3 phi0 (sum) 4 gBD (sum) */
+	double v[5] = {0.0, 1.0, 1.0, 0.0, 0.0};
+	for (int i = tid; i < T.npad; i += blockDim.x) { const double d = adx[i] + sigma * cdx[i]; b[i] = d; v[0] = fmax(v[0], fabs(d)); }
+	for (int i = tid; i < T.m; i += blockDim.x) {
+		const int fl = T.row_flags[i];
+		if (fl & ROW_EQ) continue;
+		const double d = ads[i] + sigma * cds[i];
+		v[0] = fmax(v[0], fabs(d));
+		if (fl & ROW_HASL) {
+			const double sl = s[i] - dLb[i], u = advL[i] + sigma * cdvL[i];
+			if (d < 0) v[1] = fmin(v[1], -tau * sl / d);
+			if (u < 0) v[2] = fmin(v[2], -tau * vL[i] / u);
+			v[3] -= mu * log(sl); v[4] -= mu * d / sl;
+		}
+		if (fl & ROW_HASU) {
+			const double su = dUb[i] - s[i], u = advU[i] + sigma * cdvU[i];
+			if (-d < 0) v[1] = fmin(v[1], -tau * su / -d);
+			if (u < 0) v[2] = fmin(v[2], -tau * vU[i] / u);
+			v[3] -= mu * log(su); v[4] += mu * d / su;
+		}
+	}
+	{ const int ops[5] = {1, 2, 2, 0, 0}; block_reduce<5>(v, ops, red); }
+	const double dnorm = v[0], alpha_max = v[1], alpha_du = v[2], phi0 = v[3], gBD = v[4];
+	/* ---- filter line search (BacktrackingLineSearch + FilterLSAcceptor) */
+	if (theta_max < 0.0) { theta_max = 1e4 * fmax(1.0, theta); theta_min = 1e-4 * fmax(1.0, theta); }
+	double alpha_min = 1e-5;
+	if (gBD < 0) {
+		alpha_min = fmin(1e-5, 1e-8 * theta / (-gBD));
+		if (theta <= theta_min) alpha_min = fmin(alpha_min, pow(theta, 1.1) / pow(-gBD, 2.3));
+	}
+	alpha_min *= 0.05;
+	const double eps10 = 10.0 * IP_EPS;
+	const int hid = probs[pid].hf_id >= 0 && probs[pid].hf_id < n_hf ? probs[pid].hf_id : 0;
+	const DevHeightfield hf = hfs[hid];
+	double alpha = alpha_max, th_t = 0.0, ph_t = 0.0;
+	bool accepted = false;
+	int ls = 0;
+	while (alpha > alpha_min || ls == 0) {
+		ls++;
+		for (int i = tid; i < T.n_all; i += blockDim.x) {
+			const int p = T.perm_of_var[i];
+			xt[i] = p >= 0 ? x[i] + alpha * b[p] : x[i];
+		}
+		__syncthreads();
+		eval_g_block(T, hf, xt, rt);
+		__syncthreads();
+		double u[2] = {0.0, 0.0};
+		for (int i = tid; i < T.m; i += blockDim.x) {
+			const int fl = T.row_flags[i];
+			const double g = rt[i];
+			if (fl & ROW_EQ) { const double c = sc[i] * (g - T.gl[i]); rt[i] = c; u[0] += fabs(c); continue; }
+			const double d = sc[i] * g, sn = s[i] + alpha * (ads[i] + sigma * cds[i]);
+			rt[i] = d; st[i] = sn;
+			u[0] += fabs(d - sn);
+			if (fl & ROW_HASL) u[1] -= mu * log(sn - dLb[i]);
+			if (fl & ROW_HASU) u[1] -= mu * log(dUb[i] - sn);
+		}
+		{ const int ops[2] = {0, 0}; block_reduce<2>(u, ops, red); }
+		th_t = u[0]; ph_t = u[1];
+		bool ok = false;
+		if (th_t <= theta_max && ph_t == ph_t && fabs(ph_t) < 1e300) {
+			const bool switching = gBD < 0 && alpha * pow(-gBD, 2.3) > pow(theta, 1.1);
+			if (theta <= theta_min && switching) ok = ph_t - phi0 - 1e-8 * alpha * gBD <= eps10 * fabs(phi0);
+			else {
+				ok = th_t - (1 - 1e-5) * theta <= eps10 * fabs(theta) || ph_t - phi0 + 1e-8 * theta <= eps10 * fabs(phi0);
+				if (ok && ph_t > phi0) {                         /* obj_max_inc 5 */
+					const double bas = fabs(phi0) > 10.0 ? log10(fabs(phi0)) : 1.0;
+					ok = log10(ph_t - phi0) <= 5.0 + bas;
+				}
+			}
+			if (ok) for (int k = 0; k < nfilter; ++k) if (!(ph_t <= sfphi[k] || th_t <= sfth[k])) { ok = false; break; }
+		}
+		if (ok) { accepted = true; break; }
+		alpha *= 0.5;
+	}
+	if (!accepted) {                                              /* Ipopt would enter the restoration phase here */
+		if (tid == 0) { W.status[pid] = QTOS_STEP_FAILED; atomicSub(W.n_running, 1); ip[IP_LS] = ls; }
+		return;
+	}
+	const bool switching = gBD < 0 && alpha * pow(-gBD, 2.3) > pow(theta, 1.1);
+	const bool armijo = ph_t - phi0 - 1e-8 * alpha * gBD <= eps10 * fabs(phi0);
+	const bool ftype = switching && armijo;
+	/* ---- accept the trial point */
+	for (int i = tid; i < T.n_all; i += blockDim.x) x[i] = xt[i];
+	double cs[1] = {0.0};
+	for (int i = tid; i < T.m; i += blockDim.x) {
+		const int fl = T.row_flags[i];
+		r[i] = rt[i];
+		y[i] += alpha * (ady[i] + sigma * cdy[i]);
+		if (fl & ROW_EQ) continue;
+		s[i] = st[i];
+		if (fl & ROW_HASL) { const double nv = vL[i] + alpha_du * (advL[i] + sigma * cdvL[i]); vL[i] = nv; cs[0] += (st[i] - dLb[i]) * nv; }
+		if (fl & ROW_HASU) { const double nv = vU[i] + alpha_du * (advU[i] + sigma * cdvU[i]); vU[i] = nv; cs[0] += (dUb[i] - st[i]) * nv; }
+	}
+	{ const int ops[1] = {0}; block_reduce<1>(cs, ops, red); }
+	/* IpoptAlgorithm::correct_bound_multiplier (kappa_sigma 1e10): free mode uses the trial average complementarity */
+	const double mu_c = free_mode ? fmin(cs[0] / (double)(T.n_bounds > 0 ? T.n_bounds : 1), 1e3) : mu;
+	for (int i = tid; i < T.m; i += blockDim.x) {
+		const int fl = T.row_flags[i];
+		if (fl & ROW_HASL) { const double sl = s[i] - dLb[i]; vL[i] = fmin(fmax(vL[i], mu_c / (1e10 * sl)), 1e10 * mu_c / sl); }
+		if (fl & ROW_HASU) { const double su = dUb[i] - s[i]; vU[i] = fmin(fmax(vU[i], mu_c / (1e10 * su)), 1e10 * mu_c / su); }
+	}
+	__syncthreads();
+	/* J(x_k)' lambda_{k+1} for the next limited-memory pair (the Jacobian values are still those of x_k) */
+	double *gJold = WS(gJold, T.npad);
+	for (int i = tid; i < T.npad; i += blockDim.x) gJold[i] = jt_gather(T, Jv, y, i);
+	if (tid == 0) {
+		if (!ftype) {
+			if (nfilter == IP_FILTER_MAX) { for (int k = 1; k < IP_FILTER_MAX; ++k) { ip[IP_FPHI + k - 1] = sfphi[k]; ip[IP_FTH + k - 1] = sfth[k]; } nfilter--; }
+			ip[IP_FPHI + nfilter] = phi0 - 1e-8 * theta; ip[IP_FTH + nfilter] = (1 - 1e-5) * theta; nfilter++;
+		}
+		ip[IP_NFILTER] = nfilter; ip[IP_MU] = mu; ip[IP_TAU] = tau; ip[IP_TH_MAX] = theta_max; ip[IP_TH_MIN] = theta_min;
+		ip[IP_ALPHA_PR] = alpha; ip[IP_ALPHA_DU] = alpha_du; ip[IP_DNORM] = dnorm; ip[IP_LS] = ls; ip[IP_TAG] = ftype ? 'f' : 'h';
+	}
+}
+
+#endif

@@ -128,8 +128,13 @@ scaling:
 		if (fl & ROW_EQ) { r[i] = sc[i] * (g - T.gl[i]); continue; }
 		r[i] = sc[i] * g;
 		double v = r[i], lo = 0, hi = 0;
-		if (fl & ROW_HASL) { const double b = sc[i] * T.gl[i]; lo = b - 1e-8 * fmax(1.0, fabs(b)); dL[i] = lo; zL[i] = 1.0; }
-		if (fl & ROW_HASU) { const double b = sc[i] * T.gu[i]; hi = b + 1e-8 * fmax(1.0, fabs(b)); dU[i] = hi; zU[i] = 1.0; }
+		if (opt.algorithm == QTOS_ALG_IPOPT) {            /* bound_relax_factor acts on the unscaled bound */
+			if (fl & ROW_HASL) { lo = sc[i] * (T.gl[i] - 1e-8 * fmax(1.0, fabs(T.gl[i]))); dL[i] = lo; zL[i] = 1.0; }
+			if (fl & ROW_HASU) { hi = sc[i] * (T.gu[i] + 1e-8 * fmax(1.0, fabs(T.gu[i]))); dU[i] = hi; zU[i] = 1.0; }
+		} else {
+			if (fl & ROW_HASL) { const double b = sc[i] * T.gl[i]; lo = b - 1e-8 * fmax(1.0, fabs(b)); dL[i] = lo; zL[i] = 1.0; }
+			if (fl & ROW_HASU) { const double b = sc[i] * T.gu[i]; hi = b + 1e-8 * fmax(1.0, fabs(b)); dU[i] = hi; zU[i] = 1.0; }
+		}
 		if (fl & ROW_HASL) {
 			double push = 0.01 * fmax(1.0, fabs(lo));
 			if (fl & ROW_HASU) push = fmin(push, 0.01 * (hi - lo));
@@ -145,6 +150,13 @@ scaling:
 	if (threadIdx.x == 0) {
 		double *scal = WS(scal, 16);
 		scal[SC_MU] = opt.mu_init; scal[SC_NU] = 1.0; scal[SC_NFAIL] = 0.0;
+	}
+	if (opt.algorithm == QTOS_ALG_IPOPT) {
+		/* AdaptiveMuUpdate::InitializeImpl, LimMemQuasiNewtonUpdater (limited_memory_init_val 1), empty filters */
+		double *ip = WS(ipst, IP_N), *tr = WS(trace, QTOS_TRACE_ITERS * QTOS_TRACE_COLS);
+		for (int i = threadIdx.x; i < IP_N; i += blockDim.x)
+			ip[i] = i == IP_MU || i == IP_FREE || i == IP_SIGMA_W ? 1.0 : (i == IP_MU_MAX || i == IP_TH_MAX || i == IP_TH_MIN ? -1.0 : (i == IP_AMU_THMIN ? 1e300 : 0.0));
+		for (int i = threadIdx.x; i < QTOS_TRACE_ITERS * QTOS_TRACE_COLS; i += blockDim.x) tr[i] = 0.0;
 	}
 }
 
@@ -413,7 +425,7 @@ k_asm(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 	if (tid < 16) {
 		const int i = I * 16 + tid;
 		double *d = rp + tid * rp_ld + (wI - 1) * 16 + tid;
-		*d = i < T.n_free ? *d + opt.sigma_w : 1.0;
+		*d = i < T.n_free ? *d + (opt.algorithm == QTOS_ALG_IPOPT ? W.ipst[(size_t)pid * IP_N + IP_SIGMA_F] : opt.sigma_w) : 1.0;
 	}
 	__syncthreads();
 	double2 *out = reinterpret_cast<double2 *>(WS(M, T.nM) + (size_t)T.blkptr[I] * 256);
@@ -454,10 +466,14 @@ __device__ __forceinline__ void diag_done_wait() { asm volatile("bar.sync 3, 160
  *                 z_I = inv(L[I,I]) p
  * Row I+1 needs inv(L[I,I]) and z_I only for its LAST off-diagonal block, so the serial 16x16 factorization -- a third
  * of the kernel's critical path when it sat between barriers of all warps -- runs under the sweep of the next row.
- * Then the backward substitution over the finished factor -> dx (tile warps). */
-template <int nbuf>
+ * Then the backward substitution over the finished factor -> dx (tile warps).
+ * IPM = 1 (QTOS_ALG_IPOPT): instead of one right-hand side carried through the sweep and the backward substitution, the
+ * IP_NRHS right-hand sides of W.RB (limited-memory columns, affine and centering directions) are forward-substituted as ONE
+ * MORE BLOCK ROW of the factorization: with RB' (16 x n) appended below A, row nb of L is (L^-1 RB)' -- the same two DMMA
+ * products per block as every other row, A operand from a shared-memory ring of the row's last max_w blocks. */
+template <int nbuf, int IPM>
 __global__ void __launch_bounds__(FTT, FACTOR_MINB)
-k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
+k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld, int max_w)
 {
 	const int pid = blockIdx.x;
 	if (W.status[pid] != QTOS_RUNNING) return;
@@ -473,7 +489,9 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	__shared__ int bad;
 	if (tid == 0) bad = 0;
-	for (int i = tid; i < T.npad; i += FTT) zs[i] = W.vec[(size_t)pid * T.npad + i];
+	if (!IPM) for (int i = tid; i < T.npad; i += FTT) zs[i] = W.vec[(size_t)pid * T.npad + i];
+	else for (int i = tid; i < T.npad; i += FTT) zs[i] = 0.0;
+	if (IPM && tid < 32) pp[tid] = 0.0;
 	__syncthreads();
 	if (warp == 4) {
 		/* ---------------- diagonal warp ---------------- */
@@ -622,6 +640,47 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld)
 			}
 		}
 		diag_done_wait();                              /* last diagonal block */
+		if (IPM) {
+			/* ---- block row nb: Pt[J] = (RB[J]' - sum_K Pt[K] L[J,K]') inv(L[J,J])', Pt[J] = 16 right-hand sides x 16 variables.
+			 *      Block K of the row lives in ring slot K % max_w of panel buffer 0 (step J reads K in [fb[J], J), fewer than
+			 *      max_w blocks, and writes J last); the finished block also goes to W.PB, plain [J][rhs][variable] ---- */
+			const double *RB = WS(RB, T.npad * IP_NRHS);
+			double *PB = WS(PB, T.npad * IP_NRHS);
+			double *rp = rp0;
+			const int row = tm * 8 + fr, col = tn * 8 + 2 * fc;
+			const int cp = SWZ(tn * 4 + fc, fr);
+			for (int J = 0; J < T.nb; ++J) {
+				const int K0 = T.fb[J], nK = J - K0;
+				const double2 *bi = reinterpret_cast<const double2 *>(Dinv + (size_t)J * 256 + tn * 128) + lane;
+				const double2 i01 = bi[0], i23 = bi[32];
+				const double2 cA = *reinterpret_cast<const double2 *>(RB + (size_t)(J * 16 + row) * 16 + col);
+				tile_sync();                           /* block J-1 of the row is in the ring */
+				double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0, c4 = 0.0, c5 = 0.0, c6 = 0.0, c7 = 0.0;
+				const double2 *a = reinterpret_cast<const double2 *>(rp + row * rp_ld + 4 * fc);
+				const double2 *a_lo = a + odd, *a_hi = a + (odd ^ 1);
+				const double2 *b = reinterpret_cast<const double2 *>(M + (size_t)T.blkptr[J] * 256 + tn * 128) + lane;
+				int slot = K0 % max_w;
+				for (int K = 0; K < nK; ++K) {
+					const double2 b01 = b[K * 128], b23 = b[K * 128 + 32];
+					const double2 a01 = a_lo[slot * 8], a23 = a_hi[slot * 8];
+					dmma(c0, c1, a01.x, b01.x); dmma(c2, c3, a01.y, b01.y);
+					dmma(c4, c5, a23.x, b23.x); dmma(c6, c7, a23.y, b23.y);
+					if (++slot == max_w) slot = 0;
+				}
+				c0 = (c0 + c2) + (c4 + c6); c1 = (c1 + c3) + (c5 + c7);
+				reinterpret_cast<double2 *>(tmp + row * TLT)[cp] = make_double2(cA.x - c0, cA.y - c1);
+				tile_sync();
+				const double2 *ta = reinterpret_cast<const double2 *>(tmp + row * TLT + 4 * fc);
+				const double2 t01 = ta[odd], t23 = ta[odd ^ 1];
+				double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+				dmma(x0, x1, t01.x, i01.x); dmma(x2, x3, t01.y, i01.y); dmma(x0, x1, t23.x, i23.x); dmma(x2, x3, t23.y, i23.y);
+				const double2 pj = make_double2(x0 + x2, x1 + x3);
+				reinterpret_cast<double2 *>(rp + row * rp_ld + (J % max_w) * 16)[cp] = pj;
+				*reinterpret_cast<double2 *>(PB + (size_t)(J * 16 + row) * 16 + col) = pj;
+			}
+			if (tid == 0 && bad) W.flags[pid] |= 1;
+			return;
+		}
 		/* ---- backward substitution: L' x = z.  The factor left L2 long ago (888 resident problems x 0.5 MB), so row I-1
 		 *      (inv(L_II) and its off-diagonal blocks, fragment-major, <= max_w blocks = one panel buffer) is copied
 		 *      asynchronously into the idle panel buffers while row I is solved ---- */
@@ -902,4 +961,5 @@ __global__ void k_fp64_peak(double *out, int iters)
 	out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+#include "qtos_ipopt.cuh"
 #include "qtos_capi.inc"
