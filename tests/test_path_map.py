@@ -64,7 +64,7 @@ def test_edge_cases():
 
 @pytest.mark.gpu
 def test_path_map_batch_matches_one_by_one_cli_semantics(oracle):
-    """exp_3 world map: the whole probe queue as ONE batch.  Each probe's status equals what the oracle IPM returns
+    """exp_3 world map: the whole probe queue as ONE batch.  Each probe's status equals what the oracle (Ipopt algorithm, oracle/towr_ipopt.c) returns
     for the same flags (the `returncode == 0` test of worker_f), and bool_map is the FIFO marking of those."""
     from conftest import oracle_problem
     m, shift = GOLD["exp_3_map"], int(GOLD["exp_3_shift"])
@@ -76,7 +76,7 @@ def test_path_map_batch_matches_one_by_one_cli_semantics(oracle):
     so = oracle.default_shape("Custom", 5.0)
     p = PM.probe_problems(pm.probes, 0)
     for k in range(0, len(p), 6):
-        xo, ro = oracle_problem(oracle, so, p[k], grid, 0.1).solve()
+        xo, ro = oracle_problem(oracle, so, p[k], grid, 0.1).solve_ipopt()
         assert (ro.status == 0) == bool(pm.feasible[k]), k
     assert np.array_equal(pm.bool_map, PM.mark(m.shape, pm.probes, pm.feasible, PM.diamond(1)))
     print("exp_3 probes:", len(pm.feasible), "feasible:", int(pm.feasible.sum()), "marked cells:", int(pm.bool_map.sum()))
@@ -87,7 +87,7 @@ def test_path_map_batch_matches_one_by_one_cli_semantics(oracle):
     p2 = PM.probe_problems(pm2.probes, 0)
     assert len(p2) > 0
     for k in range(len(p2)):
-        xo, ro = oracle_problem(oracle, so, p2[k], grid2, 0.1).solve()
+        xo, ro = oracle_problem(oracle, so, p2[k], grid2, 0.1).solve_ipopt()
         assert (ro.status == 0) == bool(pm2.feasible[k]), k
     assert np.array_equal(pm2.bool_map, PM.mark(m2.shape, pm2.probes, pm2.feasible, PM.diamond(1)))
     print("bump map probes:", len(p2), "feasible:", int(pm2.feasible.sum()), "marked cells:", int(pm2.bool_map.sum()))
