@@ -75,11 +75,12 @@ typedef struct {
 	int    max_iter;                  /* 200 (ref: main.cpp:461) */
 	double mu_init;                   /* 0.1 */
 	double sigma_w;                   /* Hessian model sigma_w * I */
-	double delta_c;                   /* equality-block regularisation */
+	double delta_c;                   /* equality-block penalty 1/delta_c of the condensed system; 0 = the algorithm's default
+	                                     (IPOPT 1e-6 with n_refine multiplier passes, FAST 1e-5) */
 	int    feas_exit;                 /* FAST only. 1: f == 0 on this path, so any point with violation <= constr_viol_tol is
 	                                     optimal with zero multipliers and terminates the solve (default) */
 	int    algorithm;                 /* QTOS_ALG_IPOPT (default) or QTOS_ALG_FAST */
-	int    n_refine;                  /* IPOPT: multiplier-method passes on the equality block per direction (2) */
+	int    n_refine;                  /* IPOPT: multiplier-method passes on the equality block per direction (1) */
 	int    lm_history;                /* IPOPT: limited_memory_max_history (6, the maximum) */
 } qtos_options;
 

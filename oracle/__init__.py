@@ -70,7 +70,7 @@ class IpoptResult(C.Structure):
                 ("tr_inf_pr", C.c_double * 256), ("tr_inf_du", C.c_double * 256), ("tr_mu", C.c_double * 256),
                 ("tr_dnorm", C.c_double * 256), ("tr_alpha_pr", C.c_double * 256), ("tr_alpha_du", C.c_double * 256),
                 ("tr_ls", C.c_int * 256), ("tr_pairs", C.c_int * 256), ("tr_free", C.c_int * 256),
-                ("tr_tag", C.c_char * 256), ("chol_fix", C.c_int)]
+                ("tr_tag", C.c_char * 256), ("chol_fix", C.c_int), ("n_regularized", C.c_int)]
 
 
 def build(force=False):

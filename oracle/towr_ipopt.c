@@ -39,7 +39,7 @@ void orc_ipopt_default_options(orc_ipopt_options *o)
 {
 	o->tol = 1e-3; o->constr_viol_tol = 1e-4; o->compl_inf_tol = 1e-4; o->dual_inf_tol = 1.0;
 	o->max_iter = 200;
-	o->delta_c = 1e-5; o->n_refine = 2;
+	o->delta_c = 1e-6; o->n_refine = 1;
 	o->lm_history = 6;
 	o->sigma_floor = 0.0;
 	o->verbose = 0;
@@ -234,6 +234,7 @@ int orc_ipopt_solve(orc_problem *p, const orc_ipopt_options *o, double *x, orc_i
 	double fphi[ORC_FILTER_MAX], fth[ORC_FILTER_MAX]; int nfilter = 0;   /* line-search filter */
 	double theta_max = -1.0, theta_min = -1.0;
 	int status = -1, it = 0, ls_count = 0;
+	double delta_w_last = 0.0;
 	double alpha_pr = 0, alpha_du = 0, dnorm = 0;
 	char tag = ' ';
 	const double eps10 = 10.0 * 2.220446049250313e-16;
@@ -289,51 +290,6 @@ int orc_ipopt_solve(orc_problem *p, const orc_ipopt_options *o, double *x, orc_i
 		if (nlp_error <= o->tol && dual_inf <= o->dual_inf_tol && viol <= o->constr_viol_tol && compl <= o->compl_inf_tol) { status = 0; break; }
 		if (it >= o->max_iter) { status = -1; break; }
 
-		/* ---- factor M = sigma_w I + Jd' Sigma Jd + rho Jc' Jc, Z = M^-1 Bl, C = Mid - Bl' Z */
-		for (int i = 0; i < m; ++i) {
-			if (iseq[i]) { Sig[i] = K.rho; continue; }
-			Sig[i] = (hasL[i] ? vL[i] / sL[i] : 0.0) + (hasU[i] ? vU[i] / sU[i] : 0.0);
-		}
-		memset(M, 0, sizeof(double) * S->skyptr[n]);
-		const double sigma_f = dmax(sigma_w, o->sigma_floor);
-		for (int i = 0; i < n; ++i) M[S->skyptr[i] + i - S->first[i]] = sigma_f;
-		for (int i = 0; i < m; ++i) {
-			const double D = Sig[i];
-			for (int a = S->rowptr[i]; a < S->rowptr[i + 1]; ++a) {
-				const int pa = S->iperm[S->col[a]]; const double va = jv[a];
-				if (va == 0.0) continue;
-				for (int b = S->rowptr[i]; b < S->rowptr[i + 1]; ++b) {
-					const int pb = S->iperm[S->col[b]];
-					if (pb <= pa) M[S->skyptr[pa] + pb - S->first[pa]] += D * va * jv[b];
-				}
-			}
-		}
-		if (orc_sky_chol(S, M)) res->chol_fix++;
-		K.nlr = 2 * n_pairs;
-		if (n_pairs) {
-			double Mid[4 * LM_MAX * LM_MAX];
-			const int q = 2 * n_pairs;
-			for (int a = 0; a < n_pairs; ++a) for (int i = 0; i < n; ++i) { Bl[(size_t)a * n + i] = sigma_f * Sm[(size_t)a * n + i]; Bl[(size_t)(n_pairs + a) * n + i] = Ym[(size_t)a * n + i]; }
-			for (int a = 0; a < n_pairs; ++a) for (int b = 0; b < n_pairs; ++b) {
-				double ss = 0, sy = 0;
-				for (int i = 0; i < n; ++i) { ss += Sm[(size_t)a * n + i] * Sm[(size_t)b * n + i]; sy += Sm[(size_t)a * n + i] * Ym[(size_t)b * n + i]; }
-				Mid[a * q + b] = sigma_f * ss;
-				Mid[a * q + n_pairs + b] = a > b ? sy : 0.0;             /* L: strictly lower part of S'Y */
-				Mid[(n_pairs + b) * q + a] = a > b ? sy : 0.0;           /* L' */
-				Mid[(n_pairs + a) * q + n_pairs + b] = a == b ? -sy : 0.0;   /* -D */
-			}
-			for (int a = 0; a < q; ++a) {
-				for (int i = 0; i < n; ++i) Z[(size_t)a * n + S->iperm[i]] = Bl[(size_t)a * n + i];
-				orc_sky_fwd(S, M, Z + (size_t)a * n);                 /* Q = L^-1 Bl */
-			}
-			for (int a = 0; a < q; ++a) for (int b = 0; b < q; ++b) {
-				double t = 0; for (int i = 0; i < n; ++i) t += Z[(size_t)a * n + i] * Z[(size_t)b * n + i];
-				K.Clu[a * q + b] = Mid[a * q + b] - t;
-			}
-			if (getenv("ORC_DEBUG_LM")) { printf("  Mid:"); for (int a = 0; a < q * q; ++a) printf(" %.6e", Mid[a]); printf("\n  C:"); for (int a = 0; a < q * q; ++a) printf(" %.6e", K.Clu[a]); printf("\n"); }
-			if (!lu_factor(q, K.Clu, K.Cpiv)) { K.nlr = 0; n_pairs = 0; sigma_w = 1.0; }
-		}
-
 		/* ---- barrier parameter (AdaptiveMuUpdate::UpdateBarrierParameter) */
 		if (mu_max < 0) mu_max = 1e3 * avrg_compl;
 		const int acceptable = theta <= amu_theta_min;
@@ -359,17 +315,80 @@ int orc_ipopt_solve(orc_problem *p, const orc_ipopt_options *o, double *x, orc_i
 			if (mg > 0.0 && theta - mg < amu_theta_min) amu_theta_min = theta - mg;
 		}
 
-		/* ---- affine-scaling and centering directions (two right-hand sides of one factorization) */
-		for (int i = 0; i < n; ++i) vtmp[i] = -glx[i];
-		for (int i = 0; i < m; ++i) {
-			if (iseq[i]) { rcd[i] = -r[i]; rs[i] = rvL[i] = rvU[i] = 0.0; continue; }
-			rcd[i] = -(r[i] - s[i]);
-			rs[i] = -(-y[i] - vL[i] + vU[i]);
-			rvL[i] = hasL[i] ? -sL[i] * vL[i] : 0.0; rvU[i] = hasU[i] ? -sU[i] * vU[i] : 0.0;
+		/* ---- factorization and the two directions; a non-positive pivot or a non-finite direction repeats them with
+		 *      W + delta_w I (PDPerturbationHandler: 1e-4 the first time, a third of the last successful value later, then
+		 *      x100 / x8, give up beyond 1e40) */
+		const double sigma_f = dmax(sigma_w, o->sigma_floor);
+		double delta_w = 0.0;
+		int gave_up = 0;
+		for (;;) {
+			/* ---- factor M = (sigma_w + delta_w) I + Jd' Sigma Jd + rho Jc' Jc, Q = L^-1 Bl, C = Mid - Q'Q */
+			for (int i = 0; i < m; ++i) {
+				if (iseq[i]) { Sig[i] = K.rho; continue; }
+				Sig[i] = (hasL[i] ? vL[i] / sL[i] : 0.0) + (hasU[i] ? vU[i] / sU[i] : 0.0);
+			}
+			memset(M, 0, sizeof(double) * S->skyptr[n]);
+			for (int i = 0; i < n; ++i) M[S->skyptr[i] + i - S->first[i]] = sigma_f + delta_w;
+			for (int i = 0; i < m; ++i) {
+				const double D = Sig[i];
+				for (int a = S->rowptr[i]; a < S->rowptr[i + 1]; ++a) {
+					const int pa = S->iperm[S->col[a]]; const double va = jv[a];
+					if (va == 0.0) continue;
+					for (int b = S->rowptr[i]; b < S->rowptr[i + 1]; ++b) {
+						const int pb = S->iperm[S->col[b]];
+						if (pb <= pa) M[S->skyptr[pa] + pb - S->first[pa]] += D * va * jv[b];
+					}
+				}
+			}
+			const int bad_pivot = orc_sky_chol(S, M);
+			if (bad_pivot) res->chol_fix++;
+			K.nlr = 2 * n_pairs;
+			if (n_pairs) {
+				double Mid[4 * LM_MAX * LM_MAX];
+				const int q = 2 * n_pairs;
+				for (int a = 0; a < n_pairs; ++a) for (int i = 0; i < n; ++i) { Bl[(size_t)a * n + i] = sigma_f * Sm[(size_t)a * n + i]; Bl[(size_t)(n_pairs + a) * n + i] = Ym[(size_t)a * n + i]; }
+				for (int a = 0; a < n_pairs; ++a) for (int b = 0; b < n_pairs; ++b) {
+					double ss = 0, sy = 0;
+					for (int i = 0; i < n; ++i) { ss += Sm[(size_t)a * n + i] * Sm[(size_t)b * n + i]; sy += Sm[(size_t)a * n + i] * Ym[(size_t)b * n + i]; }
+					Mid[a * q + b] = sigma_f * ss;
+					Mid[a * q + n_pairs + b] = a > b ? sy : 0.0;             /* L: strictly lower part of S'Y */
+					Mid[(n_pairs + b) * q + a] = a > b ? sy : 0.0;           /* L' */
+					Mid[(n_pairs + a) * q + n_pairs + b] = a == b ? -sy : 0.0;   /* -D */
+				}
+				for (int a = 0; a < q; ++a) {
+					for (int i = 0; i < n; ++i) Z[(size_t)a * n + S->iperm[i]] = Bl[(size_t)a * n + i];
+					orc_sky_fwd(S, M, Z + (size_t)a * n);                 /* Q = L^-1 Bl */
+				}
+				for (int a = 0; a < q; ++a) for (int b = 0; b < q; ++b) {
+					double t = 0; for (int i = 0; i < n; ++i) t += Z[(size_t)a * n + i] * Z[(size_t)b * n + i];
+					K.Clu[a * q + b] = Mid[a * q + b] - t;
+				}
+				if (getenv("ORC_DEBUG_LM")) { printf("  Mid:"); for (int a = 0; a < q * q; ++a) printf(" %.6e", Mid[a]); printf("\n  C:"); for (int a = 0; a < q * q; ++a) printf(" %.6e", K.Clu[a]); printf("\n"); }
+				if (!lu_factor(q, K.Clu, K.Cpiv)) { K.nlr = 0; n_pairs = 0; sigma_w = 1.0; }
+			}
+
+			/* ---- affine-scaling and centering directions (two right-hand sides of one factorization) */
+			for (int i = 0; i < n; ++i) vtmp[i] = -glx[i];
+			for (int i = 0; i < m; ++i) {
+				if (iseq[i]) { rcd[i] = -r[i]; rs[i] = rvL[i] = rvU[i] = 0.0; continue; }
+				rcd[i] = -(r[i] - s[i]);
+				rs[i] = -(-y[i] - vL[i] + vU[i]);
+				rvL[i] = hasL[i] ? -sL[i] * vL[i] : 0.0; rvU[i] = hasU[i] ? -sU[i] * vU[i] : 0.0;
+			}
+			kkt_solve(&K, vtmp, rs, rcd, rvL, rvU, Sig, sL, sU, vL, vU, a_dx, a_ds, a_dy, a_dvL, a_dvU, w, xt /* scratch >= n */);
+			for (int i = 0; i < m; ++i) { rcd[i] = rs[i] = 0.0; rvL[i] = hasL[i] ? avrg_compl : 0.0; rvU[i] = hasU[i] ? avrg_compl : 0.0; }
+			kkt_solve(&K, NULL, rs, rcd, rvL, rvU, Sig, sL, sU, vL, vU, c_dx, c_ds, c_dy, c_dvL, c_dvU, w, xt);
+
+			double nf = 0.0;
+			for (int i = 0; i < n; ++i) nf += 0.0 * a_dx[i] + 0.0 * c_dx[i];
+			if (nf == 0.0 && !bad_pivot) break;
+			delta_w = delta_w == 0.0 ? (delta_w_last == 0.0 ? 1e-4 : dmax(1e-20, delta_w_last / 3.0)) : delta_w * (delta_w_last == 0.0 ? 100.0 : 8.0);
+			if (delta_w > 1e40) { gave_up = 1; break; }
+			res->n_regularized++;
+			if (o->verbose) printf("  regularisation: delta_w = %.3e\n", delta_w);
 		}
-		kkt_solve(&K, vtmp, rs, rcd, rvL, rvU, Sig, sL, sU, vL, vU, a_dx, a_ds, a_dy, a_dvL, a_dvU, w, xt /* scratch >= n */);
-		for (int i = 0; i < m; ++i) { rcd[i] = rs[i] = 0.0; rvL[i] = hasL[i] ? avrg_compl : 0.0; rvU[i] = hasU[i] ? avrg_compl : 0.0; }
-		kkt_solve(&K, NULL, rs, rcd, rvL, rvU, Sig, sL, sU, vL, vU, c_dx, c_ds, c_dy, c_dvL, c_dvU, w, xt);
+		if (gave_up) { status = -2; break; }
+		if (delta_w > 0.0) delta_w_last = delta_w;
 
 		double sigma = mu / avrg_compl;
 		if (free_mode) {

@@ -178,6 +178,7 @@ typedef struct {
 	int tr_ls[ORC_TRACE_MAX], tr_pairs[ORC_TRACE_MAX], tr_free[ORC_TRACE_MAX];
 	char tr_tag[ORC_TRACE_MAX];
 	int chol_fix;
+	int n_regularized;        /* factorizations repeated with W + delta_w I */
 } orc_ipopt_result;
 
 void orc_ipopt_default_options(orc_ipopt_options *o);

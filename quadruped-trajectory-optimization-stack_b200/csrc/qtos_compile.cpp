@@ -792,23 +792,36 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 			H->as_ptr.push_back((int)H->as_col.size());
 			H->as_max = std::max(H->as_max, (int)H->as_col.size() - s0);
 		}
-		H->jg_ptr.assign(1, 0); H->jg.clear();
-		for (int g = 0; g * 32 < npad; ++g) {
-			size_t ns = 0;
-			for (int l = 0; l < 32 && g * 32 + l < npad; ++l) ns = std::max(ns, jt[g * 32 + l].size());
-			for (size_t st = 0; st < ns; ++st)
-				for (int l = 0; l < 32; ++l) {
-					const int i = g * 32 + l;
-					uint2_t d; d.x = d.y = 0;
-					if (i < npad && st < jt[i].size()) {
-						const Element &E = H->elems[jt[i][st] >> 8];
-						d.x = (uint32_t)(E.valoff + (int)(jt[i][st] & 255u) * E.ld) | ((uint32_t)E.nrows << 20);
-						d.y = (uint32_t)E.row0;
-					}
-					H->jg.push_back(d);
+		for (int pass = 0; pass < 2; ++pass) {             /* 0: all terms (J' v), 1: elements with equality rows only (Jc' v) */
+			std::vector<int> &ptr = pass ? H->jgc_ptr : H->jg_ptr;
+			std::vector<uint2_t> &tab = pass ? H->jgc : H->jg;
+			ptr.assign(1, 0); tab.clear();
+			std::vector<std::vector<uint32_t>> sel(npad);
+			for (int i = 0; i < npad; ++i)
+				for (uint32_t t : jt[i]) {
+					const Element &E = H->elems[t >> 8];
+					bool has_eq = false;
+					for (int r = 0; r < E.nrows; ++r) has_eq = has_eq || (H->row_flags[E.row0 + r] & ROW_EQ);
+					if (!pass || has_eq) sel[i].push_back(t);
 				}
-			H->jg_ptr.push_back((int)H->jg.size());
+			for (int g = 0; g * 32 < npad; ++g) {
+				size_t ns = 0;
+				for (int l = 0; l < 32 && g * 32 + l < npad; ++l) ns = std::max(ns, sel[g * 32 + l].size());
+				for (size_t st = 0; st < ns; ++st)
+					for (int l = 0; l < 32; ++l) {
+						const int i = g * 32 + l;
+						uint2_t d; d.x = d.y = 0;
+						if (i < npad && st < sel[i].size()) {
+							const Element &E = H->elems[sel[i][st] >> 8];
+							d.x = (uint32_t)(E.valoff + (int)(sel[i][st] & 255u) * E.ld) | ((uint32_t)E.nrows << 20);
+							d.y = (uint32_t)E.row0;
+						}
+						tab.push_back(d);
+					}
+				ptr.push_back((int)tab.size());
+			}
 		}
+		for (int i = 0; i < H->m; ++i) ((H->row_flags[i] & ROW_EQ) ? H->eq_rows : H->iq_rows).push_back((int16_t)i);
 	}
 
 	/* ---- 1 kHz sampler (ref: main.cpp:92-131): t accumulates += 0.001 while t <= T + 1e-4 ---- */

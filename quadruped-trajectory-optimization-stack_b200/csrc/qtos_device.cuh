@@ -40,6 +40,7 @@ struct DevTables {
 	const int *fb, *blkptr, *diag_off;
 	const int *as_ptr, *at_ptr; const AsmCol *as_col; const uint32_t *at;
 	const int *jg_ptr; const uint2_t *jg;
+	const int *jgc_ptr; const uint2_t *jgc; const int16_t *eq_rows, *iq_rows;
 	const double *csv_t, *csv_tl; const uint8_t *csv_id;
 	const double *dur; int dur_ld;          /* [10][dur_ld] */
 	double nominal[QTOS_NEE][3];
@@ -63,6 +64,7 @@ struct DevWork {
 	double *glx, *lastx, *gJold, *adx, *cdx;/* [npad] J'y, previous x, J(x_k)'y_{k+1}, affine / centering dx (permuted order) */
 	double *lmS, *lmY;                      /* [6][npad] limited-memory pairs (ring) */
 	double *RB, *PB;                        /* [nb][16][16] right-hand sides of the factorization's forward substitution, and L^-1 of them */
+	double *G;                              /* [16][16] Gram matrix PB' PB */
 	double *wA, *wC;                        /* [m] first-pass row weights of the affine / centering right-hand side */
 	double *ads, *ady, *advL, *advU, *cds, *cdy, *cdvL, *cdvU;   /* [m] the two directions, row part */
 	double *trace;                          /* [QTOS_TRACE_ITERS][QTOS_TRACE_COLS] */
@@ -71,7 +73,7 @@ struct DevWork {
 /* IPOPT algorithm state per problem (doubles) */
 enum { IP_MU = 0, IP_TAU, IP_FREE, IP_MU_MAX, IP_AMU_THMIN, IP_TH_MAX, IP_TH_MIN, IP_SIGMA_W, IP_NPAIRS, IP_SKIPPED, IP_HAVE_LAST,
        IP_NFILTER, IP_SIGMA_F, IP_AVRG, IP_ERR, IP_THETA, IP_GL2, IP_PR2, IP_ALPHA_PR, IP_ALPHA_DU, IP_DNORM, IP_LS, IP_TAG,
-       IP_HEAD, IP_FPHI = 32, IP_FTH = 64, IP_MID = 96, IP_N = 256 };
+       IP_HEAD, IP_ITER, IP_RETRY, IP_DELTA_W, IP_DELTA_LAST, IP_FPHI = 32, IP_FTH = 64, IP_MID = 96, IP_N = 256 };
 #define IP_FILTER_MAX 32
 #define IP_LM 6                             /* limited-memory history capacity */
 #define IP_NRHS 16                          /* right-hand sides of the factorization: 6 S + 6 Y columns, affine, centering, 2 spare */

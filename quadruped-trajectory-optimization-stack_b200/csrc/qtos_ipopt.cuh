@@ -26,7 +26,7 @@
 /* ------------------------------------------------------------------ kip_prepare */
 
 __global__ void __launch_bounds__(QTOS_THREADS, PREP_MINB)
-kip_prepare(DevTables T, DevWork W, qtos_options opt, int it)
+kip_prepare(DevTables T, DevWork W, qtos_options opt)
 {
 	const int pid = blockIdx.x;
 	if (W.status[pid] != QTOS_RUNNING) return;
@@ -44,7 +44,11 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 	double mu = ip[IP_MU], tau = ip[IP_TAU], sigma_w = ip[IP_SIGMA_W], mu_max = ip[IP_MU_MAX], amu_thmin = ip[IP_AMU_THMIN];
 	int free_mode = (int)ip[IP_FREE], n_pairs = (int)ip[IP_NPAIRS], skipped = (int)ip[IP_SKIPPED], head = (int)ip[IP_HEAD];
 	int nfilter = (int)ip[IP_NFILTER];
-	const int have_last = (int)ip[IP_HAVE_LAST];
+	/* a retry repeats the iteration at the same point with more regularisation on the diagonal (see kip_step): the
+	 * limited-memory update, the termination test and the barrier bookkeeping of this iteration are already done */
+	const int retry = (int)ip[IP_RETRY], it = (int)ip[IP_ITER];
+	const int have_last = retry ? 0 : (int)ip[IP_HAVE_LAST];
+	const double delta_w = retry ? ip[IP_DELTA_W] : 0.0;
 	/* v: 0 dual_inf (max) 1 primal_inf (max) 2 compl (max) 3 sum|y| 4 sum z 5 viol (max) 6 theta (sum) 7 sum s z 8 sum 0*r
 	 *    9 |grad L|^2 10 |c|^2 11 max |s z - mu| 12 s'y 13 s's 14 y'y */
 	double v[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -81,8 +85,8 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 	const double avrg_compl = v[7] / (double)nbnd;
 	const bool invalid = !(v[8] == 0.0) || !(nlp_error == nlp_error) || !(theta == theta);
 	const bool conv = !invalid && nlp_error <= opt.tol && dual_inf <= opt.dual_inf_tol && viol <= opt.constr_viol_tol && compl_ <= opt.compl_inf_tol;
-	const bool stop = invalid || conv || it >= opt.max_iter;
-	if (tid == 0) {
+	const bool stop = !retry && (invalid || conv || it >= opt.max_iter);
+	if (tid == 0 && !retry) {
 		scal[SC_DUAL] = dual_inf; scal[SC_THETA] = primal_inf; scal[SC_COMPL] = compl_; scal[SC_VIOL] = viol; scal[SC_E0] = nlp_error; scal[SC_MU] = mu;
 		W.iters[pid] = it;
 		if (it < QTOS_TRACE_ITERS) {
@@ -114,14 +118,15 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 	if (new_slot >= 0) {
 		for (int i = tid; i < T.npad; i += blockDim.x) { lmS[(size_t)new_slot * T.npad + i] = tS[i]; lmY[(size_t)new_slot * T.npad + i] = tY[i]; }
 	}
-	const double sigma_f = sigma_w;
+	const double sigma_f = sigma_w + delta_w;         /* diagonal of M; the limited-memory columns keep sigma_w (W + delta_w I) */
 
 	/* ---- barrier parameter, part one (AdaptiveMuUpdate::UpdateBarrierParameter): mode switches and the fixed-mode update;
 	 *      the free-mode oracle needs the two directions and runs in kip_step */
 	const double mu_min = fmin(1e-11, 0.5 * fmin(opt.tol, opt.compl_inf_tol));
 	if (mu_max < 0.0) mu_max = 1e3 * avrg_compl;
 	const bool acceptable = theta <= amu_thmin;
-	if (!free_mode) {
+	if (retry) { /* done in the first attempt */ }
+	else if (!free_mode) {
 		if (acceptable) free_mode = 1;
 		else {
 			const double berr = fmax(fmax(dual_inf / s_d, primal_inf), v[11] / s_c);
@@ -136,7 +141,7 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 		mu = fmin(fmax(0.8 * avrg_compl, mu_min), mu_max);
 		tau = fmax(0.99, 1.0 - mu); nfilter = 0;
 	}
-	if (free_mode && acceptable) {                        /* RememberCurrentPointAsAccepted */
+	if (!retry && free_mode && acceptable) {              /* RememberCurrentPointAsAccepted */
 		const double mg = 1e-5 * fmin(1.0, theta);
 		if (mg > 0.0 && theta - mg < amu_thmin) amu_thmin = theta - mg;
 	}
@@ -161,7 +166,7 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 #pragma unroll
 		for (int a = 0; a < IP_LM; ++a) {
 			const int sl = (head + a) % hist;
-			o[a * 16] = a < n_pairs ? sigma_f * lmS[(size_t)sl * T.npad + i] : 0.0;
+			o[a * 16] = a < n_pairs ? sigma_w * lmS[(size_t)sl * T.npad + i] : 0.0;
 			o[(IP_LM + a) * 16] = a < n_pairs ? lmY[(size_t)sl * T.npad + i] : 0.0;
 		}
 		o[12 * 16] = i < T.n_free ? va : 0.0; o[13 * 16] = i < T.n_free ? vc : 0.0; o[14 * 16] = 0.0; o[15 * 16] = 0.0;
@@ -181,7 +186,7 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 		const int a = ra % IP_LM, b = cb % IP_LM;
 		double val = 0.0;
 		if (a < n_pairs && b < n_pairs) {
-			if (ra < IP_LM && cb < IP_LM) val = sigma_f * sdots[a * IP_LM + b];
+			if (ra < IP_LM && cb < IP_LM) val = sigma_w * sdots[a * IP_LM + b];
 			else if (ra < IP_LM) val = a > b ? sdots[IP_LM * IP_LM + a * IP_LM + b] : 0.0;              /* L[a][b] */
 			else if (cb < IP_LM) val = b > a ? sdots[IP_LM * IP_LM + b * IP_LM + a] : 0.0;              /* L'[a][b] = L[b][a] */
 			else val = a == b ? -sdots[IP_LM * IP_LM + a * IP_LM + a] : 0.0;
@@ -193,6 +198,7 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 		ip[IP_SIGMA_W] = sigma_w; ip[IP_SIGMA_F] = sigma_f; ip[IP_NPAIRS] = n_pairs; ip[IP_SKIPPED] = skipped; ip[IP_HEAD] = head;
 		ip[IP_HAVE_LAST] = 1.0; ip[IP_NFILTER] = nfilter; ip[IP_AVRG] = avrg_compl; ip[IP_ERR] = nlp_error; ip[IP_THETA] = theta;
 		ip[IP_GL2] = v[9]; ip[IP_PR2] = v[10];
+		W.flags[pid] = 0;                              /* k_factor reports a non-positive pivot here */
 		W.active[atomicAdd(W.n_active, 1)] = pid;
 	}
 }
@@ -201,7 +207,7 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 
 #define KS_T 128
 #ifndef KS_MINB
-#define KS_MINB 3
+#define KS_MINB 4
 #endif
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
@@ -224,77 +230,107 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 	             :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
+/* The rows of L stream through a shared-memory RING of 2 KB blocks, several rows ahead of the row being solved: the
+ * five (2 n_refine + 1) sweeps of one kernel form ONE fetch sequence (backward, forward, backward, ...), thread 0 keeps
+ * issuing bulk copies while ring space and one of KS_NBAR mbarriers are free, so the prefetch also runs across the
+ * J-products between two sweeps.  A row = inv(L_II) (from Dinv) + its off-diagonal blocks fI..I-1 (contiguous in M),
+ * all fragment-major (see frag_off); a row may wrap around the end of the ring. */
+#define KS_NBAR 8
 struct SweepCtx {
 	const int *fb, *blkptr;
 	int nb, npad;
 	const double *M, *Dinv;
 	double *z;              /* [2][npad] */
-	double *lb;             /* [2][max_w * 256] */
+	double *ring;           /* [rc][256] */
 	double *part;           /* [4][16][2] */
 	double *xi;             /* [2][16] */
-	uint64_t *mbar;         /* [2] */
-	int lbsz;               /* doubles per row buffer */
-	unsigned phase[2];
+	uint64_t *mbar;         /* [KS_NBAR] */
+	int rc, total;          /* ring capacity in blocks; rows of the whole fetch sequence */
+	int p_seq, p_pos, p_free;   /* producer (thread 0) */
+	int c_seq, c_pos;           /* consumer (all threads alike) */
 };
 
-/* row I of L into buffer b: block 0 = inv(L_II), then the off-diagonal blocks fI..I-1, all fragment-major (see frag_off) */
-__device__ __forceinline__ void sweep_fetch(SweepCtx &C, int I, int b)
+__device__ __forceinline__ int sweep_row_of(const SweepCtx &C, int seq)
 {
-	const SweepCtx &T = C;
-	const int nbk = I - T.fb[I];
-	mbar_expect_tx(&C.mbar[b], (unsigned)((nbk + 1) * 2048));
-	bulk_g2s(C.lb + (size_t)b * C.lbsz, C.Dinv + (size_t)I * 256, 2048u, &C.mbar[b]);
-	if (nbk) bulk_g2s(C.lb + (size_t)b * C.lbsz + 256, C.M + (size_t)T.blkptr[I] * 256, (unsigned)(nbk * 2048), &C.mbar[b]);
+	const int sw = seq / C.nb, k = seq - sw * C.nb;
+	return (sw & 1) ? k : C.nb - 1 - k;               /* even sweeps run backward */
+}
+
+/* thread 0: issue the fetches of as many rows as fit */
+__device__ __forceinline__ void sweep_pump(SweepCtx &C)
+{
+	while (C.p_seq < C.total && C.p_seq - C.c_seq < KS_NBAR) {
+		const int row = sweep_row_of(C, C.p_seq), nblk = row - C.fb[row] + 1;
+		if (nblk > C.p_free) break;
+		uint64_t *bar = &C.mbar[C.p_seq % KS_NBAR];
+		mbar_expect_tx(bar, (unsigned)(nblk * 2048));
+		bulk_g2s(C.ring + (size_t)C.p_pos * 256, C.Dinv + (size_t)row * 256, 2048u, bar);
+		const int pos = C.p_pos + 1 == C.rc ? 0 : C.p_pos + 1, n = nblk - 1;
+		const double *src = C.M + (size_t)C.blkptr[row] * 256;
+		const int first = n < C.rc - pos ? n : C.rc - pos;
+		if (first) bulk_g2s(C.ring + (size_t)pos * 256, src, (unsigned)(first * 2048), bar);
+		if (n - first) bulk_g2s(C.ring, src + (size_t)first * 256, (unsigned)((n - first) * 2048), bar);
+		C.p_pos = (C.p_pos + nblk) % C.rc; C.p_free -= nblk; C.p_seq++;
+	}
+}
+
+/* all threads, after the barrier that ends a row: its blocks are free again */
+__device__ __forceinline__ void sweep_release(SweepCtx &C, int nblk)
+{
+	C.c_pos = (C.c_pos + nblk) % C.rc; C.c_seq++;
+	if (threadIdx.x == 0) { C.p_free += nblk; sweep_pump(C); }
+}
+
+__device__ __forceinline__ const double *sweep_blk(const SweepCtx &C, int j)      /* block j of the current row (0 = inverse) */
+{
+	int p = C.c_pos + j; if (p >= C.rc) p -= C.rc;
+	return C.ring + (size_t)p * 256;
 }
 
 /* L' x = z for the two right-hand sides in C.z, in place; all KS_T threads */
 __device__ __forceinline__ void sweep_backward(SweepCtx &C)
 {
-	const SweepCtx &T = C;
-	const int tid = threadIdx.x, npad = T.npad;
-	if (tid == 0) sweep_fetch(C, T.nb - 1, 0);
-	for (int I = T.nb - 1, b = 0; I >= 0; --I, b ^= 1) {
-		if (tid == 0 && I > 0) sweep_fetch(C, I - 1, b ^ 1);       /* that buffer was released by the barrier ending row I+1 */
-		mbar_wait(&C.mbar[b], C.phase[b]); C.phase[b] ^= 1;
-		const double *buf = C.lb + (size_t)b * C.lbsz;
-		const int fI = T.fb[I];
-		if (tid < 32) {
-			const int k = tid >> 4, c = tid & 15;
+	const int tid = threadIdx.x, npad = C.npad;
+	for (int I = C.nb - 1; I >= 0; --I) {
+		mbar_wait(&C.mbar[C.c_seq % KS_NBAR], (unsigned)((C.c_seq / KS_NBAR) & 1));
+		const int fI = C.fb[I];
+		{
+			/* x_I = inv(L_II)' z_I for both right-hand sides: four lanes per entry */
+			const double *inv = sweep_blk(C, 0);
+			const int k = tid >> 6, c = (tid >> 2) & 15, pt = tid & 3;
 			const double *zI = C.z + k * npad + I * 16;
 			double acc = 0.0;
-			for (int q = c; q < 16; ++q) acc += buf[frag_off(q, c)] * zI[q];
-			C.xi[tid] = acc;
+			for (int q = c + pt; q < 16; q += 4) acc += inv[frag_off(q, c)] * zI[q];
+			acc += __shfl_xor_sync(0xffffffffu, acc, 1); acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+			if (pt == 0) C.xi[k * 16 + c] = acc;
 		}
 		__syncthreads();
 		if (tid < 32) C.z[(tid >> 4) * npad + I * 16 + (tid & 15)] = C.xi[tid];
 		for (int c = tid; c < (I - fI) * 16; c += KS_T) {
-			const double *blk = buf + 256 + (c >> 4) * 256 + frag_off(0, c & 15);
+			const double *blk = sweep_blk(C, 1 + (c >> 4)) + frag_off(0, c & 15);
 			double a0 = 0.0, a1 = 0.0;
 #pragma unroll
 			for (int q = 0; q < 16; ++q) { const double l = blk[((q >> 3) << 7) + ((q & 7) << 3)]; a0 += l * C.xi[q]; a1 += l * C.xi[16 + q]; }
 			C.z[fI * 16 + c] -= a0; C.z[npad + fI * 16 + c] -= a1;
 		}
 		__syncthreads();
+		sweep_release(C, I - fI + 1);
 	}
 }
 
 /* L z = v for the two right-hand sides in C.z, in place */
 __device__ __forceinline__ void sweep_forward(SweepCtx &C)
 {
-	const SweepCtx &T = C;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, npad = T.npad;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, npad = C.npad;
 	const int fr = lane >> 2, fc = lane & 3;
-	if (tid == 0) sweep_fetch(C, 0, 0);
-	for (int I = 0, b = 0; I < T.nb; ++I, b ^= 1) {
-		if (tid == 0 && I + 1 < T.nb) sweep_fetch(C, I + 1, b ^ 1);
-		mbar_wait(&C.mbar[b], C.phase[b]); C.phase[b] ^= 1;
-		const double *buf = C.lb + (size_t)b * C.lbsz;
-		const int fI = T.fb[I], nbk = I - fI;
+	for (int I = 0; I < C.nb; ++I) {
+		mbar_wait(&C.mbar[C.c_seq % KS_NBAR], (unsigned)((C.c_seq / KS_NBAR) & 1));
+		const int fI = C.fb[I], nbk = I - fI;
 		/* every warp takes every fourth block of the row; a lane reads its operand-fragment chunks (conflict-free 128-bit
 		 * loads): rows fr and 8 + fr, columns 4 fc + 2 h + {0, 1} */
 		double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};      /* [row half][right-hand side] */
 		for (int jb = warp; jb < nbk; jb += KS_T / 32) {
-			const double2 *blk = reinterpret_cast<const double2 *>(buf + 256 + jb * 256) + lane;
+			const double2 *blk = reinterpret_cast<const double2 *>(sweep_blk(C, 1 + jb)) + lane;
 			const double *z0 = C.z + (fI + jb) * 16 + 4 * fc, *z1 = z0 + npad;
 #pragma unroll
 			for (int h = 0; h < 2; ++h) {
@@ -316,21 +352,25 @@ __device__ __forceinline__ void sweep_forward(SweepCtx &C)
 				if (fc == 0) C.part[(warp * 16 + tn * 8 + fr) * 2 + k] = a;
 			}
 		__syncthreads();
-		if (tid < 32) {
-			const int k = tid >> 4, q = tid & 15;
-			double sacc = 0.0;
-#pragma unroll
-			for (int w = 0; w < KS_T / 32; ++w) sacc += C.part[(w * 16 + q) * 2 + k];
-			C.xi[tid] = C.z[k * npad + I * 16 + q] - sacc;
-		}
-		__syncthreads();
-		if (tid < 32) {
-			const int k = tid >> 4, rr = tid & 15;
+		{
+			/* z_I = inv(L_II) (v_I - L[I,<I] z): four lanes per (right-hand side, row), each rebuilds the entries of the
+			 * reduced right-hand side it needs from the warps' partial sums */
+			const double *inv = sweep_blk(C, 0);
+			const int k = tid >> 6, q = (tid >> 2) & 15, pt = tid & 3;
 			double a = 0.0;
-			for (int q = 0; q <= rr; ++q) a += buf[frag_off(rr, q)] * C.xi[k * 16 + q];
-			C.z[k * npad + I * 16 + rr] = a;
+			for (int j = pt; j <= q; j += 4) {
+				double sv = C.z[k * npad + I * 16 + j];
+#pragma unroll
+				for (int w = 0; w < KS_T / 32; ++w) sv -= C.part[(w * 16 + j) * 2 + k];
+				a += inv[frag_off(q, j)] * sv;
+			}
+			a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
+			C.xi[tid >> 2] = a;                           /* entry (k, q) = index k * 16 + q; the four lanes write the same value */
 		}
 		__syncthreads();
+		if (tid < 32) C.z[(tid >> 4) * npad + I * 16 + (tid & 15)] = C.xi[tid];
+		__syncthreads();
+		sweep_release(C, nbk + 1);
 	}
 }
 
@@ -359,22 +399,63 @@ __device__ inline void lu12_solve(const double *A, const int *piv, double *b)
 	for (int k = n - 1; k >= 0; --k) { for (int j = k + 1; j < n; ++j) b[k] -= A[k * n + j] * b[j]; b[k] /= A[k * n + k]; }
 }
 
+/* (J' wa)_i and (J' wb)_i together for permuted variable i over a term table (see jt_gather): the column is read once */
+__device__ __forceinline__ void jt_gather2(const int *ptr, const uint2_t *tab, const double *Jv, const double *wa, const double *wb, int i, double &ga, double &gb)
+{
+	const int g = i >> 5, base = ptr[g], ns = (ptr[g + 1] - base) >> 5;
+	const uint2 *tk = reinterpret_cast<const uint2 *>(tab) + base + (i & 31);
+	double a0 = 0.0, a1 = 0.0;
+	for (int s = 0; s < ns; s += 2) {
+		uint2 d[2];
+		double c[2][6], u[2][6], w[2][6];
+#pragma unroll
+		for (int q = 0; q < 2; ++q) d[q] = s + q < ns ? __ldg(tk + 32 * (s + q)) : make_uint2(0u, 0u);
+#pragma unroll
+		for (int q = 0; q < 2; ++q) {
+			const int nr = d[q].x >> 20;
+			const double *col = Jv + (d[q].x & 0xfffffu), *pa = wa + d[q].y, *pb = wb + d[q].y;
+#pragma unroll
+			for (int rr = 0; rr < 6; ++rr) { c[q][rr] = rr < nr ? col[rr] : 0.0; u[q][rr] = rr < nr ? pa[rr] : 0.0; w[q][rr] = rr < nr ? pb[rr] : 0.0; }
+		}
+#pragma unroll
+		for (int q = 0; q < 2; ++q)
+#pragma unroll
+			for (int rr = 0; rr < 6; ++rr) { a0 += c[q][rr] * u[q][rr]; a1 += c[q][rr] * w[q][rr]; }
+	}
+	ga = a0; gb = a1;
+}
+
+/* (J z0)_row and (J z1)_row: eight lanes share a row (columns strided), all 32 lanes of the warp call it together */
+__device__ __forceinline__ void row_dot2(const DevTables &T, const double *Jv, const double *z0, const double *z1, int row, bool valid, double &j0, double &j1)
+{
+	double a0 = 0.0, a1 = 0.0;
+	if (valid) {
+		const Element &E = T.elems[T.row_elem[row]];
+		const double *jr = Jv + E.valoff + (row - E.row0);
+		const int16_t *cols = T.elem_cols + E.coloff;
+		for (int a = threadIdx.x & 7; a < E.ncols; a += 8) { const double jv = jr[a * E.ld]; const int c = cols[a]; a0 += jv * z0[c]; a1 += jv * z1[c]; }
+	}
+#pragma unroll
+	for (int o = 1; o < 8; o <<= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+	j0 = a0; j1 = a1;
+}
+
 __global__ void __launch_bounds__(KS_T, KS_MINB)
-kip_solve(DevTables T, DevWork W, qtos_options opt, int max_w)
+kip_solve(DevTables T, DevWork W, qtos_options opt, int rc)
 {
 	const int pid = blockIdx.x;
 	if (W.status[pid] != QTOS_RUNNING) return;
 	extern __shared__ __align__(16) double sm[];
 	const int npad = T.npad, q12 = 2 * IP_LM;
 	double *z = sm;                                /* [2][npad] */
-	double *lb = z + 2 * npad;                     /* [2][max_w * 256] */
-	double *G = lb + 2 * max_w * 256;              /* [12][14]  Q'[Q, p_aff, p_cen] */
+	double *ring = z + 2 * npad;                   /* [rc][256] */
+	double *G = ring + (size_t)rc * 256;           /* [12][14]  Q'[Q, p_aff, p_cen] */
 	double *Clu = G + q12 * 14;                    /* [12][12] */
 	double *tt = Clu + q12 * q12;                  /* [2][12] */
 	double *part = tt + 2 * q12;                   /* [4][16][2] */
 	double *xi = part + 128;                       /* [2][16] */
-	uint64_t *mbar = reinterpret_cast<uint64_t *>(xi + 32);   /* [2] */
-	int *piv = reinterpret_cast<int *>(mbar + 2);  /* [12] + flag */
+	uint64_t *mbar = reinterpret_cast<uint64_t *>(xi + 32);   /* [KS_NBAR] */
+	int *piv = reinterpret_cast<int *>(mbar + KS_NBAR);  /* [12] + flag */
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const double *Jv = WS(Jv, T.nJ), *r = WS(r, T.m), *s = WS(s, T.m), *vL = WS(zL, T.m), *vU = WS(zU, T.m);
 	const double *dL = WS(dL, T.m), *dU = WS(dU, T.m), *y = WS(y, T.m), *Sig = WS(Sig, T.m);
@@ -383,39 +464,38 @@ kip_solve(DevTables T, DevWork W, qtos_options opt, int max_w)
 	double *ady = WS(ady, T.m), *cdy = WS(cdy, T.m), *eA = WS(rt, T.m), *eC = WS(st, T.m);
 	const int n_pairs = (int)ip[IP_NPAIRS];
 	const double avrg_compl = ip[IP_AVRG], rho = 1.0 / opt.delta_c;
-	if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-	SweepCtx C; C.fb = T.fb; C.blkptr = T.blkptr; C.nb = T.nb; C.npad = npad; C.M = WS(M, T.nM); C.Dinv = WS(Dinv, T.nb * 256); C.z = z; C.lb = lb; C.part = part; C.xi = xi; C.mbar = mbar;
-	C.lbsz = max_w * 256; C.phase[0] = C.phase[1] = 0;
+	SweepCtx C; C.fb = T.fb; C.blkptr = T.blkptr; C.nb = T.nb; C.npad = npad; C.M = WS(M, T.nM); C.Dinv = WS(Dinv, T.nb * 256);
+	C.z = z; C.ring = ring; C.part = part; C.xi = xi; C.mbar = mbar; C.rc = rc; C.total = (2 * opt.n_refine + 1) * T.nb;
+	C.p_seq = C.p_pos = C.c_seq = C.c_pos = 0; C.p_free = rc;
+	if (tid == 0) {
+		for (int b = 0; b < KS_NBAR; ++b) mbar_init(&mbar[b], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		sweep_pump(C);                                 /* the first rows of L are on their way while the Woodbury term is set up */
+	}
 	for (int i = tid; i < npad; i += KS_T) {
 		const double *o = PB + (size_t)(i >> 4) * 256 + (i & 15);
 		z[i] = o[12 * 16]; z[npad + i] = o[13 * 16];
 	}
-	for (int i = tid; i < T.m; i += KS_T) { ady[i] = 0.0; cdy[i] = 0.0; eA[i] = 0.0; eC[i] = 0.0; }
+	for (int i = tid; i < T.m; i += KS_T) { eA[i] = 0.0; eC[i] = 0.0; }          /* inequality rows of the Jc' dy operand stay zero */
 	__syncthreads();
 	int nlr = 2 * n_pairs;
 	for (int pass = 0; pass <= opt.n_refine; ++pass) {
 		if (nlr) {
-			/* G[a][b] = Q_a' [Q_b | p_aff | p_cen]: a warp takes column a and keeps all partial sums of its row of G */
-			for (int a = warp; a < q12; a += KS_T / 32) {
-				if ((a % IP_LM) >= n_pairs) continue;
-				double acc[14];
-#pragma unroll
-				for (int b = 0; b < 14; ++b) acc[b] = 0.0;
-				for (int i = lane; i < npad; i += 32) {
-					const double *o = PB + (size_t)(i >> 4) * 256 + (i & 15);
-					const double qa = o[a * 16];
-					if (pass == 0) {
-#pragma unroll
-						for (int b = 0; b < q12; ++b) acc[b] += qa * o[b * 16];
+			if (pass == 0) {
+				/* G = Q'[Q | p_aff | p_cen] came with the factorization (k_factor's Gram matrix of the right-hand-side row) */
+				const double *Gg = WS(G, 256);
+				for (int q = tid; q < q12 * 14; q += KS_T) G[q] = Gg[(q / 14) * 16 + (q % 14)];
+			} else {
+				/* later passes: only Q'p of the two new right-hand sides; a warp takes every fourth column of Q */
+				for (int a = warp; a < q12; a += KS_T / 32) {
+					if ((a % IP_LM) >= n_pairs) continue;
+					double a0 = 0.0, a1 = 0.0;
+					for (int i = lane; i < npad; i += 32) {
+						const double qa = PB[(size_t)(i >> 4) * 256 + a * 16 + (i & 15)];
+						a0 += qa * z[i]; a1 += qa * z[npad + i];
 					}
-					acc[12] += qa * z[i]; acc[13] += qa * z[npad + i];
-				}
-#pragma unroll
-				for (int b = 0; b < 14; ++b) {
-					if (pass > 0 && b < q12) continue;
-					double t = acc[b];
-					for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-					if (lane == 0) G[a * 14 + b] = t;
+					for (int o = 16; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+					if (lane == 0) { G[a * 14 + 12] = a0; G[a * 14 + 13] = a1; }
 				}
 			}
 			__syncthreads();
@@ -454,23 +534,24 @@ kip_solve(DevTables T, DevWork W, qtos_options opt, int max_w)
 		}
 		sweep_backward(C);                         /* z = dx of both directions, permuted order */
 		/* multiplier-method update on the equality rows: dy += rho (Jc dx - b2) */
-		for (int i = tid; i < T.m; i += KS_T) {
-			if (!(T.row_flags[i] & ROW_EQ)) continue;
-			const Element &E = T.elems[T.row_elem[i]];
-			const int rr = i - E.row0;
-			const int16_t *cols = T.elem_cols + E.coloff;
-			double j0 = 0.0, j1 = 0.0;
-			for (int a = 0; a < E.ncols; ++a) { const double jv = Jv[E.valoff + a * E.ld + rr]; j0 += jv * z[cols[a]]; j1 += jv * z[npad + cols[a]]; }
-			const double da = ady[i] + rho * (j0 + r[i]), dc = cdy[i] + rho * j1;      /* b2 = -r (affine), 0 (centering) */
-			ady[i] = da; cdy[i] = dc; eA[i] = da; eC[i] = dc;
+		for (int base = 0; base < T.n_eq; base += KS_T / 8) {
+			const int idx = base + (tid >> 3);
+			const bool valid = idx < T.n_eq;
+			const int i = valid ? T.eq_rows[idx] : 0;
+			double j0, j1;
+			row_dot2(T, Jv, z, z + npad, i, valid, j0, j1);
+			if (valid && (tid & 7) == 0) {
+				const double da = (pass ? ady[i] : 0.0) + rho * (j0 + r[i]), dc = (pass ? cdy[i] : 0.0) + rho * j1;      /* b2 = -r (affine), 0 (centering) */
+				ady[i] = da; cdy[i] = dc; eA[i] = da; eC[i] = dc;
+			}
 		}
 		if (pass == opt.n_refine) break;
 		__syncthreads();
 		/* next right-hand side: v = v0 - Jc' dy, then p = L^-1 v */
-		for (int i = tid; i < ((npad + 31) & ~31); i += KS_T) {
-			if (i >= npad) continue;
+		for (int i = tid; i < npad; i += KS_T) {
 			const double *o = RB + (size_t)(i >> 4) * 256 + (i & 15);
-			const double ga = jt_gather(T, Jv, eA, i), gc = jt_gather(T, Jv, eC, i);
+			double ga, gc;
+			jt_gather2(T.jgc_ptr, T.jgc, Jv, eA, eC, i, ga, gc);
 			z[i] = i < T.n_free ? o[12 * 16] - ga : 0.0; z[npad + i] = i < T.n_free ? o[13 * 16] - gc : 0.0;
 		}
 		__syncthreads();
@@ -481,14 +562,14 @@ kip_solve(DevTables T, DevWork W, qtos_options opt, int max_w)
 	double *adx = WS(adx, npad), *cdx = WS(cdx, npad);
 	for (int i = tid; i < npad; i += KS_T) { adx[i] = z[i]; cdx[i] = z[npad + i]; }
 	double *ads = WS(ads, T.m), *advL = WS(advL, T.m), *advU = WS(advU, T.m), *cds = WS(cds, T.m), *cdvL = WS(cdvL, T.m), *cdvU = WS(cdvU, T.m);
-	for (int i = tid; i < T.m; i += KS_T) {
+	for (int base = 0; base < T.n_ineq; base += KS_T / 8) {
+		const int idx = base + (tid >> 3);
+		const bool valid = idx < T.n_ineq;
+		const int i = valid ? T.iq_rows[idx] : 0;
+		double j0, j1;
+		row_dot2(T, Jv, z, z + npad, i, valid, j0, j1);
+		if (!valid || (tid & 7)) continue;
 		const int fl = T.row_flags[i];
-		if (fl & ROW_EQ) continue;
-		const Element &E = T.elems[T.row_elem[i]];
-		const int rr = i - E.row0;
-		const int16_t *cols = T.elem_cols + E.coloff;
-		double j0 = 0.0, j1 = 0.0;
-		for (int a = 0; a < E.ncols; ++a) { const double jv = Jv[E.valoff + a * E.ld + rr]; j0 += jv * z[cols[a]]; j1 += jv * z[npad + cols[a]]; }
 		double augA = -(-y[i] - vL[i] + vU[i]), augC = 0.0, sl = 1.0, su = 1.0;
 		if (fl & ROW_HASL) { sl = s[i] - dL[i]; augA += (-sl * vL[i]) / sl; augC += avrg_compl / sl; }
 		if (fl & ROW_HASU) { su = dU[i] - s[i]; augA -= (-su * vU[i]) / su; augC -= avrg_compl / su; }
@@ -555,7 +636,24 @@ kip_step(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield
 	const double avrg_compl = ip[IP_AVRG], nlp_error = ip[IP_ERR], theta = ip[IP_THETA], gl2 = ip[IP_GL2], pr2 = ip[IP_PR2], mu_max = ip[IP_MU_MAX];
 	double theta_max = ip[IP_TH_MAX], theta_min = ip[IP_TH_MIN];
 	if (tid < IP_FILTER_MAX) { sfphi[tid] = ip[IP_FPHI + tid]; sfth[tid] = ip[IP_FTH + tid]; }
-	__syncthreads();
+	{
+		/* A factorization that met a non-positive pivot or produced a non-finite direction is repeated with W + delta_w I
+		 * (Ipopt's PDPerturbationHandler: 1e-4 the first time, a third of the last successful value later, then x100 / x8):
+		 * the problem sits this step out and kip_prepare re-enters the same iteration with the larger diagonal. */
+		double nf[1] = {0.0};
+		for (int i = tid; i < T.npad; i += blockDim.x) nf[0] += 0.0 * adx[i] + 0.0 * cdx[i];
+		{ const int ops[1] = {0}; block_reduce<1>(nf, ops, red); }
+		if (!(nf[0] == 0.0) || (W.flags[pid] & 1)) {
+			if (tid == 0) {
+				const double last = ip[IP_DELTA_LAST];
+				double dw = ip[IP_RETRY] != 0.0 ? ip[IP_DELTA_W] : 0.0;
+				dw = dw == 0.0 ? (last == 0.0 ? 1e-4 : fmax(1e-20, last / 3.0)) : dw * (last == 0.0 ? 100.0 : 8.0);
+				if (dw > 1e40) { W.status[pid] = QTOS_STEP_FAILED; atomicSub(W.n_running, 1); }
+				ip[IP_DELTA_W] = dw; ip[IP_RETRY] = 1.0;
+			}
+			return;
+		}
+	}
 	const double mu_min = fmin(1e-11, 0.5 * fmin(opt.tol, opt.compl_inf_tol));
 	double sigma = mu / avrg_compl;
 	if (free_mode) {
@@ -701,6 +799,8 @@ kip_step(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield
 		}
 		ip[IP_NFILTER] = nfilter; ip[IP_MU] = mu; ip[IP_TAU] = tau; ip[IP_TH_MAX] = theta_max; ip[IP_TH_MIN] = theta_min;
 		ip[IP_ALPHA_PR] = alpha; ip[IP_ALPHA_DU] = alpha_du; ip[IP_DNORM] = dnorm; ip[IP_LS] = ls; ip[IP_TAG] = ftype ? 'f' : 'h';
+		ip[IP_ITER] += 1.0;
+		if (ip[IP_RETRY] != 0.0) { ip[IP_DELTA_LAST] = ip[IP_DELTA_W]; ip[IP_RETRY] = 0.0; ip[IP_DELTA_W] = 0.0; }
 	}
 }
 

@@ -649,15 +649,26 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld, int max_w)
 			double *rp = rp0;
 			const int row = tm * 8 + fr, col = tn * 8 + 2 * fc;
 			const int cp = SWZ(tn * 4 + fc, fr);
+			const double2 *a = reinterpret_cast<const double2 *>(rp + row * rp_ld + 4 * fc);
+			const double2 *a_lo = a + odd, *a_hi = a + (odd ^ 1);
+			/* Gram matrix of the row, G = P'P (16 x 16: Q'Q, Q'p and p'p of kip_solve's Woodbury term): one more product per
+			 * block while it sits in the ring, B operand = the same block read by rows */
+			const double2 *gb = reinterpret_cast<const double2 *>(rp + (tn * 8 + fr) * rp_ld + 4 * fc);
+			const double2 *gb_lo = gb + odd, *gb_hi = gb + (odd ^ 1);
+			double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0, g4 = 0.0, g5 = 0.0, g6 = 0.0, g7 = 0.0;
+			auto gram = [&](int slot) {
+				const double2 a01 = a_lo[slot * 8], a23 = a_hi[slot * 8], b01 = gb_lo[slot * 8], b23 = gb_hi[slot * 8];
+				dmma(g0, g1, a01.x, b01.x); dmma(g2, g3, a01.y, b01.y);
+				dmma(g4, g5, a23.x, b23.x); dmma(g6, g7, a23.y, b23.y);
+			};
 			for (int J = 0; J < T.nb; ++J) {
 				const int K0 = T.fb[J], nK = J - K0;
 				const double2 *bi = reinterpret_cast<const double2 *>(Dinv + (size_t)J * 256 + tn * 128) + lane;
 				const double2 i01 = bi[0], i23 = bi[32];
 				const double2 cA = *reinterpret_cast<const double2 *>(RB + (size_t)(J * 16 + row) * 16 + col);
 				tile_sync();                           /* block J-1 of the row is in the ring */
+				if (J > 0) gram((J - 1) % max_w);
 				double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0, c4 = 0.0, c5 = 0.0, c6 = 0.0, c7 = 0.0;
-				const double2 *a = reinterpret_cast<const double2 *>(rp + row * rp_ld + 4 * fc);
-				const double2 *a_lo = a + odd, *a_hi = a + (odd ^ 1);
 				const double2 *b = reinterpret_cast<const double2 *>(M + (size_t)T.blkptr[J] * 256 + tn * 128) + lane;
 				int slot = K0 % max_w;
 				for (int K = 0; K < nK; ++K) {
@@ -678,6 +689,9 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld, int max_w)
 				reinterpret_cast<double2 *>(rp + row * rp_ld + (J % max_w) * 16)[cp] = pj;
 				*reinterpret_cast<double2 *>(PB + (size_t)(J * 16 + row) * 16 + col) = pj;
 			}
+			tile_sync();
+			gram((T.nb - 1) % max_w);
+			*reinterpret_cast<double2 *>(WS(G, 256) + row * 16 + col) = make_double2((g0 + g2) + (g4 + g6), (g1 + g3) + (g5 + g7));
 			if (tid == 0 && bad) W.flags[pid] |= 1;
 			return;
 		}
@@ -853,7 +867,7 @@ __global__ void k_results(DevTables T, DevWork W, qtos_result *res, double *x_ou
 	if (threadIdx.x == 0 && res) {
 		const double *scal = WS(scal, 16);
 		qtos_result R;
-		R.status = W.status[pid]; R.iters = W.iters[pid];
+		R.status = W.status[pid] == QTOS_RUNNING ? QTOS_MAX_ITER : W.status[pid]; R.iters = W.iters[pid];
 		R.constr_viol = scal[SC_VIOL]; R.dual_inf = scal[SC_DUAL]; R.compl_inf = scal[SC_COMPL]; R.nlp_error = scal[SC_E0]; R.mu = scal[SC_MU];
 		R.cost = 0.0;
 		res[pid] = R;

@@ -125,6 +125,10 @@ struct HostTables {
 	 * keeps several columns in flight: lo = value offset of the column | rows << 20, hi = first constraint row */
 	std::vector<int>     jg_ptr;                         /* [ceil(npad/32)+1], multiples of 32 */
 	std::vector<uint2_t> jg;
+	/* the same gather restricted to elements that hold equality rows (Jc' v: the multiplier passes of kip_solve) */
+	std::vector<int>     jgc_ptr;
+	std::vector<uint2_t> jgc;
+	std::vector<int16_t> eq_rows, iq_rows;               /* [n_eq], [n_ineq] row indices */
 	/* 1 kHz sampler */
 	std::vector<double>  csv_t;                          /* [csv_rows] accumulated sample times */
 	std::vector<uint8_t> csv_id;                         /* [csv_rows][10] */
