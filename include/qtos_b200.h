@@ -147,11 +147,23 @@ int  qtos_solve_batch(qtos_ctx *ctx, const qtos_problem *p, int n, const qtos_op
 /* same with device-resident buffers (problems, results, x) on the context's stream */
 int  qtos_solve_batch_device(qtos_ctx *ctx, const qtos_problem *d_p, int n, const qtos_options *o,
                              qtos_result *d_res, double *d_x_out);
+/* Asynchronous variants (SURVEY 8b "batch call is synchronous by default with an async variant"): the call returns at once,
+ * a worker thread of the context drives the solve on the context's stream; one call in flight per context; every buffer
+ * must stay valid until qtos_wait returns (its return value is the solve's).  Two contexts on one device overlap: the
+ * straggler iterations of one batch run beside the full launches of the next. */
+int  qtos_solve_batch_async(qtos_ctx *ctx, const qtos_problem *p, int n, const qtos_options *o,
+                            qtos_result *res, double *x_out, double *csv_out);
+int  qtos_solve_batch_device_async(qtos_ctx *ctx, const qtos_problem *d_p, int n, const qtos_options *o,
+                                   qtos_result *d_res, double *d_x_out);
+int  qtos_wait(qtos_ctx *ctx);
 /* IPOPT algorithm: the per-iteration table Ipopt prints (ref: logs/towr_log.out:55-62), for the first n problems of the
  * last solve: trace_out = n * QTOS_TRACE_ITERS * QTOS_TRACE_COLS doubles; rows past a problem's last iteration are zero */
 int  qtos_get_trace(qtos_ctx *ctx, int n, double *trace_out);
 /* 1 kHz sampler (ref: main.cpp:92-131): rows_out = n * csv_rows * 37 */
 int  qtos_sample_csv(qtos_ctx *ctx, const qtos_problem *p, int n, const double *x, double *rows_out);
+/* rows [row0, row0 + n_rows) only: rows_out = n * n_rows * 37 (e.g. the one look-ahead row Combiner._state reads,
+ * ref: QTOS/combiner.py:245-296) */
+int  qtos_sample_csv_rows(qtos_ctx *ctx, const qtos_problem *p, int n, const double *x, int row0, int n_rows, double *rows_out);
 /* write one trajectory as the reference's traj.csv text ("%g", comma separated) */
 int  qtos_write_csv(const double *rows, int n_rows, const char *path);
 

@@ -97,7 +97,8 @@ assert PROBLEM_DTYPE.itemsize == 8 * 28 + 8 and RESULT_DTYPE.itemsize == 56
 
 EXPORTS = ["qtos_default_shape", "qtos_default_options", "qtos_create", "qtos_destroy", "qtos_last_error",
            "qtos_get_dims", "qtos_upload_heightfield", "qtos_heightfield_query", "qtos_heightfield_cells",
-           "qtos_get_initial", "qtos_eval", "qtos_solve_batch", "qtos_solve_batch_device", "qtos_get_trace", "qtos_sample_csv",
+           "qtos_get_initial", "qtos_eval", "qtos_solve_batch", "qtos_solve_batch_device", "qtos_solve_batch_async",
+           "qtos_solve_batch_device_async", "qtos_wait", "qtos_get_trace", "qtos_sample_csv", "qtos_sample_csv_rows",
            "qtos_write_csv", "qtos_launch_count", "qtos_set_profiling", "qtos_last_stats", "qtos_stream",
            "qtos_measure_fp64_peak"]
 
@@ -125,8 +126,12 @@ def lib():
         L.qtos_eval.argtypes = [vp, vp, C.c_int, dp, dp, dp]
         L.qtos_solve_batch.argtypes = [vp, vp, C.c_int, C.POINTER(Options), vp, dp, dp]
         L.qtos_solve_batch_device.argtypes = [vp, vp, C.c_int, C.POINTER(Options), vp, vp]
+        L.qtos_solve_batch_async.argtypes = [vp, vp, C.c_int, C.POINTER(Options), vp, dp, dp]
+        L.qtos_solve_batch_device_async.argtypes = [vp, vp, C.c_int, C.POINTER(Options), vp, vp]
+        L.qtos_wait.argtypes = [vp]
         L.qtos_get_trace.argtypes = [vp, C.c_int, dp]
         L.qtos_sample_csv.argtypes = [vp, vp, C.c_int, dp, dp]
+        L.qtos_sample_csv_rows.argtypes = [vp, vp, C.c_int, dp, C.c_int, C.c_int, dp]
         L.qtos_write_csv.argtypes = [dp, C.c_int, C.c_char_p]
         L.qtos_launch_count.argtypes = [vp]
         L.qtos_launch_count.restype = C.c_longlong
@@ -273,6 +278,33 @@ class Solver:
         self._ck(self._L.qtos_solve_batch(self._h, pp, n, C.byref(o), res.ctypes.data_as(C.c_void_p), _dp(x), _dp(rows)))
         return res, x, rows
 
+    def solve_async(self, problems, out, options=None):
+        """Asynchronous solve into caller-supplied host buffers out = (results, x) (see solve); returns at once.
+        `wait()` returns the same (results, x).  One call in flight per Solver."""
+        p, pp = self._probs(problems)
+        n = len(p)
+        res, x = out
+        if res.dtype != RESULT_DTYPE or res.shape != (n,) or x.dtype != np.float64 or x.shape != (n, self.n_vars) \
+                or not res.flags.c_contiguous or not x.flags.c_contiguous:
+            raise ValueError("out must be (RESULT_DTYPE[n], float64[n, n_vars]), C-contiguous")
+        o = options if options is not None else default_options()
+        self._inflight = (p, res, x, o)            # keep the buffers alive until wait()
+        self._ck(self._L.qtos_solve_batch_async(self._h, pp, n, C.byref(o), res.ctypes.data_as(C.c_void_p), _dp(x), None))
+
+    def solve_device_async(self, d_problems_ptr, n, options=None, d_results_ptr=None, d_x_ptr=None):
+        o = options if options is not None else default_options()
+        self._inflight = (None, None, None, o)
+        self._ck(self._L.qtos_solve_batch_device_async(self._h, C.c_void_p(d_problems_ptr), int(n), C.byref(o),
+                                                       C.c_void_p(d_results_ptr) if d_results_ptr else None,
+                                                       C.c_void_p(d_x_ptr) if d_x_ptr else None))
+
+    def wait(self):
+        """Join the asynchronous call of this Solver; raises if the solve failed."""
+        self._ck(self._L.qtos_wait(self._h))
+        _, res, x, _ = getattr(self, "_inflight", (None, None, None, None))
+        self._inflight = None
+        return res, x
+
     def solve_device(self, d_problems_ptr, n, options=None, d_results_ptr=None, d_x_ptr=None):
         """Device-resident variant: raw device pointers (e.g. torch tensor .data_ptr())."""
         o = options if options is not None else default_options()
@@ -293,6 +325,17 @@ class Solver:
         xx = np.ascontiguousarray(x, dtype=np.float64).reshape(n, self.n_vars)
         rows = np.zeros((n, self.csv_rows, CSV_COLS))
         self._ck(self._L.qtos_sample_csv(self._h, pp, n, _dp(xx), _dp(rows)))
+        return rows
+
+    def sample_rows(self, problems, x, row0, n_rows=1):
+        """rows [row0, row0 + n_rows) of the 1 kHz trajectories: [n, n_rows, 37] (negative row0 counts from the end)."""
+        p, pp = self._probs(problems)
+        n = len(p)
+        if row0 < 0:
+            row0 += self.csv_rows
+        xx = np.ascontiguousarray(x, dtype=np.float64).reshape(n, self.n_vars)
+        rows = np.zeros((n, n_rows, CSV_COLS))
+        self._ck(self._L.qtos_sample_csv_rows(self._h, pp, n, _dp(xx), int(row0), int(n_rows), _dp(rows)))
         return rows
 
     def launch_count(self):

@@ -895,13 +895,14 @@ __global__ void k_cost(DevTables T, const double *x_all, qtos_result *res, int n
 	if (threadIdx.x == 0) res[pid].cost = u[0];
 }
 
-__global__ void k_csv(DevTables T, const double *x_all, const qtos_problem *probs, double *rows, int n)
+/* rows [row0, row0 + n_rows) of every plan's 1 kHz trajectory */
+__global__ void k_csv(DevTables T, const double *x_all, const qtos_problem *probs, double *rows, int n, int row0, int n_rows)
 {
 	const int pid = blockIdx.y;
-	const int row = blockIdx.x * blockDim.x + threadIdx.x;
-	if (row >= T.csv_rows || pid >= n) return;
+	const int lr = blockIdx.x * blockDim.x + threadIdx.x, row = row0 + lr;
+	if (lr >= n_rows || pid >= n) return;
 	const double *x = x_all + (size_t)pid * T.n_all;
-	double *c = rows + ((size_t)pid * T.csv_rows + row) * QTOS_CSV_COLS;
+	double *c = rows + ((size_t)pid * n_rows + lr) * QTOS_CSV_COLS;
 	c[0] = T.csv_t[row] + probs[pid].t_start;
 	for (int s = 0; s < 10; ++s) {
 		const int id = T.csv_id[(size_t)row * 10 + s];

@@ -22,14 +22,16 @@ def make_records(results, global_idx, groups):
     rec = np.empty((len(results), 5), dtype=np.float64)
     rec[:, 0] = groups
     rec[:, 1] = (results["status"] != 0).astype(np.float64)
-    rec[:, 2] = results["cost"]
-    rec[:, 3] = results["constr_viol"]
+    # a window that ended on non-finite values (status -13) carries NaN metrics: +inf keeps every selector's minimum defined
+    rec[:, 2] = np.nan_to_num(results["cost"], nan=np.inf)
+    rec[:, 3] = np.nan_to_num(results["constr_viol"], nan=np.inf)
     rec[:, 4] = global_idx
     return rec
 
 
 def argmin_per_group_sorted(rec):
     """reference implementation: one lexicographic sort of all records (O(n log n), ~20 ms for 32768 records)."""
+    rec = np.nan_to_num(rec, nan=np.inf, posinf=np.inf)
     order = np.lexsort((rec[:, 4], rec[:, 3], rec[:, 2], rec[:, 1], rec[:, 0]))
     srt = rec[order]
     first = np.ones(len(srt), dtype=bool)
@@ -45,7 +47,7 @@ def argmin_per_group(rec):
     if len(rec) == 0:
         return {}
     order = np.argsort(rec[:, 0].astype(np.int64), kind="stable")
-    srt = rec[order]
+    srt = np.nan_to_num(rec[order], nan=np.inf, posinf=np.inf)
     grp = srt[:, 0]
     starts = np.flatnonzero(np.concatenate(([True], grp[1:] != grp[:-1])))
     counts = np.diff(np.concatenate((starts, [len(srt)])))
@@ -62,6 +64,7 @@ def argmin_per_group_torch(rec):
     """the same selection on a torch tensor [n, 5] (device-resident after the all-gather): dense group index by
     torch.unique, then one segmented minimum (scatter_reduce amin) per key over the still-tied candidates.
     Returns (groups int64 [G], winning global ids int64 [G]) on the tensor's device."""
+    rec = torch.nan_to_num(rec, nan=float("inf"), posinf=float("inf"))
     grp, inv = torch.unique(rec[:, 0].to(torch.int64), return_inverse=True)
     tied = torch.ones(rec.shape[0], dtype=torch.bool, device=rec.device)
     inf = torch.tensor(float("inf"), dtype=rec.dtype, device=rec.device)

@@ -32,6 +32,35 @@ def terrain_variants(n_variants=8):
     return [rough_terrain(seed=s) for s in range(n_variants)]
 
 
+def replan_from_rows(prev_problems, row, step=(0.4, 0.0)):
+    """vectorised replan_problems: `row` [n, 37] is every plan's CSV row at the hand-over time."""
+    p = prev_problems.copy()
+    row = np.asarray(row, dtype=np.float64)
+    p["start_pos"] = row[:, 1:4]
+    p["start_ang"] = row[:, 4:7]
+    p["start_vel"] = 0.0
+    p["start_ang_vel"] = 0.0
+    p["ee"] = row[:, 7:19].reshape(-1, 4, 3)
+    p["t_start"] = row[:, 0]
+    p["goal"][:, 0] = prev_problems["goal"][:, 0] + step[0]
+    p["goal"][:, 1] = prev_problems["goal"][:, 1] + step[1]
+    return p
+
+
+def replan_sweep_problems(n_total, variants, hf_ids, seed=1234, group_size=8):
+    """BASELINE config 5, generation 0: n_total windows spread evenly over the terrain variants (multi-start pairs on each
+    variant's own grid, groups of `group_size` candidates); the timed generation is made of their successors
+    (replan_from_rows on each plan's final, all-stance row)."""
+    nv = len(variants)
+    per = n_total // nv
+    out = []
+    for v, (grid, res) in enumerate(variants):
+        q = multistart_problems(per, grid, res, seed=seed + v, hf_id=hf_ids[v], group_size=group_size)
+        q["group"] += v * ((per + group_size - 1) // group_size)
+        out.append(q)
+    return np.concatenate(out)
+
+
 def replan_problems(prev_problems, rows, lookahead_row, step=(0.4, 0.0)):
     """Receding-horizon successors (config 5): the next window of every plan starts from the plan's own state at
     `lookahead_row` of its 1 kHz CSV rows -- what Combiner._state reads back from towr.csv (ref: QTOS/combiner.py:245-296,

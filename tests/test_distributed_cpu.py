@@ -85,3 +85,23 @@ def test_torch_selection_equals_numpy():
         rec = rec[rng.permutation(n)]
         grp, win = parallel.argmin_per_group_torch(torch.from_numpy(rec))
         assert dict(zip(grp.tolist(), win.tolist())) == parallel.argmin_per_group(rec)
+
+
+def test_nan_records_do_not_win_or_poison_a_group():
+    """a status -13 window carries NaN cost / violation: every selector must still name a valid member of each group
+    (the minimum of a NaN key used to come back as INT64_MIN)."""
+    import torch
+    from qtos_b200 import parallel
+    nan = float("nan")
+    rec = np.array([[0, 1, nan, nan, 0], [0, 1, 2.0, 0.1, 1],            # no candidate converged, one is all-NaN
+                    [1, 1, nan, nan, 2], [1, 0, 5.0, 0.0, 3],            # NaN beside a converged candidate
+                    [2, 1, nan, nan, 4]], dtype=np.float64)             # a group of one NaN window: it still names itself
+    want = {0: 1, 1: 3, 2: 4}
+    assert parallel.argmin_per_group_sorted(rec) == want
+    assert parallel.argmin_per_group(rec) == want
+    g, w = parallel.argmin_per_group_torch(torch.from_numpy(rec))
+    assert dict(zip(g.tolist(), w.tolist())) == want
+    import qtos_b200 as Q
+    r = np.zeros(2, dtype=Q.RESULT_DTYPE); r["status"] = (-13, 0); r["cost"] = (nan, 1.0); r["constr_viol"] = (nan, 0.0)
+    out = parallel.make_records(r, np.array([7, 8]), np.array([0, 0]))
+    assert np.isinf(out[0, 2]) and np.isinf(out[0, 3]) and not np.isnan(out).any()
