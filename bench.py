@@ -17,7 +17,7 @@ the reference's algorithm (QTOS_ALG_IPOPT) to the reference's convergence criter
          variants (seeds 0..7), each window started from the final state of a previously solved plan on its
          own grid; one process per GPU (torchrun), windows sharded statically (weak scaling), one all-gather
          of per-candidate records for best-plan selection inside the timed region.
-Two batches are in flight per GPU (two solver contexts driven through the asynchronous C ABI), so the
+Three batches are in flight per GPU (three solver contexts driven through the asynchronous C ABI), so the
 straggler iterations of one batch run beside the full launches of the next; `serial` in the JSON line is the
 same measurement with one batch in flight, and the per-kernel / roofline figures come from that serial pass.
 """
@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 
 PER_GPU = 4096
 GROUP = 8
-IN_FLIGHT = 2
+IN_FLIGHT = int(os.environ.get("QTOS_IN_FLIGHT", "3"))
 N_VARIANTS = 8
 COMBO, DURATION = "C1", 2.0
 CPU_SAMPLE = 192
