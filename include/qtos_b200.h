@@ -30,7 +30,9 @@ enum {
 	QTOS_SOLVE_SUCCEEDED = 0,         /* Ipopt Solve_Succeeded */
 	QTOS_MAX_ITER = -1,               /* Ipopt Maximum_Iterations_Exceeded */
 	QTOS_STEP_FAILED = -2,            /* line search could not make progress (Ipopt: Restoration_Failed) */
-	QTOS_INVALID_NUMBER = -13,        /* Ipopt Invalid_Number_Detected: NaN/Inf in the constraints (bad inputs) */
+	QTOS_MAX_CPUTIME = -4,            /* Ipopt Maximum_CpuTime_Exceeded: the iteration budget derived from max_cpu_time (-r) ran out */
+	QTOS_INVALID_NUMBER = -13,        /* Ipopt Invalid_Number_Detected: NaN/Inf in the constraints (bad inputs), or a problem that
+	                                     names a heightfield id that does not exist (device-resident problems cannot be checked on the host) */
 	QTOS_RUNNING = 99
 };
 
@@ -82,7 +84,12 @@ typedef struct {
 	int    algorithm;                 /* QTOS_ALG_IPOPT (default) or QTOS_ALG_FAST */
 	int    n_refine;                  /* IPOPT: multiplier-method passes on the equality block per direction (1) */
 	int    lm_history;                /* IPOPT: limited_memory_max_history (6, the maximum) */
+	double max_cpu_time;              /* the reference's `-r` / Ipopt max_cpu_time in seconds (ref: main.cpp:180,459-460); 0 = none.
+	                                     Wall-clock limits are not deterministic on a batched device, so the budget is counted in
+	                                     iterations: floor(max_cpu_time / QTOS_REF_SECONDS_PER_ITERATION), i.e. the iterations the
+	                                     reference itself completes in that time; reaching it returns QTOS_MAX_CPUTIME */
 } qtos_options;
+#define QTOS_REF_SECONDS_PER_ITERATION 0.1   /* 0.75-0.88 s for 7-8 iterations, ref: logs/towr_log.out:64,81-82 */
 
 /* QTOS_ALG_IPOPT: the algorithm the reference runs (Ipopt 3.11.9 as configured by ifopt, ref: solver/towr/src/main.cpp:444-463,
  *   logs/towr_log.out:37-64): limited-memory BFGS Hessian (history 6), adaptive quality-function barrier update, filter line
@@ -129,6 +136,8 @@ int  qtos_get_dims(const qtos_ctx *ctx, qtos_dims *d);
 
 /* hf[ix*ny + iy], ix = row of towr_heightfield.txt = world x (ref: custom_terrain.cpp:12-49) */
 int  qtos_upload_heightfield(qtos_ctx *ctx, const double *hf, int nx, int ny, double res, int *hf_id);
+/* release a grid; its id is reused by a later upload; problems that still name it end with QTOS_INVALID_NUMBER */
+int  qtos_free_heightfield(qtos_ctx *ctx, int hf_id);
 /* batched CustomTerrain::GetHeight (ref: custom_terrain.cpp:51-94), bit-exact; xy = n pairs */
 int  qtos_heightfield_query(qtos_ctx *ctx, int hf_id, const double *xy, int n, double *h_out);
 int  qtos_heightfield_cells(qtos_ctx *ctx, int hf_id, const double *xy, int n, long long *idx4_out);

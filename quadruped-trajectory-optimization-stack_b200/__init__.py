@@ -68,7 +68,7 @@ class Options(C.Structure):
     _fields_ = [("tol", C.c_double), ("constr_viol_tol", C.c_double), ("compl_inf_tol", C.c_double),
                 ("dual_inf_tol", C.c_double), ("max_iter", C.c_int), ("mu_init", C.c_double),
                 ("sigma_w", C.c_double), ("delta_c", C.c_double), ("feas_exit", C.c_int),
-                ("algorithm", C.c_int), ("n_refine", C.c_int), ("lm_history", C.c_int)]
+                ("algorithm", C.c_int), ("n_refine", C.c_int), ("lm_history", C.c_int), ("max_cpu_time", C.c_double)]
 
 
 ALG_IPOPT, ALG_FAST = 0, 1          # qtos_options.algorithm
@@ -96,7 +96,7 @@ RESULT_DTYPE = np.dtype([("status", "i4"), ("iters", "i4"), ("constr_viol", "f8"
 assert PROBLEM_DTYPE.itemsize == 8 * 28 + 8 and RESULT_DTYPE.itemsize == 56
 
 EXPORTS = ["qtos_default_shape", "qtos_default_options", "qtos_create", "qtos_destroy", "qtos_last_error",
-           "qtos_get_dims", "qtos_upload_heightfield", "qtos_heightfield_query", "qtos_heightfield_cells",
+           "qtos_get_dims", "qtos_upload_heightfield", "qtos_free_heightfield", "qtos_heightfield_query", "qtos_heightfield_cells",
            "qtos_get_initial", "qtos_eval", "qtos_solve_batch", "qtos_solve_batch_device", "qtos_solve_batch_async",
            "qtos_solve_batch_device_async", "qtos_wait", "qtos_get_trace", "qtos_sample_csv", "qtos_sample_csv_rows",
            "qtos_write_csv", "qtos_launch_count", "qtos_set_profiling", "qtos_last_stats", "qtos_stream",
@@ -120,6 +120,7 @@ def lib():
         L.qtos_last_error.restype = C.c_char_p
         L.qtos_get_dims.argtypes = [vp, C.POINTER(Dims)]
         L.qtos_upload_heightfield.argtypes = [vp, dp, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int)]
+        L.qtos_free_heightfield.argtypes = [vp, C.c_int]
         L.qtos_heightfield_query.argtypes = [vp, C.c_int, dp, C.c_int, dp]
         L.qtos_heightfield_cells.argtypes = [vp, C.c_int, dp, C.c_int, C.POINTER(C.c_longlong)]
         L.qtos_get_initial.argtypes = [vp, vp, C.c_int, dp, dp, dp, dp, dp]
@@ -228,6 +229,10 @@ class Solver:
         self._ck(self._L.qtos_upload_heightfield(self._h, _dp(g), g.shape[0], g.shape[1], float(res), C.byref(hid)))
         return hid.value
 
+    def free_heightfield(self, hf_id):
+        """release a grid on the device; the id is handed out again by a later upload"""
+        self._ck(self._L.qtos_free_heightfield(self._h, int(hf_id)))
+
     def height(self, hf_id, xy):
         xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
         out = np.zeros(len(xy))
@@ -301,7 +306,7 @@ class Solver:
     def wait(self):
         """Join the asynchronous call of this Solver; raises if the solve failed."""
         self._ck(self._L.qtos_wait(self._h))
-        _, res, x, _ = getattr(self, "_inflight", (None, None, None, None))
+        _, res, x, _ = getattr(self, "_inflight", None) or (None, None, None, None)
         self._inflight = None
         return res, x
 

@@ -85,7 +85,8 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt)
 	const double avrg_compl = v[7] / (double)nbnd;
 	const bool invalid = !(v[8] == 0.0) || !(nlp_error == nlp_error) || !(theta == theta);
 	const bool conv = !invalid && nlp_error <= opt.tol && dual_inf <= opt.dual_inf_tol && viol <= opt.constr_viol_tol && compl_ <= opt.compl_inf_tol;
-	const bool stop = !retry && (invalid || conv || it >= opt.max_iter);
+	const bool out_of_time = it >= cpu_budget(opt);
+	const bool stop = !retry && (invalid || conv || it >= opt.max_iter || out_of_time);
 	if (tid == 0 && !retry) {
 		scal[SC_DUAL] = dual_inf; scal[SC_THETA] = primal_inf; scal[SC_COMPL] = compl_; scal[SC_VIOL] = viol; scal[SC_E0] = nlp_error; scal[SC_MU] = mu;
 		W.iters[pid] = it;
@@ -95,7 +96,7 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt)
 		}
 		if (stop) {
 			if (invalid) { const double qnan = v[8] - v[8] + (nlp_error - nlp_error); scal[SC_VIOL] = scal[SC_E0] = qnan; }
-			W.status[pid] = invalid ? QTOS_INVALID_NUMBER : (conv ? QTOS_SOLVE_SUCCEEDED : QTOS_MAX_ITER);
+			W.status[pid] = invalid ? QTOS_INVALID_NUMBER : (conv ? QTOS_SOLVE_SUCCEEDED : (out_of_time ? QTOS_MAX_CPUTIME : QTOS_MAX_ITER));
 			atomicSub(W.n_running, 1);
 		}
 	}

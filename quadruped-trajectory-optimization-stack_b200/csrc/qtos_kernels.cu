@@ -56,6 +56,8 @@ __device__ __forceinline__ void scaled_rows(const DevTables &T, const double *sc
 
 /* ------------------------------------------------------------------ k_init */
 
+__device__ __forceinline__ double qnan_fill() { return nan(""); }
+
 __global__ void __launch_bounds__(QTOS_THREADS)
 k_init(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *hfs, int n_hf, qtos_options opt, int do_solver_init)
 {
@@ -63,8 +65,20 @@ k_init(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *
 	const qtos_problem &pr = probs[pid];
 	double *x = WS(x, T.n_all), *P = WS(P, 32), *sc = WS(sc, T.m), *r = WS(r, T.m), *Jv = WS(Jv, T.nJ);
 	__shared__ double sfin[6][3];
-	const int hid = pr.hf_id >= 0 && pr.hf_id < n_hf ? pr.hf_id : 0;
-	const DevHeightfield hf = hfs[hid];
+	const bool hf_ok = pr.hf_id >= 0 && pr.hf_id < n_hf && hfs[pr.hf_id].h != nullptr;
+	const DevHeightfield hf = hfs[hf_ok ? pr.hf_id : 0];
+	if (!hf_ok && do_solver_init) {
+		/* unknown or released heightfield: the window ends here with Invalid_Number_Detected instead of being solved on some
+		 * other grid (host-resident problems are refused before the launch; device-resident ones can only be caught here) */
+		if (do_solver_init == 1 && threadIdx.x == 0) {
+			double *scal = WS(scal, 16);
+			const double qnan = nan("");
+			scal[SC_DUAL] = scal[SC_THETA] = scal[SC_COMPL] = scal[SC_VIOL] = scal[SC_E0] = qnan; scal[SC_MU] = 0.0;
+			W.status[pid] = QTOS_INVALID_NUMBER; W.iters[pid] = 0; W.flags[pid] = 0; atomicSub(W.n_running, 1);
+		}
+		if (do_solver_init == 1) for (int v = threadIdx.x; v < T.n_all; v += blockDim.x) x[v] = qnan_fill();
+		return;
+	}
 	/* do_solver_init: 0 = x0 only (qtos_get_initial / qtos_eval); 1 = x0, g(x0), constant Jacobian elements, problem
 	 * marked running -- the x-dependent elements then come from k_jac_dyn / k_jac_rom (one thread per sample instead
 	 * of one block per problem); 2 = row scaling from J(x0), scaled J, slacks and multipliers */
@@ -191,6 +205,12 @@ k_jac_rom(DevTables T, DevWork W, int n)
 
 /* ------------------------------------------------------------------ k_prepare */
 
+/* iterations the reference completes within max_cpu_time (`-r`), see qtos_options */
+__device__ __forceinline__ int cpu_budget(const qtos_options &opt)
+{
+	return opt.max_cpu_time > 0.0 ? (int)fmin(1e9, floor(opt.max_cpu_time / QTOS_REF_SECONDS_PER_ITERATION)) : 0x7fffffff;
+}
+
 #ifndef JG_U
 #define JG_U 2          /* terms in flight per lane of the J' v gather: more costs the fourth resident CTA and loses */
 #endif
@@ -275,9 +295,10 @@ k_prepare(DevTables T, DevWork W, qtos_options opt, int it)
 		scal[SC_DUAL] = dual_inf; scal[SC_THETA] = theta_inf; scal[SC_COMPL] = cmax; scal[SC_VIOL] = v[6]; scal[SC_E0] = E0;
 		W.iters[pid] = it;
 		if (conv) { W.status[pid] = QTOS_SOLVE_SUCCEEDED; atomicSub(W.n_running, 1); }
+		else if (it >= cpu_budget(opt)) { W.status[pid] = QTOS_MAX_CPUTIME; atomicSub(W.n_running, 1); }
 		else if (it >= opt.max_iter) { W.status[pid] = QTOS_MAX_ITER; atomicSub(W.n_running, 1); }
 	}
-	if (conv || it >= opt.max_iter) return;
+	if (conv || it >= opt.max_iter || it >= cpu_budget(opt)) return;
 	/* monotone barrier update: max_i |z_i s_i - mu| = max(cmax - mu, mu - cmin) */
 	const double kappa_eps = 10.0, mu_min = fmin(opt.tol, opt.compl_inf_tol) / (kappa_eps + 1.0);
 	for (;;) {

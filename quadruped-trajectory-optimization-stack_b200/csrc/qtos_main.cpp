@@ -88,7 +88,13 @@ int main(int argc, char **argv)
 		vec3(argc, argv, "-g", goal); scalar(argc, argv, "-r", &runtime); vec3(argc, argv, "-s", start);
 		vec3(argc, argv, "-s_ang", p.start_ang); vec3(argc, argv, "-s_ang_vel", p.start_ang_vel); vec3(argc, argv, "-s_vel", p.start_vel);
 		std::vector<std::string> n = grab(argc, argv, "-n");
-		if (!n.empty()) normalize = n[0] == "t";
+		if (!n.empty()) {
+			/* the reference compares the JOINED (up to three) tokens after -n with "t" (main.cpp:66,228-232): `-n t` only
+			 * normalises when it is the last thing on the command line */
+			std::string joined = n[0];
+			for (size_t i = 1; i < n.size(); ++i) joined += " " + n[i];
+			normalize = joined == "t";
+		}
 		else p.start_vel[0] = p.start_vel[1] = p.start_vel[2] = 0.0;
 		const char *eopt[4] = {"-e1", "-e2", "-e3", "-e4"};
 		for (int e = 0; e < 4; ++e) vec3(argc, argv, eopt[e], ee[e]);
@@ -119,14 +125,18 @@ int main(int argc, char **argv)
 	std::vector<double> x(d.n_vars), rows((size_t)d.csv_rows * QTOS_CSV_COLS);
 	qtos_result r; memset(&r, 0, sizeof(r));
 	qtos_options o; qtos_default_options(&o);
-	(void)runtime;   /* max_cpu_time has no deterministic GPU analogue: the iteration cap (200) bounds the solve */
+	o.max_cpu_time = runtime;   /* -r: counted in reference iterations (0.1 s each), see qtos_options.max_cpu_time */
 	if (rc == QTOS_OK) rc = qtos_solve_batch(ctx, &p, 1, &o, &r, x.data(), rows.data());
 	if (rc != QTOS_OK) { std::cerr << "qtos: " << qtos_last_error(ctx) << std::endl; qtos_destroy(ctx); return 3; }
 	lap("upload + solve + 1 kHz sampling");
 	std::cout << "Number of Iterations....: " << r.iters << std::endl;
 	std::cout << "Constraint violation....: " << r.constr_viol << std::endl;
 	std::cout << "status -> " << r.status << std::endl;
-	qtos_write_csv(rows.data(), d.csv_rows, "traj.csv");
+	if (qtos_write_csv(rows.data(), d.csv_rows, "traj.csv") != QTOS_OK) {
+		std::cerr << "qtos: cannot write traj.csv" << std::endl;
+		qtos_destroy(ctx);
+		return 3;
+	}
 	lap("traj.csv");
 	qtos_destroy(ctx);
 	lap("qtos_destroy");

@@ -11,16 +11,15 @@ the uploaded heightfields, and a thin client behind the same command line:
                                                                    runs the native `main` binary otherwise
 
 Protocol: one JSON object per connection, newline-terminated -- request {"argv": [...], "cwd": "..."} or
-{"cmd": "shutdown" | "ping"}; reply {"rc": exit code, "out": / "err": what ./main would have printed on stdout / stderr}.  Requests are served
-one at a time (a solve takes ~5 ms; the 32 PATH_MAP workers simply queue on the socket).
+{"cmd": "shutdown" | "ping"}; reply {"rc": exit code, "out": / "err": what ./main would have printed on stdout / stderr}.  Every connection
+that is already waiting when the daemon comes back to its socket is taken in the same round, and the ./main requests of a
+round are solved as ONE batch (towr_cli.towr_main_many): the 32 PATH_MAP workers cost one launch sequence, not 32.
 """
 import argparse
-import io
 import json
 import os
 import socket
 import sys
-from contextlib import redirect_stderr, redirect_stdout
 
 
 def default_socket():
@@ -62,14 +61,17 @@ def serve(sock_path=None, device=0, ready=None):
         ready()
     try:
         while True:
-            conn, _ = srv.accept()
-            with conn:
-                conn.settimeout(10.0)                        # a silent or vanished client must not stall the queue
-                try:
-                    if _serve_one(conn, towr_cli, device):
-                        return
-                except OSError:
-                    continue
+            conns = [srv.accept()[0]]
+            srv.setblocking(False)
+            try:                                             # everything that queued up meanwhile joins this round
+                while len(conns) < MAX_ROUND:
+                    conns.append(srv.accept()[0])
+            except (BlockingIOError, InterruptedError):
+                pass
+            finally:
+                srv.setblocking(True)
+            if _serve_round(conns, towr_cli, device):
+                return
     finally:
         srv.close()
         try:
@@ -78,34 +80,57 @@ def serve(sock_path=None, device=0, ready=None):
             pass
 
 
-def _serve_one(conn, towr_cli, device):
-    """one request on an accepted connection; True when it was the shutdown command."""
+MAX_ROUND = 64
+
+
+def _read_request(conn):
     buf = b""
     while not buf.endswith(b"\n"):
         chunk = conn.recv(65536)
         if not chunk:
             break
         buf += chunk
+    req = json.loads(buf.decode())
+    if not isinstance(req, dict):
+        raise ValueError("request is not a JSON object")
+    return req
+
+
+def _reply(conn, obj):
     try:
-        req = json.loads(buf.decode())
-    except ValueError:
-        conn.sendall(b'{"rc": 3, "out": "bad request"}\n')
-        return False
-    if req.get("cmd") == "shutdown":
-        conn.sendall(b'{"rc": 0, "out": "bye"}\n')
-        return True
-    if req.get("cmd") == "ping":
-        conn.sendall(b'{"rc": 0, "out": "pong"}\n')
-        return False
-    out, err = io.StringIO(), io.StringIO()
-    try:
-        with redirect_stdout(out), redirect_stderr(err):
-            rc = towr_cli.towr_main(list(req.get("argv", [])), cwd=req.get("cwd", "."), device=device)
-    except Exception as e:                       # the daemon outlives a bad request
-        rc = 3
-        err.write("qtos: %s\n" % e)
-    conn.sendall((json.dumps({"rc": int(rc), "out": out.getvalue(), "err": err.getvalue()}) + "\n").encode())
-    return False
+        conn.sendall((json.dumps(obj) + "\n").encode())
+    except OSError:
+        pass                                                 # the client went away: nobody to tell
+
+
+def _serve_round(conns, towr_cli, device):
+    """the requests of the connections accepted in one round; True when one of them was the shutdown command."""
+    shutdown = False
+    jobs = []
+    for conn in conns:
+        conn.settimeout(10.0)                                # a silent or vanished client must not stall the queue
+        try:
+            req = _read_request(conn)
+        except (OSError, ValueError):
+            _reply(conn, {"rc": 3, "out": "bad request", "err": ""})
+            conn.close()
+            continue
+        if req.get("cmd") == "shutdown":
+            _reply(conn, {"rc": 0, "out": "bye"}); conn.close(); shutdown = True
+        elif req.get("cmd") == "ping":
+            _reply(conn, {"rc": 0, "out": "pong"}); conn.close()
+        else:
+            argv = req.get("argv", [])
+            jobs.append((conn, [str(a) for a in argv] if isinstance(argv, list) else [], str(req.get("cwd", "."))))
+    if jobs:
+        try:
+            results = towr_cli.towr_main_many([(argv, cwd) for _, argv, cwd in jobs], device=device)
+        except Exception as e:                               # the daemon outlives a bad request
+            results = [(3, "", "qtos: %s\n" % e)] * len(jobs)
+        for (conn, _, _), (rc, out, err) in zip(jobs, results):
+            _reply(conn, {"rc": int(rc), "out": out, "err": err})
+            conn.close()
+    return shutdown
 
 
 if __name__ == "__main__":

@@ -97,7 +97,7 @@ def parse_main_argv(argv):
         vec3("-s_ang_vel", "start_ang_vel"); vec3("-s_vel", "start_vel")
         t = _grab(argv, "-n")
         if t is not None:
-            out["normalize"] = t[0] == "t"
+            out["normalize"] = " ".join(t) == "t"       # the reference compares the JOINED tokens (main.cpp:66,228-232): only a trailing `-n t` normalises
         else:
             out["start_vel"] = [0.0, 0.0, 0.0]          # main.cpp:237-242: no -n => start velocity zeroed
         for i in range(4):
@@ -126,13 +126,17 @@ def problem_from_args(a, hf_id=0):
 
 
 _SOLVERS = {}
-_HEIGHTFIELDS = {}
+_HEIGHTFIELDS = {}                 # insertion-ordered: (solver, path, mtime, size, resolution) -> device heightfield id
+HEIGHTFIELD_CACHE = 8              # grids kept on the device per solver of a long-lived process
+
+
+SOLVER_BATCH = 64                  # windows one cached solver takes per launch (the daemon batches queued requests)
 
 
 def _solver(combo, duration, device=0):
     key = (combo, float(duration), device)
     if key not in _SOLVERS:
-        _SOLVERS[key] = Solver(default_shape(combo, duration), device=device, max_batch=1)
+        _SOLVERS[key] = Solver(default_shape(combo, duration), device=device, max_batch=SOLVER_BATCH)
     return _SOLVERS[key]
 
 
@@ -141,28 +145,64 @@ def exit_code(status):
     return int(status) & 0xFF
 
 
+def towr_main_many(requests, device=0):
+    """`requests` = [(argv, cwd), ...] -> [(exit code, stdout text, stderr text), ...].  Every request is one `./main`
+    call; requests that share a shape and a runtime budget are solved as ONE batch (what the 32 concurrent PATH_MAP
+    workers of the reference amount to, ref: QTOS/generateHeightField.py:344-404).  traj.csv is written per request,
+    in request order, exactly where the one-by-one calls would have written it."""
+    out = [None] * len(requests)
+    groups = {}
+    for k, (argv, cwd) in enumerate(requests):
+        a = parse_main_argv(argv)
+        hf_path = os.path.join(cwd, HEIGHTFIELD_REL)
+        if not os.path.exists(hf_path):
+            # the reference prints and then reads an empty grid (UB); the replacement fails loudly
+            out[k] = (2, "", "Could not open file %s\n" % hf_path)
+            continue
+        try:
+            S = _solver(a["combo"], a["duration"], device)
+            st = os.stat(hf_path)
+            key = (id(S), os.path.abspath(hf_path), st.st_mtime_ns, st.st_size, float(a["resolution"]))
+            hid = _HEIGHTFIELDS.get(key)
+            if hid is None:         # a long-lived process (serve.py) re-reads and re-uploads only a CHANGED terrain file
+                mine = [q for q in _HEIGHTFIELDS if q[0] == id(S)]
+                busy = {g[1] for gk, gl in groups.items() if gk[0] == id(S) for g in gl}
+                if len(mine) >= HEIGHTFIELD_CACHE and _HEIGHTFIELDS[mine[0]] not in busy:
+                    S.free_heightfield(_HEIGHTFIELDS.pop(mine[0]))     # oldest grid of this solver leaves the device, its id is reused
+                grid = read_towr_heightfield(hf_path)
+                hid = _HEIGHTFIELDS[key] = S.upload_heightfield(grid, a["resolution"])
+        except Exception as e:
+            out[k] = (3, "", "qtos: %s\n" % e)
+            continue
+        # -r (max_cpu_time, ref: main.cpp:180,459-460) becomes an iteration budget, see qtos_options.max_cpu_time
+        groups.setdefault((id(S), float(a["runtime"])), []).append((k, hid, a, S, cwd))
+    for (_, runtime), members in groups.items():
+        S = members[0][3]
+        p = np.concatenate([problem_from_args(a, hid) for _, hid, a, _, _ in members])
+        try:
+            res, x, rows = S.solve(p, default_options(max_cpu_time=runtime), csv=True)
+        except Exception as e:
+            for k, *_ in members:
+                out[k] = (3, "", "qtos: %s\n" % e)
+            continue
+        for j, (k, _, _, _, cwd) in enumerate(members):
+            try:
+                write_csv(rows[j], os.path.join(cwd, TRAJ_FILE))
+            except Exception as e:
+                out[k] = (3, "", "qtos: %s\n" % e)
+                continue
+            out[k] = (exit_code(res["status"][j]),
+                      "status -> %d  iterations %d  constraint violation %.3e\n" % (res["status"][j], res["iters"][j], res["constr_viol"][j]), "")
+    return out
+
+
 def towr_main(argv, cwd=".", device=0, quiet=False):
-    a = parse_main_argv(argv)
-    hf_path = os.path.join(cwd, HEIGHTFIELD_REL)
-    if not os.path.exists(hf_path):
-        # the reference prints and then reads an empty grid (UB); the replacement fails loudly
-        sys.stderr.write("Could not open file %s\n" % hf_path)
-        return 2
-    S = _solver(a["combo"], a["duration"], device)
-    st = os.stat(hf_path)
-    key = (id(S), os.path.abspath(hf_path), st.st_mtime_ns, st.st_size, float(a["resolution"]))
-    hid = _HEIGHTFIELDS.get(key)
-    if hid is None:                 # a long-lived process (serve.py) re-reads and re-uploads only a CHANGED terrain file
-        if len(_HEIGHTFIELDS) >= 256:
-            raise RuntimeError("more than 256 distinct heightfields uploaded by one process: restart the daemon")
-        grid = read_towr_heightfield(hf_path)
-        hid = _HEIGHTFIELDS[key] = S.upload_heightfield(grid, a["resolution"])
-    p = problem_from_args(a, hid)
-    res, x, rows = S.solve(p, default_options(), csv=True)
-    write_csv(rows[0], os.path.join(cwd, TRAJ_FILE))
-    if not quiet:
-        print("status -> %d  iterations %d  constraint violation %.3e" % (res["status"][0], res["iters"][0], res["constr_viol"][0]))
-    return exit_code(res["status"][0])
+    rc, text, err = towr_main_many([(argv, cwd)], device)[0]
+    if err:
+        sys.stderr.write(err)
+    if text and not quiet:
+        sys.stdout.write(text)
+    return rc
 
 
 if __name__ == "__main__":

@@ -151,3 +151,13 @@ def test_heightfield_file_edge_cases(tmp_path):
     HF.write_heightfield(str(tmp_path / "rt.txt"), m)
     assert not open(tmp_path / "rt.txt").read().endswith("\n")
     assert np.array_equal(HF.read_towr_heightfield(str(tmp_path / "rt.txt")), m)
+
+
+def test_n_flag_compares_the_joined_tokens():
+    """main.cpp joins the (up to three) tokens after -n and compares the result with "t" (main.cpp:66,228-232): `-n t`
+    normalises only as the LAST thing on the command line; followed by another flag it reads "t -g 0.5" != "t"."""
+    from qtos_b200 import towr_cli
+    a = towr_cli.parse_main_argv(["-s", "1.0", "2.0", "0.24", "-g", "1.5", "2.0", "0.24", "-n", "t"])
+    assert a["normalize"] and a["start"][:2] == [0.0, 0.0] and a["goal"][:2] == [0.5, 0.0]
+    b = towr_cli.parse_main_argv(["-n", "t", "-s", "1.0", "2.0", "0.24", "-g", "1.5", "2.0", "0.24"])
+    assert not b["normalize"] and b["start"][:2] == [1.0, 2.0]

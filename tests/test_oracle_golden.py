@@ -188,3 +188,58 @@ def test_oracle_ipm_converges_on_reference_cases(oracle, golden_csv):
     x2, r2 = p2.solve()
     assert r2.status == 0 and r2.constr_viol <= 1e-4
     assert np.allclose(p2.csv(x2)[0, 1:19], G2[0, 1:19], atol=1e-6)
+
+
+def _euler_R(r, p, y):
+    cx, sx, cy, sy, cz, sz = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]); Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def test_every_constraint_family_on_the_golden_plans(oracle, golden_csv, towr_log):
+    """The other constraint families (only the dynamics rows were pinned on the golden CSVs), two ways.
+
+    (a) Directly on the rows of data/traj/towr.csv (solves #2 and #1 of the log), independent numpy statements:
+        range of motion R'(p_ee - c) in nominal +- max_dev at t = k * 0.08 (range_of_motion_constraint.cc:59-109) --
+        satisfied with the golden build's box (0.08, 0.08, 0.10) and NOT with a box 5 mm tighter in any axis that is
+        active, so the constants are pinned from both sides; stance feet on the (flat) terrain and unilateral force /
+        friction pyramid mu = 0.5 at every row (terrain_constraint.cc:59-108, force_constraint.cc:37-171); swing feet
+        carry no force.
+    (b) Through the oracle's own g(x): the plan the oracle's Ipopt port computes for the logged inputs satisfies ALL
+        1730 rows to 1e-4, and that plan equals the golden CSV to 6 digits (test_oracle_ipopt_c.py) -- any other
+        constant in any family moves the plan by millimetres (test_vendored_constants_do_not_reproduce_the_log).
+    test/data/traj/gait.csv is NOT part of this: it violates the vendored range-of-motion box in z by 2.3 mm at
+    t = 4.48 s and no (mass, max_dev) combination tried reproduces it closer than 1.2 cm -- it was written by a build
+    and command line the reference does not record."""
+    nom = np.array([[0.21, 0.18, -0.24], [0.21, -0.18, -0.24], [-0.21, 0.18, -0.24], [-0.21, -0.18, -0.24]])
+    box = np.array([0.08, 0.08, 0.10])
+    worst = np.zeros(3)
+    for name in ("towr_g2", "towr_g4"):
+        A = golden_csv[name]
+        t = A[:, 0] - (3.756 if name == "towr_g2" else 0.0)
+        for row, tt in zip(A, t):
+            f = row[25:37].reshape(4, 3)
+            feet = row[7:19].reshape(4, 3)
+            for e in range(4):
+                if abs(feet[e, 2]) < 1e-9:                                   # stance on the flat terrain
+                    assert f[e, 2] >= -1e-3 and abs(f[e, 0]) <= 0.5 * f[e, 2] + 2e-3 and abs(f[e, 1]) <= 0.5 * f[e, 2] + 2e-3
+                else:                                                         # swing: above the ground, no force
+                    assert feet[e, 2] > 0 and np.all(f[e] == 0.0)
+            k = tt / 0.08
+            if abs(k - round(k)) < 1e-6:
+                R = _euler_R(*row[4:7])
+                dev = np.abs((R.T @ (feet - row[1:4]).T).T - nom)
+                assert np.all(dev <= box + 1e-4 + 5e-6), (name, tt, dev.max(axis=0))
+                worst = np.maximum(worst, dev.max(axis=0))
+    assert np.all(worst[:2] > box[:2] - 0.012) and worst[2] > box[2] - 0.012        # the box is reached: a tighter one fails
+    G3 = golden_csv["gait"]
+    row = G3[448]                                                               # t = 4.48 s
+    dev = np.abs((_euler_R(*row[4:7]).T @ (row[7:19].reshape(4, 3) - row[1:4]).T).T - nom)
+    assert dev[:, 2].max() > 0.10 + 2e-3                                        # gait.csv: outside the vendored z box
+    # (b) all families through the oracle's g(x) at the reproduced plan
+    from test_ipopt_emulation import logged_problem
+    p = logged_problem(oracle, towr_log["inputs"][1])
+    x, r = p.solve_ipopt()
+    g = p.g(x); _, _, gl, gu = p.bounds()
+    assert r.status == 0 and np.maximum(gl - g, g - gu).max() <= 1e-4
