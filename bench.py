@@ -53,8 +53,15 @@ ALG_FLOP_RHS = 2.0 * 50728 * 16 + 2.0 * 605 * 16 * 16
 TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r02_traffic.json")     # ncu dram bytes per problem, written by tools/ncu_traffic.py
 
 
+SWEEP_AT_N1 = os.environ.get("QTOS_BENCH_SWEEP") == "1"     # development: the N > 1 workload on one GPU (weak-scaling reference point)
+
+
+def is_sweep(world):
+    return world > 1 or SWEEP_AT_N1
+
+
 def workload_name(world):
-    return WORKLOAD_1 if world == 1 else WORKLOAD_N
+    return WORKLOAD_N if is_sweep(world) else WORKLOAD_1
 
 
 def build_workload(n_total, seed=1234):
@@ -85,7 +92,7 @@ def cpu_sample_jobs(world, n_sample):
     solving generation 0 with the oracle first, untimed)."""
     import multiprocessing as mp
     from qtos_b200 import parallel, workloads
-    if world == 1:
+    if not is_sweep(world):
         grid, res, p = build_workload(PER_GPU)
         return [(p[i], grid, res, False) for i in range(n_sample)]
     variants = workloads.terrain_variants(N_VARIANTS)
@@ -224,7 +231,7 @@ def run_gpu(args):
 
     ctxs = [Q.Solver(Q.default_shape(COMBO, DURATION), device=local, max_batch=PER_GPU) for _ in range(IN_FLIGHT)]
     S = ctxs[0]
-    if world == 1:
+    if not is_sweep(world):
         grid, res, p_all = build_workload(n_total)
         for c in ctxs:
             hid = c.upload_heightfield(grid, res)
@@ -360,7 +367,7 @@ def run_gpu(args):
     e2e_csv = int((r_c["status"] == 0).sum()) / (time.perf_counter() - t0)
     del rows_c
     S1 = Q.Solver(Q.default_shape(COMBO, DURATION), device=local, max_batch=1)
-    if world == 1:
+    if not is_sweep(world):
         S1.upload_heightfield(grid, res)
     else:
         for g, r_ in variants:
@@ -371,7 +378,7 @@ def run_gpu(args):
     lat = sorted(lat[4:])
     S1.close()
     fast = None; s5 = None
-    if world == 1:
+    if not is_sweep(world):
         of = Q.default_options(algorithm=Q.ALG_FAST)
         S.solve(p, of)
         t0 = time.perf_counter(); rf, _, _ = S.solve(p, of); dtf = time.perf_counter() - t0
@@ -380,7 +387,7 @@ def run_gpu(args):
     fp64_peak = S.fp64_peak_tflops()
     for c in ctxs[1:]:
         c.close()
-    if world == 1:
+    if not is_sweep(world):
         S5 = Q.Solver(Q.default_shape("Custom", 5.0), device=local, max_batch=PER_GPU)
         p5 = p.copy(); p5["hf_id"] = S5.upload_heightfield(grid, res)
         S5.solve(p5[:256], opts)

@@ -35,3 +35,99 @@ def state_of_row(row):
     st["CoM_vel"] = r[18:21]
     st["CoM_vel_ang"] = r[21:24]
     return st
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Combiner on arrays.  The four functions below are the array forms of utils.look_ahead,
+# Combiner._state, Combiner._truncate_csv and Combiner.combine (ref: QTOS/utils.py:495-521, QTOS/combiner.py:78-92,125-135,
+# 245-312); `values` is always what a reader of the CSV file would hold (as_csv_values of the sampler rows, or the result
+# of an earlier combine).  tests/test_handoff.py checks them against outputs of the reference's own methods
+# (tests/golden/make_golden_handoff.py).
+
+def look_ahead_rows(values, start_time=0.0, timesteps=6000, ndigits=3):
+    """-> (index of the row the reference's reader would hand out next, stop_idx).  Raises StopIteration like the
+    reference's csv reader when the plan ends first."""
+    t = np.round(np.asarray(values)[:, 0], ndigits)
+    hit = np.flatnonzero(start_time <= t)
+    if len(hit) == 0:
+        raise StopIteration
+    stop_idx = int(hit[0]) + 1
+    nxt = stop_idx + timesteps - 1
+    if nxt - 1 > len(t):                      # the skip loop itself ran off the end of the file
+        raise StopIteration
+    return nxt, stop_idx
+
+
+def feet_in_contact(row, height_set, tol=6):
+    """Combiner.check_legs_contact on one row: every foot z, rounded to `tol` decimals, is a height of the map."""
+    return all(round(float(row[9 + 3 * e]), tol) in height_set for e in range(4))
+
+
+def combiner_state(values, last_timestep, lookahead, height_set, ndigits=3):
+    """Combiner._state: the first row at or after the look-ahead with all four feet on a terrain height (or, when the plan
+    ends first, the look-ahead row itself).  -> (state dict, next_traj_step, lookahead actually used)."""
+    values = np.asarray(values, dtype=np.float64)
+    look = lookahead
+    idx, step = look_ahead_rows(values, last_timestep, look, ndigits)
+    while True:
+        if idx >= len(values):                # StopIteration branch of the reference: start over, take the row as it is
+            look = lookahead
+            idx, step = look_ahead_rows(values, last_timestep, look, ndigits)
+            row = values[idx]
+            break
+        row = values[idx]
+        if feet_in_contact(row, height_set):
+            break
+        look += 1
+        idx += 1
+    st = state_of_row(row)
+    st = {k: [0 if abs(x) < 1e-4 else x for x in v] for k, v in st.items()}          # utils.zero_filter
+    return st, step + look - 1, look
+
+
+def truncate_rows(values, cutoff_idx, next_traj_step):
+    """Combiner._truncate_csv: pandas took row 0 as the header; iloc[start:end] of what is left."""
+    start = 0 if cutoff_idx <= 0 else cutoff_idx - 1
+    return np.asarray(values)[1:][start:next_traj_step]
+
+
+def combine_rows(current_values, new_values, cutoff_idx, next_traj_step):
+    """Combiner.combine: the kept part of the current plan followed by the new plan (whose first row went as a header).
+    The result is both `traj_plan` and the content of the file the reference writes back."""
+    return np.concatenate((truncate_rows(current_values, cutoff_idx, next_traj_step), np.asarray(new_values)[1:]), axis=0)
+
+
+class ArrayPlans:
+    """Array-backed stand-in for Combiner's two plan files.  `patch(combiner)` replaces the file-reading methods of a live
+    reference Combiner (its attributes last_timestep, lookahead_original, cutoff_idx, next_traj_step, height_set are used
+    and updated exactly as the originals do); `new_plan(rows)` is what `docker cp ... towr.csv` was."""
+
+    def __init__(self, current_rows=None):
+        self.current = None if current_rows is None else as_csv_values(current_rows)
+        self.new = None
+
+    def new_plan(self, rows):
+        self.new = as_csv_values(rows)
+
+    def promote(self):
+        """scripts/main.py:54-57: the combined plan becomes the current one"""
+        self.current = self.new
+
+    def patch(self, combiner):
+        plans = self
+
+        def _state():
+            st, nts, look = combiner_state(plans.current, combiner.last_timestep, combiner.lookahead_original, combiner.height_set)
+            combiner.lookahead = look
+            combiner.next_traj_step = nts
+            return st
+
+        def combine():
+            if combiner.cutoff_idx <= 0:
+                combiner.cutoff_idx = 0
+            out = combine_rows(plans.current, plans.new, combiner.cutoff_idx, combiner.next_traj_step)
+            combiner.traj_plan = out
+            plans.new = out
+
+        combiner._state, combiner.combine = _state, combine
+        return combiner
