@@ -563,13 +563,20 @@ kip_solve(DevTables T, DevWork W, qtos_options opt, int rc)
 	double *adx = WS(adx, npad), *cdx = WS(cdx, npad);
 	for (int i = tid; i < npad; i += KS_T) { adx[i] = z[i]; cdx[i] = z[npad + i]; }
 	double *ads = WS(ads, T.m), *advL = WS(advL, T.m), *advU = WS(advU, T.m), *cds = WS(cds, T.m), *cdvL = WS(cdvL, T.m), *cdvU = WS(cdvU, T.m);
+	/* Jd dx of both directions first (eight lanes per row), parked in the ring's shared memory (the sweeps are over), then
+	 * the row-wise expansion with one thread per row: all lanes busy, neighbouring rows read neighbouring addresses */
+	double *jd = ring;                             /* [2][n_ineq] */
 	for (int base = 0; base < T.n_ineq; base += KS_T / 8) {
 		const int idx = base + (tid >> 3);
 		const bool valid = idx < T.n_ineq;
-		const int i = valid ? T.iq_rows[idx] : 0;
 		double j0, j1;
-		row_dot2(T, Jv, z, z + npad, i, valid, j0, j1);
-		if (!valid || (tid & 7)) continue;
+		row_dot2(T, Jv, z, z + npad, valid ? T.iq_rows[idx] : 0, valid, j0, j1);
+		if (valid && (tid & 7) == 0) { jd[idx] = j0; jd[T.n_ineq + idx] = j1; }
+	}
+	__syncthreads();
+	for (int idx = tid; idx < T.n_ineq; idx += KS_T) {
+		const int i = T.iq_rows[idx];
+		const double j0 = jd[idx], j1 = jd[T.n_ineq + idx];
 		const int fl = T.row_flags[i];
 		double augA = -(-y[i] - vL[i] + vU[i]), augC = 0.0, sl = 1.0, su = 1.0;
 		if (fl & ROW_HASL) { sl = s[i] - dL[i]; augA += (-sl * vL[i]) / sl; augC += avrg_compl / sl; }
