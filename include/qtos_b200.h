@@ -165,6 +165,26 @@ int  qtos_solve_batch_async(qtos_ctx *ctx, const qtos_problem *p, int n, const q
 int  qtos_solve_batch_device_async(qtos_ctx *ctx, const qtos_problem *d_p, int n, const qtos_options *o,
                                    qtos_result *d_res, double *d_x_out);
 int  qtos_wait(qtos_ctx *ctx);
+/* Continuous batching (IPOPT algorithm): the context's max_batch workspace slots become a pool; jobs are submitted at any
+ * time and their windows enter the pool as slots fall free, so every launch of the iteration kernels works on a full pool
+ * and the last slow windows of one job run beside the fresh windows of the next (the reference's counterpart: 32 worker
+ * processes polling one queue, ref: QTOS/generateHeightField.py:344-404).  A window's result is bit-identical to the one
+ * qtos_solve_batch returns.  Host-buffer jobs hold at most max_batch windows; all buffers stay valid until the job's
+ * qtos_stream_wait returns.  Heightfields are uploaded before qtos_stream_begin. */
+typedef struct {
+	long long iterations;             /* batch iterations launched */
+	long long slot_iterations;        /* occupied slots summed over them (= problem-iterations) */
+	long long windows_done;
+	long long launches;               /* kernel launches of the session */
+	double factor_ms, solve_ms;       /* device time of k_factor / kip_solve (CUDA events on the context's stream) ... */
+	long long timed_iterations, timed_slot_iterations;   /* ... over this many iterations / problem-iterations */
+} qtos_stream_info;
+int  qtos_stream_begin(qtos_ctx *ctx, const qtos_options *o);
+int  qtos_stream_submit(qtos_ctx *ctx, const qtos_problem *p, int n, qtos_result *res, double *x_out, int *ticket);
+int  qtos_stream_submit_device(qtos_ctx *ctx, const qtos_problem *d_p, int n, qtos_result *d_res, double *d_x_out, int *ticket);
+int  qtos_stream_wait(qtos_ctx *ctx, int ticket);
+int  qtos_stream_stats(const qtos_ctx *ctx, qtos_stream_info *out);
+int  qtos_stream_end(qtos_ctx *ctx);              /* drains every submitted job, then closes the session */
 /* IPOPT algorithm: the per-iteration table Ipopt prints (ref: logs/towr_log.out:55-62), for the first n problems of the
  * last solve: trace_out = n * QTOS_TRACE_ITERS * QTOS_TRACE_COLS doubles; rows past a problem's last iteration are zero */
 int  qtos_get_trace(qtos_ctx *ctx, int n, double *trace_out);

@@ -82,6 +82,12 @@ class Dims(C.Structure):
                 ("flops_factor", C.c_double), ("workspace_bytes_per_problem", C.c_longlong)]
 
 
+class StreamInfo(C.Structure):
+    _fields_ = [("iterations", C.c_longlong), ("slot_iterations", C.c_longlong), ("windows_done", C.c_longlong),
+                ("launches", C.c_longlong), ("factor_ms", C.c_double), ("solve_ms", C.c_double),
+                ("timed_iterations", C.c_longlong), ("timed_slot_iterations", C.c_longlong)]
+
+
 class Stats(C.Structure):
     _fields_ = [("ms", C.c_float * 8), ("factorizations", C.c_longlong), ("factor_launches", C.c_longlong),
                 ("iterations", C.c_int)]
@@ -98,7 +104,8 @@ assert PROBLEM_DTYPE.itemsize == 8 * 28 + 8 and RESULT_DTYPE.itemsize == 56
 EXPORTS = ["qtos_default_shape", "qtos_default_options", "qtos_create", "qtos_destroy", "qtos_last_error",
            "qtos_get_dims", "qtos_upload_heightfield", "qtos_free_heightfield", "qtos_heightfield_query", "qtos_heightfield_cells",
            "qtos_get_initial", "qtos_eval", "qtos_solve_batch", "qtos_solve_batch_device", "qtos_solve_batch_async",
-           "qtos_solve_batch_device_async", "qtos_wait", "qtos_get_trace", "qtos_sample_csv", "qtos_sample_csv_rows",
+           "qtos_solve_batch_device_async", "qtos_wait", "qtos_stream_begin", "qtos_stream_submit", "qtos_stream_submit_device",
+           "qtos_stream_wait", "qtos_stream_stats", "qtos_stream_end", "qtos_get_trace", "qtos_sample_csv", "qtos_sample_csv_rows",
            "qtos_write_csv", "qtos_launch_count", "qtos_set_profiling", "qtos_last_stats", "qtos_stream",
            "qtos_measure_fp64_peak"]
 
@@ -130,6 +137,12 @@ def lib():
         L.qtos_solve_batch_async.argtypes = [vp, vp, C.c_int, C.POINTER(Options), vp, dp, dp]
         L.qtos_solve_batch_device_async.argtypes = [vp, vp, C.c_int, C.POINTER(Options), vp, vp]
         L.qtos_wait.argtypes = [vp]
+        L.qtos_stream_begin.argtypes = [vp, C.POINTER(Options)]
+        L.qtos_stream_submit.argtypes = [vp, vp, C.c_int, vp, dp, C.POINTER(C.c_int)]
+        L.qtos_stream_submit_device.argtypes = [vp, vp, C.c_int, vp, vp, C.POINTER(C.c_int)]
+        L.qtos_stream_wait.argtypes = [vp, C.c_int]
+        L.qtos_stream_stats.argtypes = [vp, C.POINTER(StreamInfo)]
+        L.qtos_stream_end.argtypes = [vp]
         L.qtos_get_trace.argtypes = [vp, C.c_int, dp]
         L.qtos_sample_csv.argtypes = [vp, vp, C.c_int, dp, dp]
         L.qtos_sample_csv_rows.argtypes = [vp, vp, C.c_int, dp, C.c_int, C.c_int, dp]
@@ -309,6 +322,48 @@ class Solver:
         _, res, x, _ = getattr(self, "_inflight", None) or (None, None, None, None)
         self._inflight = None
         return res, x
+
+    # ---- continuous batching: the max_batch workspace slots as a pool that jobs flow through
+    def stream_begin(self, options=None):
+        o = options if options is not None else default_options()
+        self._stream_keep = {}
+        self._ck(self._L.qtos_stream_begin(self._h, C.byref(o)))
+
+    def stream_submit(self, problems, out=None):
+        """queue a job of <= max_batch windows (host buffers); returns a ticket for stream_wait.  `out` = (results, x) as
+        in solve(); fresh arrays otherwise."""
+        p, pp = self._probs(problems)
+        n = len(p)
+        res, x = out if out is not None else (np.zeros(n, dtype=RESULT_DTYPE), np.zeros((n, self.n_vars)))
+        if res.dtype != RESULT_DTYPE or res.shape != (n,) or x.dtype != np.float64 or x.shape != (n, self.n_vars) \
+                or not res.flags.c_contiguous or not x.flags.c_contiguous:
+            raise ValueError("out must be (RESULT_DTYPE[n], float64[n, n_vars]), C-contiguous")
+        t = C.c_int(-1)
+        self._ck(self._L.qtos_stream_submit(self._h, pp, n, res.ctypes.data_as(C.c_void_p), _dp(x), C.byref(t)))
+        self._stream_keep[t.value] = (p, res, x)
+        return t.value
+
+    def stream_submit_device(self, d_problems_ptr, n, d_results_ptr, d_x_ptr):
+        t = C.c_int(-1)
+        self._ck(self._L.qtos_stream_submit_device(self._h, C.c_void_p(d_problems_ptr), int(n), C.c_void_p(d_results_ptr),
+                                                   C.c_void_p(d_x_ptr), C.byref(t)))
+        self._stream_keep[t.value] = (None, None, None)
+        return t.value
+
+    def stream_wait(self, ticket):
+        """block until every window of the job has ended; returns its (results, x) (None, None for device jobs)"""
+        self._ck(self._L.qtos_stream_wait(self._h, int(ticket)))
+        _, res, x = self._stream_keep.pop(ticket, (None, None, None))
+        return res, x
+
+    def stream_info(self):
+        s = StreamInfo()
+        self._ck(self._L.qtos_stream_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in StreamInfo._fields_}
+
+    def stream_end(self):
+        self._ck(self._L.qtos_stream_end(self._h))
+        self._stream_keep = {}
 
     def solve_device(self, d_problems_ptr, n, options=None, d_results_ptr=None, d_x_ptr=None):
         """Device-resident variant: raw device pointers (e.g. torch tensor .data_ptr())."""

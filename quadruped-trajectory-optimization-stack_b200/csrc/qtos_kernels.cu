@@ -59,9 +59,9 @@ __device__ __forceinline__ void scaled_rows(const DevTables &T, const double *sc
 __device__ __forceinline__ double qnan_fill() { return nan(""); }
 
 __global__ void __launch_bounds__(QTOS_THREADS)
-k_init(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *hfs, int n_hf, qtos_options opt, int do_solver_init)
+k_init(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *hfs, int n_hf, qtos_options opt, int do_solver_init, const int *slots)
 {
-	const int pid = blockIdx.x;
+	const int pid = slots ? slots[blockIdx.x] : blockIdx.x;      /* streaming: the workspace slots that were just refilled */
 	const qtos_problem &pr = probs[pid];
 	double *x = WS(x, T.n_all), *P = WS(P, 32), *sc = WS(sc, T.m), *r = WS(r, T.m), *Jv = WS(Jv, T.nJ);
 	__shared__ double sfin[6][3];
@@ -881,19 +881,27 @@ k_step(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *
 
 /* ------------------------------------------------------------------ results, sampler, queries */
 
-__global__ void k_results(DevTables T, DevWork W, qtos_result *res, double *x_out, int n)
+/* streaming: slot k of the list receives problem src[src_idx[k]] */
+__global__ void k_admit(const qtos_problem *src, const int *src_idx, const int *slots, qtos_problem *dst, int n)
 {
-	const int pid = blockIdx.x;
-	if (pid >= n) return;
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n) dst[slots[k]] = src[src_idx[k]];
+}
+
+/* results of workspace slot `pid` to position `out` of the caller's arrays (batch call: both are the block index) */
+__global__ void k_results(DevTables T, DevWork W, qtos_result *res, double *x_out, int n, const int *slots, const int *dst)
+{
+	if ((int)blockIdx.x >= n) return;
+	const int pid = slots ? slots[blockIdx.x] : blockIdx.x, out = dst ? dst[blockIdx.x] : blockIdx.x;
 	if (threadIdx.x == 0 && res) {
 		const double *scal = WS(scal, 16);
 		qtos_result R;
 		R.status = W.status[pid] == QTOS_RUNNING ? QTOS_MAX_ITER : W.status[pid]; R.iters = W.iters[pid];
 		R.constr_viol = scal[SC_VIOL]; R.dual_inf = scal[SC_DUAL]; R.compl_inf = scal[SC_COMPL]; R.nlp_error = scal[SC_E0]; R.mu = scal[SC_MU];
 		R.cost = 0.0;
-		res[pid] = R;
+		res[out] = R;
 	}
-	if (x_out) for (int i = threadIdx.x; i < T.n_all; i += blockDim.x) x_out[(size_t)pid * T.n_all + i] = WS(x, T.n_all)[i];
+	if (x_out) for (int i = threadIdx.x; i < T.n_all; i += blockDim.x) x_out[(size_t)out * T.n_all + i] = WS(x, T.n_all)[i];
 }
 
 /* post-hoc plan cost for best-plan selection: sum over optimised nodes of f_z^2 (force) and

@@ -472,3 +472,43 @@ def test_runtime_budget_and_async_calls(solvers):
     full = S.sample_csv(p[:3], x0[:3])
     assert rows.shape == (3, 1, 37) and np.array_equal(rows[:, 0], full[:, -1])
     assert np.array_equal(S.sample_rows(p[:3], x0[:3], 750, 2), full[:, 750:752])
+
+
+def test_continuous_batching_returns_the_batch_call_results():
+    """Streaming session: jobs flow through a pool of 64 slots that is smaller than the work queued (48 + 64 + 20 + 64
+    windows, all submitted at once); every window's plan, status and iteration count is BIT-IDENTICAL to what
+    qtos_solve_batch returns for it, whatever company it kept in the pool; the pool stays full while work is waiting."""
+    import torch
+    S = Q.Solver(Q.default_shape(*SHAPES["S2"]), max_batch=64)
+    grid, res = HF.rough_terrain(1234)
+    hid = S.upload_heightfield(grid, res)
+    p = workloads.multistart_problems(196, grid, res, hf_id=hid)
+    r0, x0, _ = S.solve(p)
+    S.stream_begin()
+    with pytest.raises(Q.QtosError, match="stream"):
+        S.solve(p[:4])                                              # the context is busy streaming
+    cuts = [(0, 48), (48, 112), (112, 132)]
+    tickets = [S.stream_submit(p[a:b]) for a, b in cuts]
+    d_p = torch.from_numpy(p[132:196].view(np.uint8).reshape(64, -1)).cuda()
+    d_res = torch.zeros((64, Q.RESULT_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+    d_x = torch.zeros((64, S.n_vars), dtype=torch.float64, device="cuda")
+    td = S.stream_submit_device(d_p.data_ptr(), 64, d_res.data_ptr(), d_x.data_ptr())
+    for t, (a, b) in reversed(list(zip(tickets, cuts))):           # waiting out of order is fine
+        r, x = S.stream_wait(t)
+        assert np.array_equal(x, x0[a:b]) and np.array_equal(r["status"], r0["status"][a:b]) and np.array_equal(r["iters"], r0["iters"][a:b])
+        assert np.array_equal(r["cost"], r0["cost"][a:b]) and np.array_equal(r["constr_viol"], r0["constr_viol"][a:b])
+    S.stream_wait(td)
+    rd = d_res.cpu().numpy().view(Q.RESULT_DTYPE).reshape(64)
+    assert np.array_equal(d_x.cpu().numpy(), x0[132:]) and np.array_equal(rd["iters"], r0["iters"][132:])
+    info = S.stream_info()
+    assert info["windows_done"] == 196 and info["slot_iterations"] >= int(r0["iters"].sum())
+    # the tail of one job rides with the next: fewer batch iterations than the four jobs need one after the other
+    serial = sum(int(r0["iters"][a:b].max()) + 1 for a, b in cuts + [(132, 196)])
+    assert info["iterations"] < serial, (info, serial)
+    t2 = S.stream_submit(p[:8])                                     # the session outlives an idle period
+    r, x = S.stream_wait(t2)
+    assert np.array_equal(x, x0[:8])
+    S.stream_end()
+    r1, x1, _ = S.solve(p[:16])                                     # and the context is a batch solver again
+    assert np.array_equal(x1, x0[:16])
+    S.close()
