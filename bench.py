@@ -17,9 +17,12 @@ the reference's algorithm (QTOS_ALG_IPOPT) to the reference's convergence criter
          variants (seeds 0..7), each window started from the final state of a previously solved plan on its
          own grid; one process per GPU (torchrun), windows sharded statically (weak scaling), one all-gather
          of per-candidate records for best-plan selection inside the timed region.
-Three batches are in flight per GPU (three solver contexts driven through the asynchronous C ABI), so the
-straggler iterations of one batch run beside the full launches of the next; `serial` in the JSON line is the
-same measurement with one batch in flight, and the per-kernel / roofline figures come from that serial pass.
+The steps run through the library's continuous-batching session (qtos_stream_*): the 4096 workspace slots of the
+context are a pool, a step is one job of 4096 windows, eight jobs are queued at a time (the slowest windows of a job take ~70 iterations, a job's bulk ~10), and the windows of the next
+job enter the pool as the windows of the current one finish -- so every launch works on a full pool and the last slow
+windows of a step do not run as a chain of near-empty launches.  `serial` in the JSON line is the same work through
+the synchronous batch call (one step at a time, stragglers exposed); the per-phase times come from that pass, the
+roofline figures from CUDA events the streaming session records around its k_factor and kip_solve launches.
 """
 import argparse
 import json
@@ -36,7 +39,7 @@ sys.path.insert(0, ROOT)
 
 PER_GPU = 4096
 GROUP = 8
-IN_FLIGHT = int(os.environ.get("QTOS_IN_FLIGHT", "3"))
+IN_FLIGHT = int(os.environ.get("QTOS_IN_FLIGHT", "8"))       # jobs queued in the streaming session
 N_VARIANTS = 8
 COMBO, DURATION = "C1", 2.0
 CPU_SAMPLE = 192
@@ -229,7 +232,7 @@ def run_gpu(args):
     n = len(idx)
     opts = Q.default_options()                               # QTOS_ALG_IPOPT
 
-    ctxs = [Q.Solver(Q.default_shape(COMBO, DURATION), device=local, max_batch=PER_GPU) for _ in range(IN_FLIGHT)]
+    ctxs = [Q.Solver(Q.default_shape(COMBO, DURATION), device=local, max_batch=PER_GPU)]
     S = ctxs[0]
     if not is_sweep(world):
         grid, res, p_all = build_workload(n_total)
@@ -243,15 +246,15 @@ def run_gpu(args):
         p0 = workloads.replan_sweep_problems(n_total, variants, hids, group_size=GROUP)[idx]
         r0, x0, _ = S.solve(p0, opts)                        # generation 0 (untimed): the plans the timed windows start from
         p = np.ascontiguousarray(workloads.replan_from_rows(p0, S.sample_rows(p0, x0, -1)[:, 0]))
-    streams = [torch.cuda.ExternalStream(c.stream, device=dev) for c in ctxs]
+    streams = [torch.cuda.ExternalStream(S.stream, device=dev)] * IN_FLIGHT
 
     # device-resident inputs/outputs for `value`; pinned host buffers for `e2e`
     d_p = torch.from_numpy(p.view(np.uint8).reshape(n, -1)).to(dev)
-    d_res = [torch.zeros((n, Q.RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev) for _ in ctxs]
-    d_x = [torch.zeros((n, S.n_vars), dtype=torch.float64, device=dev) for _ in ctxs]
+    d_res = [torch.zeros((n, Q.RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev) for _ in range(IN_FLIGHT)]
+    d_x = [torch.zeros((n, S.n_vars), dtype=torch.float64, device=dev) for _ in range(IN_FLIGHT)]
     h_p = torch.from_numpy(p.view(np.uint8).reshape(n, -1)).pin_memory()
-    h_res = [torch.empty(n * Q.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory() for _ in ctxs]
-    h_x = [torch.empty((n, S.n_vars), dtype=torch.float64).pin_memory() for _ in ctxs]
+    h_res = [torch.empty(n * Q.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory() for _ in range(IN_FLIGHT)]
+    h_x = [torch.empty((n, S.n_vars), dtype=torch.float64).pin_memory() for _ in range(IN_FLIGHT)]
     torch.cuda.synchronize()
 
     def barrier():
@@ -265,21 +268,31 @@ def run_gpu(args):
         winners, _ = parallel.select_best(rec, device=dev)
         return winners
 
-    def submit_device(k):
-        ctxs[k].solve_device_async(d_p.data_ptr(), n, opts, d_res[k].data_ptr(), d_x[k].data_ptr())
+    tickets = {}
+
+    def submit_device(k):                                    # streaming, inputs and outputs resident in HBM
+        tickets[k] = S.stream_submit_device(d_p.data_ptr(), n, d_res[k].data_ptr(), d_x[k].data_ptr())
 
     def collect_device(k):
-        ctxs[k].wait()
+        S.stream_wait(tickets.pop(k))
         r = d_res[k].cpu().numpy().view(Q.RESULT_DTYPE).reshape(n)      # 229 KB of records: the step's result
         finish(r)
         return r
 
-    def submit_host(k):
+    def submit_host(k):                                      # streaming, pinned host buffers through the public API
         pp = h_p.numpy().view(Q.PROBLEM_DTYPE).reshape(n)
-        ctxs[k].solve_async(pp, (h_res[k].numpy().view(Q.RESULT_DTYPE).reshape(n), h_x[k].numpy()), opts)
+        tickets[k] = S.stream_submit(pp, (h_res[k].numpy().view(Q.RESULT_DTYPE).reshape(n), h_x[k].numpy()))
 
     def collect_host(k):
-        r, x = ctxs[k].wait()
+        r, x = S.stream_wait(tickets.pop(k))
+        finish(r)
+        return r
+
+    def submit_serial(k):
+        S.solve_device(d_p.data_ptr(), n, opts, d_res[k].data_ptr(), d_x[k].data_ptr())
+
+    def collect_serial(k):
+        r = d_res[k].cpu().numpy().view(Q.RESULT_DTYPE).reshape(n)
         finish(r)
         return r
 
@@ -319,41 +332,44 @@ def run_gpu(args):
         return ms, float(conv)
 
     for _ in range(max(args.warmup, 3)):
-        submit_device(0); collect_device(0)
-    submit_device(1); collect_device(1)
+        submit_serial(0); collect_serial(0)
 
-    # ---- serial pass with per-kernel events (one batch in flight): phase times and the roofline figures
+    # ---- serial pass with per-kernel events (synchronous batch call, one step at a time): phase times
     prof_steps = min(args.steps, 3)
     stats = {"fact": 0, "launches": 0, "phase": {}, "iters": []}
 
     def on_prof(r, k):
-        st = ctxs[k].last_stats()
+        st = S.last_stats()
         stats["fact"] += st["factorizations"]; stats["launches"] += st["factor_launches"]
         for name, v in st["ms"].items():
             stats["phase"][name] = stats["phase"].get(name, 0.0) + v
         stats["iters"].append(r["iters"].copy())
 
     S.set_profiling(True)
-    serial_ms, serial_conv = timed(prof_steps, submit_device, collect_device, 1, on_prof)
+    serial_ms, serial_conv = timed(prof_steps, submit_serial, collect_serial, 1, on_prof)
     S.set_profiling(False)
     serial_ms, serial_conv = reduce_max_sum(serial_ms, serial_conv)
 
-    # ---- the measurement: K steps, IN_FLIGHT batches in flight, inputs resident in HBM
+    # ---- the measurement: K steps through the streaming session, IN_FLIGHT jobs queued, inputs resident in HBM
+    S.stream_begin(opts)
+    timed(IN_FLIGHT + 1, submit_device, collect_device, IN_FLIGHT)      # the pool is warm and full
     clk_path = os.path.join(tempfile.gettempdir(), "qtos_clocks_%d.csv" % rank)
     sampler = clocks_sampler(clk_path, local) if rank == 0 else None
-    launches0 = sum(c.launch_count() for c in ctxs)
+    info0 = S.stream_info()
     step_ms, conv = timed(args.steps, submit_device, collect_device, IN_FLIGHT)
-    launches = sum(c.launch_count() for c in ctxs) - launches0
+    info1 = S.stream_info()
+    launches = info1["launches"] - info0["launches"]
     if sampler is not None:
         sampler.terminate()
     step_ms, conv_all = reduce_max_sum(step_ms, conv)
     value = conv_all / args.steps / (step_ms * 1e-3)
 
     # ---- e2e: host buffers through the public API (H2D problems from pinned memory, D2H results + node values)
-    submit_host(0); collect_host(0); submit_host(1); collect_host(1)
+    timed(IN_FLIGHT, submit_host, collect_host, IN_FLIGHT)
     e_ms, conv_e = timed(args.steps, submit_host, collect_host, IN_FLIGHT)
     e_ms, conv_e_all = reduce_max_sum(e_ms, conv_e)
     e2e_value = conv_e_all / args.steps / (e_ms * 1e-3)
+    S.stream_end()
 
     if rank != 0:
         if world > 1:
@@ -385,8 +401,6 @@ def run_gpu(args):
         fast = {"value": float((rf["status"] == 0).sum() / dtf), "unit": "solves/s", "converged_fraction": float((rf["status"] == 0).mean()),
                 "note": "QTOS_ALG_FAST (sigma I Hessian, monotone mu, l1 merit): feasible plans, not Ipopt's plans; one batch in flight, host buffers"}
     fp64_peak = S.fp64_peak_tflops()
-    for c in ctxs[1:]:
-        c.close()
     if not is_sweep(world):
         S5 = Q.Solver(Q.default_shape("Custom", 5.0), device=local, max_batch=PER_GPU)
         p5 = p.copy(); p5["hf_id"] = S5.upload_heightfield(grid, res)
@@ -417,9 +431,12 @@ def run_gpu(args):
     except Exception:
         pass
     dims = S.dims
-    fact, fl = stats["fact"], max(1, stats["launches"])
     ph = {k: v / prof_steps for k, v in stats["phase"].items()}
-    f_ms, s_ms = stats["phase"].get("factor", 0.0), stats["phase"].get("solve", 0.0)
+    # roofline: the streaming session's own CUDA events around k_factor / kip_solve, over the timed steps
+    fact = info1["timed_slot_iterations"] - info0["timed_slot_iterations"]
+    fl = max(1, info1["timed_iterations"] - info0["timed_iterations"])
+    f_ms, s_ms = info1["factor_ms"] - info0["factor_ms"], info1["solve_ms"] - info0["solve_ms"]
+    pool_occupancy = (info1["slot_iterations"] - info0["slot_iterations"]) / max(1, info1["iterations"] - info0["iterations"]) / PER_GPU
     flop_fact = ALG_FLOP_FACTOR + ALG_FLOP_RHS
     achieved = fact * flop_fact / (f_ms * 1e-3) / 1e12 if f_ms > 0 else None
     # kip_solve: algorithmic bytes per problem = the factor read once per sweep (2 n_refine + 1 sweeps: stored blocks + inverses of
@@ -440,11 +457,12 @@ def run_gpu(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(world), "problems_per_gpu": PER_GPU, "parallelism": "shard%d" % world, "algorithm": "ipopt",
-                   "batches_in_flight": IN_FLIGHT,
+                   "mode": "continuous batching (qtos_stream_*): pool of %d slots, %d jobs queued" % (PER_GPU, IN_FLIGHT), "pool_occupancy": pool_occupancy,
                    "l2": "per-step working set %.1f GB per GPU > 126 MB L2" % (PER_GPU * dims.workspace_bytes_per_problem / 1e9)},
         "converged_fraction": conv_all / (args.steps * n_total), "iters_mean": float(iters.mean()), "iters_max": int(iters.max()),
         "p50_latency_ms": 1e3 * lat[len(lat) // 2], "p99_latency_ms": 1e3 * lat[-1],
-        "serial": {"value": serial_conv / prof_steps / (serial_ms * 1e-3), "ms_per_step": serial_ms, "note": "one batch in flight"},
+        "serial": {"value": serial_conv / prof_steps / (serial_ms * 1e-3), "ms_per_step": serial_ms,
+                   "note": "the same steps through the synchronous batch call, one at a time (straggler iterations exposed)"},
         "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(n * Q.PROBLEM_DTYPE.itemsize),
                 "d2h_bytes_per_step": int(n * (Q.RESULT_DTYPE.itemsize + 8 * S.n_vars)), "ms_per_step": e_ms,
                 "returns": "per-window status records + spline node values (the plan); the reference's 1 kHz CSV rows are sampled on demand",
@@ -458,7 +476,7 @@ def run_gpu(args):
                                      "FP64 FMA rate as the bounding roofline, and B200's FP64 tensor and FMA peaks coincide",
                      "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (achieved / fp64_peak) if achieved else None,
                      "peak_source": "FP64 FMA loop measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
-                     "alg_flop_per_factorization": flop_fact, "factorizations_per_step": fact / prof_steps,
+                     "alg_flop_per_factorization": flop_fact, "factorizations_per_step": fact / args.steps,
                      "avg_launch_ms": f_ms / fl,
                      "traffic": (tr_f * fact / fl) if tr_f else None,
                      "traffic_source": "profiles/r02_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 4096-problem launch) x problems per average launch",
