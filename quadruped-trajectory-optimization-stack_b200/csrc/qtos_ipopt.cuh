@@ -25,6 +25,33 @@
 
 /* ------------------------------------------------------------------ kip_prepare */
 
+/* (J' wa)_i and (J' wb)_i together for permuted variable i over a term table (see jt_gather): the column is read once */
+__device__ __forceinline__ void jt_gather2(const int *ptr, const uint2_t *tab, const double *Jv, const double *wa, const double *wb, int i, double &ga, double &gb)
+{
+	const int g = i >> 5, base = ptr[g], ns = (ptr[g + 1] - base) >> 5;
+	const uint2 *tk = reinterpret_cast<const uint2 *>(tab) + base + (i & 31);
+	double a0 = 0.0, a1 = 0.0;
+	for (int s = 0; s < ns; s += 2) {
+		uint2 d[2];
+		double c[2][6], u[2][6], w[2][6];
+#pragma unroll
+		for (int q = 0; q < 2; ++q) d[q] = s + q < ns ? __ldg(tk + 32 * (s + q)) : make_uint2(0u, 0u);
+#pragma unroll
+		for (int q = 0; q < 2; ++q) {
+			const int nr = d[q].x >> 20;
+			const double *col = Jv + (d[q].x & 0xfffffu), *pa = wa + d[q].y, *pb = wb + d[q].y;
+#pragma unroll
+			for (int rr = 0; rr < 6; ++rr) { c[q][rr] = rr < nr ? col[rr] : 0.0; u[q][rr] = rr < nr ? pa[rr] : 0.0; w[q][rr] = rr < nr ? pb[rr] : 0.0; }
+		}
+#pragma unroll
+		for (int q = 0; q < 2; ++q)
+#pragma unroll
+			for (int rr = 0; rr < 6; ++rr) { a0 += c[q][rr] * u[q][rr]; a1 += c[q][rr] * w[q][rr]; }
+	}
+	ga = a0; gb = a1;
+}
+
+
 __global__ void __launch_bounds__(QTOS_THREADS, PREP_MINB)
 kip_prepare(DevTables T, DevWork W, qtos_options opt)
 {
@@ -162,7 +189,9 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt)
 	__syncthreads();
 	/* ---- right-hand-side block: columns 0..5 sigma S, 6..11 Y (chronological, unused ones zero), 12 affine, 13 centering */
 	for (int i = tid; i < T.npad; i += blockDim.x) {
-		const double va = -glx[i] + jt_gather(T, Jv, wA, i), vc = jt_gather(T, Jv, wC, i);
+		double ga, vc;
+		jt_gather2(T.jg_ptr, T.jg, Jv, wA, wC, i, ga, vc);          /* both right-hand sides from one pass over the columns */
+		const double va = -glx[i] + ga;
 		double *o = RB + (size_t)(i >> 4) * 256 + (i & 15);
 #pragma unroll
 		for (int a = 0; a < IP_LM; ++a) {
@@ -398,32 +427,6 @@ __device__ inline void lu12_solve(const double *A, const int *piv, double *b)
 	for (int k = 0; k < n; ++k) { const double t = b[k]; b[k] = b[piv[k]]; b[piv[k]] = t; }
 	for (int k = 0; k < n; ++k) for (int i = k + 1; i < n; ++i) b[i] -= A[i * n + k] * b[k];
 	for (int k = n - 1; k >= 0; --k) { for (int j = k + 1; j < n; ++j) b[k] -= A[k * n + j] * b[j]; b[k] /= A[k * n + k]; }
-}
-
-/* (J' wa)_i and (J' wb)_i together for permuted variable i over a term table (see jt_gather): the column is read once */
-__device__ __forceinline__ void jt_gather2(const int *ptr, const uint2_t *tab, const double *Jv, const double *wa, const double *wb, int i, double &ga, double &gb)
-{
-	const int g = i >> 5, base = ptr[g], ns = (ptr[g + 1] - base) >> 5;
-	const uint2 *tk = reinterpret_cast<const uint2 *>(tab) + base + (i & 31);
-	double a0 = 0.0, a1 = 0.0;
-	for (int s = 0; s < ns; s += 2) {
-		uint2 d[2];
-		double c[2][6], u[2][6], w[2][6];
-#pragma unroll
-		for (int q = 0; q < 2; ++q) d[q] = s + q < ns ? __ldg(tk + 32 * (s + q)) : make_uint2(0u, 0u);
-#pragma unroll
-		for (int q = 0; q < 2; ++q) {
-			const int nr = d[q].x >> 20;
-			const double *col = Jv + (d[q].x & 0xfffffu), *pa = wa + d[q].y, *pb = wb + d[q].y;
-#pragma unroll
-			for (int rr = 0; rr < 6; ++rr) { c[q][rr] = rr < nr ? col[rr] : 0.0; u[q][rr] = rr < nr ? pa[rr] : 0.0; w[q][rr] = rr < nr ? pb[rr] : 0.0; }
-		}
-#pragma unroll
-		for (int q = 0; q < 2; ++q)
-#pragma unroll
-			for (int rr = 0; rr < 6; ++rr) { a0 += c[q][rr] * u[q][rr]; a1 += c[q][rr] * w[q][rr]; }
-	}
-	ga = a0; gb = a1;
 }
 
 /* (J z0)_row and (J z1)_row: eight lanes share a row (columns strided), all 32 lanes of the warp call it together */
