@@ -88,6 +88,11 @@ typedef struct {
 	                                     Wall-clock limits are not deterministic on a batched device, so the budget is counted in
 	                                     iterations: floor(max_cpu_time / QTOS_REF_SECONDS_PER_ITERATION), i.e. the iterations the
 	                                     reference itself completes in that time; reaching it returns QTOS_MAX_CPUTIME */
+	double lm_init_val_min;           /* IPOPT: Ipopt's limited_memory_init_val_min, the floor of the L-BFGS scalar sigma_w; 0 = Ipopt's 1e-8 */
+	int    retry_failed;              /* IPOPT: 1 (default) = a window whose filter line search fails (where Ipopt would enter its
+	                                     restoration phase) is restarted once from x0 with lm_init_val_min = retry_lm_init_val_min;
+	                                     its iteration count is the sum of both attempts.  0 = report -2 at once */
+	double retry_lm_init_val_min;     /* 1e-2 */
 } qtos_options;
 #define QTOS_REF_SECONDS_PER_ITERATION 0.1   /* 0.75-0.88 s for 7-8 iterations, ref: logs/towr_log.out:64,81-82 */
 
@@ -178,6 +183,7 @@ typedef struct {
 	long long launches;               /* kernel launches of the session */
 	double factor_ms, solve_ms;       /* device time of k_factor / kip_solve (CUDA events on the context's stream) ... */
 	long long timed_iterations, timed_slot_iterations;   /* ... over this many iterations / problem-iterations */
+	long long retried;                /* windows that needed the second attempt (qtos_options.retry_failed) */
 } qtos_stream_info;
 int  qtos_stream_begin(qtos_ctx *ctx, const qtos_options *o);
 int  qtos_stream_submit(qtos_ctx *ctx, const qtos_problem *p, int n, qtos_result *res, double *x_out, int *ticket);
@@ -203,6 +209,7 @@ typedef struct {
 	long long factorizations;         /* problems factored, summed over the iterations of the last solve */
 	long long factor_launches;        /* k_factor launches of the last solve */
 	int iterations;                   /* batch iterations of the last solve */
+	int retried;                      /* windows that needed the second attempt (qtos_options.retry_failed) */
 } qtos_stats;
 long long qtos_launch_count(const qtos_ctx *ctx);  /* kernel launches issued by this context so far */
 int  qtos_set_profiling(qtos_ctx *ctx, int on);

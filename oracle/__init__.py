@@ -60,7 +60,8 @@ class IpmResult(C.Structure):
 class IpoptOptions(C.Structure):
     _fields_ = [("tol", C.c_double), ("constr_viol_tol", C.c_double), ("compl_inf_tol", C.c_double),
                 ("dual_inf_tol", C.c_double), ("max_iter", C.c_int), ("delta_c", C.c_double),
-                ("n_refine", C.c_int), ("lm_history", C.c_int), ("verbose", C.c_int), ("sigma_floor", C.c_double)]
+                ("n_refine", C.c_int), ("lm_history", C.c_int), ("verbose", C.c_int), ("sigma_floor", C.c_double),
+                ("retry_failed", C.c_int), ("retry_sigma_floor", C.c_double)]
 
 
 class IpoptResult(C.Structure):
@@ -70,7 +71,7 @@ class IpoptResult(C.Structure):
                 ("tr_inf_pr", C.c_double * 256), ("tr_inf_du", C.c_double * 256), ("tr_mu", C.c_double * 256),
                 ("tr_dnorm", C.c_double * 256), ("tr_alpha_pr", C.c_double * 256), ("tr_alpha_du", C.c_double * 256),
                 ("tr_ls", C.c_int * 256), ("tr_pairs", C.c_int * 256), ("tr_free", C.c_int * 256),
-                ("tr_tag", C.c_char * 256), ("chol_fix", C.c_int), ("n_regularized", C.c_int)]
+                ("tr_tag", C.c_char * 256), ("chol_fix", C.c_int), ("n_regularized", C.c_int), ("retried", C.c_int)]
 
 
 def build(force=False):

@@ -43,6 +43,7 @@ void orc_ipopt_default_options(orc_ipopt_options *o)
 	o->lm_history = 6;
 	o->sigma_floor = 0.0;
 	o->verbose = 0;
+	o->retry_failed = 1; o->retry_sigma_floor = 1e-2;
 }
 
 static double dmax(double a, double b) { return a > b ? a : b; }
@@ -158,7 +159,7 @@ static double frac_to_bound(int m, const unsigned char *hasL, const unsigned cha
 	return al;
 }
 
-int orc_ipopt_solve(orc_problem *p, const orc_ipopt_options *o, double *x, orc_ipopt_result *res)
+static int ipopt_attempt(orc_problem *p, const orc_ipopt_options *o, double *x, orc_ipopt_result *res)
 {
 	const int na = p->n, m = p->m;
 	memset(res, 0, sizeof(*res));
@@ -536,4 +537,25 @@ int orc_ipopt_solve(orc_problem *p, const orc_ipopt_options *o, double *x, orc_i
 	free(Sm); free(Ym); free(Bl); free(Z); free(iseq); free(hasL); free(hasU);
 	orc_free_struct(S);
 	return status;
+}
+
+/* One attempt, and -- like the CUDA product (qtos_options.retry_failed) -- a second one from the same x0 with Ipopt's
+ * limited_memory_init_val_min raised to retry_sigma_floor when the filter line search of the first fails (status -2, where
+ * Ipopt would enter its restoration phase).  The iteration count is the sum of both attempts. */
+int orc_ipopt_solve(orc_problem *p, const orc_ipopt_options *o, double *x, orc_ipopt_result *res)
+{
+	double *x0 = (double *)malloc(sizeof(double) * p->n);
+	memcpy(x0, x, sizeof(double) * p->n);
+	int st = ipopt_attempt(p, o, x, res);
+	if (st == -2 && o->retry_failed && o->sigma_floor < o->retry_sigma_floor) {
+		const int first = res->iters;
+		orc_ipopt_options o2 = *o;
+		o2.sigma_floor = o->retry_sigma_floor;
+		memcpy(x, x0, sizeof(double) * p->n);
+		st = ipopt_attempt(p, &o2, x, res);
+		res->iters += first;
+		res->retried = 1;
+	}
+	free(x0);
+	return st;
 }

@@ -167,6 +167,8 @@ typedef struct {
 	int    lm_history;        /* limited_memory_max_history 6 */
 	int    verbose;
 	double sigma_floor;       /* lower bound of the limited-memory scalar sigma_w (0: Ipopt's 1e-8) */
+	int    retry_failed;      /* 1: a second attempt with sigma_floor = retry_sigma_floor after a failed line search */
+	double retry_sigma_floor; /* 1e-2 */
 } orc_ipopt_options;
 
 typedef struct {
@@ -179,6 +181,7 @@ typedef struct {
 	char tr_tag[ORC_TRACE_MAX];
 	int chol_fix;
 	int n_regularized;        /* factorizations repeated with W + delta_w I */
+	int retried;              /* the second attempt ran */
 } orc_ipopt_result;
 
 void orc_ipopt_default_options(orc_ipopt_options *o);

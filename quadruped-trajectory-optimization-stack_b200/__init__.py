@@ -68,7 +68,8 @@ class Options(C.Structure):
     _fields_ = [("tol", C.c_double), ("constr_viol_tol", C.c_double), ("compl_inf_tol", C.c_double),
                 ("dual_inf_tol", C.c_double), ("max_iter", C.c_int), ("mu_init", C.c_double),
                 ("sigma_w", C.c_double), ("delta_c", C.c_double), ("feas_exit", C.c_int),
-                ("algorithm", C.c_int), ("n_refine", C.c_int), ("lm_history", C.c_int), ("max_cpu_time", C.c_double)]
+                ("algorithm", C.c_int), ("n_refine", C.c_int), ("lm_history", C.c_int), ("max_cpu_time", C.c_double),
+                ("lm_init_val_min", C.c_double), ("retry_failed", C.c_int), ("retry_lm_init_val_min", C.c_double)]
 
 
 ALG_IPOPT, ALG_FAST = 0, 1          # qtos_options.algorithm
@@ -85,12 +86,12 @@ class Dims(C.Structure):
 class StreamInfo(C.Structure):
     _fields_ = [("iterations", C.c_longlong), ("slot_iterations", C.c_longlong), ("windows_done", C.c_longlong),
                 ("launches", C.c_longlong), ("factor_ms", C.c_double), ("solve_ms", C.c_double),
-                ("timed_iterations", C.c_longlong), ("timed_slot_iterations", C.c_longlong)]
+                ("timed_iterations", C.c_longlong), ("timed_slot_iterations", C.c_longlong), ("retried", C.c_longlong)]
 
 
 class Stats(C.Structure):
     _fields_ = [("ms", C.c_float * 8), ("factorizations", C.c_longlong), ("factor_launches", C.c_longlong),
-                ("iterations", C.c_int)]
+                ("iterations", C.c_int), ("retried", C.c_int)]
 
 
 # numpy mirrors of qtos_problem / qtos_result (C layout, checked against ctypes sizes below)
@@ -410,7 +411,7 @@ class Solver:
         self._L.qtos_last_stats(self._h, C.byref(st))
         names = ["init", "jac", "prepare", "assemble", "factor", "step", "solve"]
         return {"ms": dict(zip(names, list(st.ms)[:7])), "factorizations": st.factorizations,
-                "factor_launches": st.factor_launches, "iterations": st.iterations}
+                "factor_launches": st.factor_launches, "iterations": st.iterations, "retried": st.retried}
 
     def fp64_peak_tflops(self):
         v = C.c_double()

@@ -73,7 +73,7 @@ struct DevWork {
 /* IPOPT algorithm state per problem (doubles) */
 enum { IP_MU = 0, IP_TAU, IP_FREE, IP_MU_MAX, IP_AMU_THMIN, IP_TH_MAX, IP_TH_MIN, IP_SIGMA_W, IP_NPAIRS, IP_SKIPPED, IP_HAVE_LAST,
        IP_NFILTER, IP_SIGMA_F, IP_AVRG, IP_ERR, IP_THETA, IP_GL2, IP_PR2, IP_ALPHA_PR, IP_ALPHA_DU, IP_DNORM, IP_LS, IP_TAG,
-       IP_HEAD, IP_ITER, IP_RETRY, IP_DELTA_W, IP_DELTA_LAST, IP_FPHI = 32, IP_FTH = 64, IP_MID = 96, IP_N = 256 };
+       IP_HEAD, IP_ITER, IP_RETRY, IP_DELTA_W, IP_DELTA_LAST, IP_SIGMA_MIN, IP_ITER_BASE, IP_FPHI = 32, IP_FTH = 64, IP_MID = 96, IP_N = 256 };
 #define IP_FILTER_MAX 32
 #define IP_LM 6                             /* limited-memory history capacity */
 #define IP_NRHS 16                          /* right-hand sides of the factorization: 6 S + 6 Y columns, affine, centering, 2 spare */

@@ -116,7 +116,7 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt)
 	const bool stop = !retry && (invalid || conv || it >= opt.max_iter || out_of_time);
 	if (tid == 0 && !retry) {
 		scal[SC_DUAL] = dual_inf; scal[SC_THETA] = primal_inf; scal[SC_COMPL] = compl_; scal[SC_VIOL] = viol; scal[SC_E0] = nlp_error; scal[SC_MU] = mu;
-		W.iters[pid] = it;
+		W.iters[pid] = (int)ip[IP_ITER_BASE] + it;
 		if (it < QTOS_TRACE_ITERS) {
 			double *tr = WS(trace, QTOS_TRACE_ITERS * QTOS_TRACE_COLS) + it * QTOS_TRACE_COLS;
 			tr[0] = viol; tr[1] = dual_inf; tr[2] = mu; tr[3] = ip[IP_DNORM]; tr[4] = ip[IP_ALPHA_DU]; tr[5] = ip[IP_ALPHA_PR]; tr[6] = ip[IP_LS]; tr[7] = ip[IP_TAG];
@@ -146,7 +146,8 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt)
 	if (new_slot >= 0) {
 		for (int i = tid; i < T.npad; i += blockDim.x) { lmS[(size_t)new_slot * T.npad + i] = tS[i]; lmY[(size_t)new_slot * T.npad + i] = tY[i]; }
 	}
-	const double sigma_f = sigma_w + delta_w;         /* diagonal of M; the limited-memory columns keep sigma_w (W + delta_w I) */
+	const double sigma_b = fmax(sigma_w, ip[IP_SIGMA_MIN]);   /* limited_memory_init_val_min above Ipopt's 1e-8 (second attempts) */
+	const double sigma_f = sigma_b + delta_w;         /* diagonal of M; the limited-memory columns keep sigma_b (W + delta_w I) */
 
 	/* ---- barrier parameter, part one (AdaptiveMuUpdate::UpdateBarrierParameter): mode switches and the fixed-mode update;
 	 *      the free-mode oracle needs the two directions and runs in kip_step */
@@ -196,7 +197,7 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt)
 #pragma unroll
 		for (int a = 0; a < IP_LM; ++a) {
 			const int sl = (head + a) % hist;
-			o[a * 16] = a < n_pairs ? sigma_w * lmS[(size_t)sl * T.npad + i] : 0.0;
+			o[a * 16] = a < n_pairs ? sigma_b * lmS[(size_t)sl * T.npad + i] : 0.0;
 			o[(IP_LM + a) * 16] = a < n_pairs ? lmY[(size_t)sl * T.npad + i] : 0.0;
 		}
 		o[12 * 16] = i < T.n_free ? va : 0.0; o[13 * 16] = i < T.n_free ? vc : 0.0; o[14 * 16] = 0.0; o[15 * 16] = 0.0;
@@ -216,7 +217,7 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt)
 		const int a = ra % IP_LM, b = cb % IP_LM;
 		double val = 0.0;
 		if (a < n_pairs && b < n_pairs) {
-			if (ra < IP_LM && cb < IP_LM) val = sigma_w * sdots[a * IP_LM + b];
+			if (ra < IP_LM && cb < IP_LM) val = sigma_b * sdots[a * IP_LM + b];
 			else if (ra < IP_LM) val = a > b ? sdots[IP_LM * IP_LM + a * IP_LM + b] : 0.0;              /* L[a][b] */
 			else if (cb < IP_LM) val = b > a ? sdots[IP_LM * IP_LM + b * IP_LM + a] : 0.0;              /* L'[a][b] = L[b][a] */
 			else val = a == b ? -sdots[IP_LM * IP_LM + a * IP_LM + a] : 0.0;

@@ -82,6 +82,9 @@ k_init(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *
 	/* do_solver_init: 0 = x0 only (qtos_get_initial / qtos_eval); 1 = x0, g(x0), constant Jacobian elements, problem
 	 * marked running -- the x-dependent elements then come from k_jac_dyn / k_jac_rom (one thread per sample instead
 	 * of one block per problem); 2 = row scaling from J(x0), scaled J, slacks and multipliers */
+	/* 3 = 1 for the second attempt of a window (qtos_options.retry_failed): the iterations spent so far are kept */
+	const bool restart = do_solver_init == 3;
+	if (restart) do_solver_init = 1;
 	if (do_solver_init == 2) goto scaling;
 	if (threadIdx.x == 0) {
 		for (int d = 0; d < 3; ++d) {
@@ -118,7 +121,7 @@ k_init(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *
 	__syncthreads();
 	eval_g_block(T, hf, x, r);
 	for (int i = threadIdx.x; i < T.nJ; i += blockDim.x) Jv[i] = T.Jconst[i];
-	if (threadIdx.x == 0) { W.status[pid] = QTOS_RUNNING; W.iters[pid] = 0; W.flags[pid] = 0; }
+	if (threadIdx.x == 0) { W.status[pid] = QTOS_RUNNING; W.iters[pid] = restart ? W.iters[pid] : 0; W.flags[pid] = 0; }
 	return;
 scaling:
 	/* gradient-based row scaling min(1, 100/||row||_inf) at x0 */
@@ -168,8 +171,10 @@ scaling:
 	if (opt.algorithm == QTOS_ALG_IPOPT) {
 		/* AdaptiveMuUpdate::InitializeImpl, LimMemQuasiNewtonUpdater (limited_memory_init_val 1), empty filters */
 		double *ip = WS(ipst, IP_N), *tr = WS(trace, QTOS_TRACE_ITERS * QTOS_TRACE_COLS);
+		const double base = (double)W.iters[pid];          /* 0, or the iterations of the first attempt */
 		for (int i = threadIdx.x; i < IP_N; i += blockDim.x)
-			ip[i] = i == IP_MU || i == IP_FREE || i == IP_SIGMA_W ? 1.0 : (i == IP_MU_MAX || i == IP_TH_MAX || i == IP_TH_MIN ? -1.0 : (i == IP_AMU_THMIN ? 1e300 : 0.0));
+			ip[i] = i == IP_MU || i == IP_FREE || i == IP_SIGMA_W ? 1.0 : (i == IP_MU_MAX || i == IP_TH_MAX || i == IP_TH_MIN ? -1.0 : (i == IP_AMU_THMIN ? 1e300 :
+			        (i == IP_SIGMA_MIN ? opt.lm_init_val_min : (i == IP_ITER_BASE ? base : 0.0))));
 		for (int i = threadIdx.x; i < QTOS_TRACE_ITERS * QTOS_TRACE_COLS; i += blockDim.x) tr[i] = 0.0;
 	}
 }
