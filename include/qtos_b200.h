@@ -215,6 +215,10 @@ long long qtos_launch_count(const qtos_ctx *ctx);  /* kernel launches issued by 
 int  qtos_set_profiling(qtos_ctx *ctx, int on);
 int  qtos_last_stats(const qtos_ctx *ctx, qtos_stats *st);
 void *qtos_stream(const qtos_ctx *ctx);            /* cudaStream_t the context launches on */
+/* measurement behind DESIGN.md section 4: the heightfield queries of n_groups evaluations (group_size <= 64 queries each)
+ * answered from global memory and from a shared-memory tile filled by 1-D bulk asynchronous copies (TMA unit) */
+int  qtos_measure_heightfield_staging(qtos_ctx *ctx, int hf_id, const double *xy, int n_groups, int group_size,
+                                      double *ms_direct, double *ms_staged, double *max_diff, int *fallbacks);
 /* FP64 FMA throughput of the device measured with a register-resident FMA loop, TFLOP/s */
 int  qtos_measure_fp64_peak(qtos_ctx *ctx, double *tflops);
 

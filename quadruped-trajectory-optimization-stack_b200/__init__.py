@@ -108,7 +108,7 @@ EXPORTS = ["qtos_default_shape", "qtos_default_options", "qtos_create", "qtos_de
            "qtos_solve_batch_device_async", "qtos_wait", "qtos_stream_begin", "qtos_stream_submit", "qtos_stream_submit_device",
            "qtos_stream_wait", "qtos_stream_stats", "qtos_stream_end", "qtos_get_trace", "qtos_sample_csv", "qtos_sample_csv_rows",
            "qtos_write_csv", "qtos_launch_count", "qtos_set_profiling", "qtos_last_stats", "qtos_stream",
-           "qtos_measure_fp64_peak"]
+           "qtos_measure_fp64_peak", "qtos_measure_heightfield_staging"]
 
 _LIB = None
 
@@ -155,6 +155,7 @@ def lib():
         L.qtos_stream.argtypes = [vp]
         L.qtos_stream.restype = vp
         L.qtos_measure_fp64_peak.argtypes = [vp, dp]
+        L.qtos_measure_heightfield_staging.argtypes = [vp, C.c_int, dp, C.c_int, C.c_int, dp, dp, dp, C.POINTER(C.c_int)]
         _LIB = L
     return _LIB
 
@@ -412,6 +413,15 @@ class Solver:
         names = ["init", "jac", "prepare", "assemble", "factor", "step", "solve"]
         return {"ms": dict(zip(names, list(st.ms)[:7])), "factorizations": st.factorizations,
                 "factor_launches": st.factor_launches, "iterations": st.iterations, "retried": st.retried}
+
+    def measure_heightfield_staging(self, hf_id, xy, group_size):
+        """xy [n_groups * group_size, 2]: ms per launch answering from global memory / from a bulk-copied shared-memory tile,
+        the largest difference of the answers, groups that did not fit the tile"""
+        xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+        a, b, d, f = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+        self._ck(self._L.qtos_measure_heightfield_staging(self._h, int(hf_id), _dp(xy), len(xy) // group_size, int(group_size),
+                                                          C.byref(a), C.byref(b), C.byref(d), C.byref(f)))
+        return {"ms_direct": a.value, "ms_staged": b.value, "max_diff": d.value, "fallbacks": f.value}
 
     def fp64_peak_tflops(self):
         v = C.c_double()

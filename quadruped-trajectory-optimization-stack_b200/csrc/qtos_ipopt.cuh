@@ -816,4 +816,72 @@ kip_step(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield
 	}
 }
 
+/* ------------------------------------------------------------------ heightfield tile staging (measurement only)
+ *
+ * north_star asks for heightfield tiles "staged through TMA/shared memory".  The product reads the four corner heights of a
+ * query straight from global memory (read-only path): an evaluation makes ~50-100 queries scattered over the <= 1 m^2 a window
+ * covers.  These two kernels measure the alternative on exactly that access pattern -- one CTA per GROUP of queries (the
+ * queries of one evaluation): k_height_group reads global memory, k_height_staged first brings the bounding box of the group's
+ * cells into shared memory with one 1-D bulk asynchronous copy per grid row (TMA unit, mbarrier completion) and then answers
+ * from there with the same bit-exact arithmetic.  qtos_measure_heightfield_staging times both. */
+__global__ void k_height_group(DevHeightfield hf, const double *xy, int group, double *h_out)
+{
+	const int q = blockIdx.x * group + threadIdx.x;
+	if ((int)threadIdx.x < group) h_out[q] = qtos_height(hf, xy[2 * q], xy[2 * q + 1]);
+}
+
+#define HS_MAX_ROWS 72
+#define HS_MAX_COLS 80
+__global__ void k_height_staged(DevHeightfield hf, const double *xy, int group, double *h_out, int *fallbacks)
+{
+	__shared__ __align__(16) double tile[HS_MAX_ROWS * HS_MAX_COLS];
+	__shared__ long long box[4];
+	__shared__ uint64_t bar;
+	const int tid = threadIdx.x, q = blockIdx.x * group + tid;
+	long long c[4] = {0, 0, 0, 0};
+	double x = 0.0, y = 0.0;
+	if (tid < group) { x = xy[2 * q]; y = xy[2 * q + 1]; qtos_height_cell(hf, x, y, c); }
+	/* bounding box of the group's cells (warp shuffles + one shared-memory round for two warps) */
+	long long lo0 = tid < group ? c[0] : (1LL << 40), hi0 = tid < group ? c[2] : -1, lo1 = tid < group ? c[1] : (1LL << 40), hi1 = tid < group ? c[3] : -1;
+	for (int o = 16; o > 0; o >>= 1) {
+		lo0 = min(lo0, __shfl_xor_sync(0xffffffffu, lo0, o)); hi0 = max(hi0, __shfl_xor_sync(0xffffffffu, hi0, o));
+		lo1 = min(lo1, __shfl_xor_sync(0xffffffffu, lo1, o)); hi1 = max(hi1, __shfl_xor_sync(0xffffffffu, hi1, o));
+	}
+	__shared__ long long part[2][4];
+	if ((tid & 31) == 0) { part[tid >> 5][0] = lo0; part[tid >> 5][1] = hi0; part[tid >> 5][2] = lo1; part[tid >> 5][3] = hi1; }
+	if (tid == 0) mbar_init(&bar, 1);
+	__syncthreads();
+	if (tid == 0) {
+		const int nw = (blockDim.x + 31) >> 5;
+		long long a = part[0][0], b = part[0][1], cc = part[0][2], d = part[0][3];
+		for (int w = 1; w < nw; ++w) { a = min(a, part[w][0]); b = max(b, part[w][1]); cc = min(cc, part[w][2]); d = max(d, part[w][3]); }
+		cc &= ~1LL;                                        /* 16-byte aligned row starts */
+		long long cols = ((d - cc + 1) + 1) & ~1LL;         /* and sizes */
+		if (cc + cols > hf.ny) cols = (hf.ny - cc) & ~1LL;
+		box[0] = a; box[1] = b - a + 1; box[2] = cc; box[3] = cols;
+		const bool fits = box[1] <= HS_MAX_ROWS && cols <= HS_MAX_COLS && cols > 0 && d < cc + cols && (hf.ny & 1) == 0;
+		if (!fits) { box[3] = 0; atomicAdd(fallbacks, 1); }
+		else {
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			mbar_expect_tx(&bar, (unsigned)(box[1] * cols * 8));
+			for (long long r = 0; r < box[1]; ++r) bulk_g2s(tile + r * cols, hf.h + (a + r) * hf.ny + cc, (unsigned)(cols * 8), &bar);
+		}
+	}
+	__syncthreads();
+	if (box[3] == 0) { if (tid < group) h_out[q] = qtos_height(hf, x, y); return; }
+	mbar_wait(&bar, 0u);
+	if (tid >= group) return;
+	const long long cols = box[3];
+	const double res = hf.res;
+	const double x0 = __dadd_rn(__dmul_rn((double)c[0], res), -1.0), x1 = __dadd_rn(__dmul_rn((double)c[2], res), -1.0);
+	const double y0 = __dadd_rn(__dmul_rn((double)c[1], res), -1.0), y1 = __dadd_rn(__dmul_rn((double)c[3], res), -1.0);
+	const double z00 = tile[(c[0] - box[0]) * cols + (c[1] - box[2])], z01 = tile[(c[0] - box[0]) * cols + (c[3] - box[2])];
+	const double z10 = tile[(c[2] - box[0]) * cols + (c[1] - box[2])], z11 = tile[(c[2] - box[0]) * cols + (c[3] - box[2])];
+	const double sxy = __ddiv_rn(1.0, __dmul_rn(res, res));
+	const double u0 = __dmul_rn(sxy, __dsub_rn(x1, x)), u1 = __dmul_rn(sxy, __dsub_rn(x, x0));
+	const double w0 = __dadd_rn(__dmul_rn(u0, z00), __dmul_rn(u1, z10));
+	const double w1 = __dadd_rn(__dmul_rn(u0, z01), __dmul_rn(u1, z11));
+	h_out[q] = __dadd_rn(__dmul_rn(w0, __dsub_rn(y1, y)), __dmul_rn(w1, __dsub_rn(y, y0)));
+}
+
 #endif
