@@ -247,6 +247,7 @@ def run_gpu(args):
         r0, x0, _ = S.solve(p0, opts)                        # generation 0 (untimed): the plans the timed windows start from
         p = np.ascontiguousarray(workloads.replan_from_rows(p0, S.sample_rows(p0, x0, -1)[:, 0]))
     streams = [torch.cuda.ExternalStream(S.stream, device=dev)] * IN_FLIGHT
+    p_all_groups = n_total // GROUP                          # group ids are dense over the whole job: 8 candidates per group
 
     # device-resident inputs/outputs for `value`; pinned host buffers for `e2e`
     d_p = torch.from_numpy(p.view(np.uint8).reshape(n, -1)).to(dev)
@@ -273,11 +274,15 @@ def run_gpu(args):
     def submit_device(k):                                    # streaming, inputs and outputs resident in HBM
         tickets[k] = S.stream_submit_device(d_p.data_ptr(), n, d_res[k].data_ptr(), d_x[k].data_ptr())
 
+    d_group = torch.from_numpy(np.ascontiguousarray(p["group"], dtype=np.int32)).to(dev)
+    n_groups = int(p_all_groups)
+
     def collect_device(k):
         S.stream_wait(tickets.pop(k))
-        r = d_res[k].cpu().numpy().view(Q.RESULT_DTYPE).reshape(n)      # 229 KB of records: the step's result
-        finish(r)
-        return r
+        # the step's result: best plan per group, selected on the device (k_records -> all-gather -> k_select), 32 KB of winners
+        win = parallel.select_best_device(S, d_res[k], d_group, rank, world, n_groups).cpu()
+        assert int((win < 0).sum()) == 0
+        return d_res[k].cpu().numpy().view(Q.RESULT_DTYPE).reshape(n)     # statuses / iteration counts for the line's statistics
 
     def submit_host(k):                                      # streaming, pinned host buffers through the public API
         pp = h_p.numpy().view(Q.PROBLEM_DTYPE).reshape(n)

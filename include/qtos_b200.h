@@ -191,6 +191,12 @@ int  qtos_stream_submit_device(qtos_ctx *ctx, const qtos_problem *d_p, int n, qt
 int  qtos_stream_wait(qtos_ctx *ctx, int ticket);
 int  qtos_stream_stats(const qtos_ctx *ctx, qtos_stream_info *out);
 int  qtos_stream_end(qtos_ctx *ctx);              /* drains every submitted job, then closes the session */
+/* Best-plan selection, the one exchange step of the path (multi-start candidates of the same window compete).  A record is five
+ * doubles (group, not converged, cost, violation, global id); the winner of a group is the lexicographic minimum of the last
+ * four.  qtos_make_records builds this rank's records on the device (candidate i gets id0 + id_stride * i), the caller
+ * all-gathers them (NCCL), qtos_select_best returns the winning id of every group in [0, n_groups) (-1: no candidate). */
+int  qtos_make_records(qtos_ctx *ctx, const qtos_result *d_res, const int *d_group, long long id0, long long id_stride, int n, double *d_rec);
+int  qtos_select_best(qtos_ctx *ctx, const double *d_rec, int n_rec, int n_groups, long long *d_winner);
 /* IPOPT algorithm: the per-iteration table Ipopt prints (ref: logs/towr_log.out:55-62), for the first n problems of the
  * last solve: trace_out = n * QTOS_TRACE_ITERS * QTOS_TRACE_COLS doubles; rows past a problem's last iteration are zero */
 int  qtos_get_trace(qtos_ctx *ctx, int n, double *trace_out);

@@ -106,7 +106,7 @@ EXPORTS = ["qtos_default_shape", "qtos_default_options", "qtos_create", "qtos_de
            "qtos_get_dims", "qtos_upload_heightfield", "qtos_free_heightfield", "qtos_heightfield_query", "qtos_heightfield_cells",
            "qtos_get_initial", "qtos_eval", "qtos_solve_batch", "qtos_solve_batch_device", "qtos_solve_batch_async",
            "qtos_solve_batch_device_async", "qtos_wait", "qtos_stream_begin", "qtos_stream_submit", "qtos_stream_submit_device",
-           "qtos_stream_wait", "qtos_stream_stats", "qtos_stream_end", "qtos_get_trace", "qtos_sample_csv", "qtos_sample_csv_rows",
+           "qtos_stream_wait", "qtos_stream_stats", "qtos_stream_end", "qtos_make_records", "qtos_select_best", "qtos_get_trace", "qtos_sample_csv", "qtos_sample_csv_rows",
            "qtos_write_csv", "qtos_launch_count", "qtos_set_profiling", "qtos_last_stats", "qtos_stream",
            "qtos_measure_fp64_peak", "qtos_measure_heightfield_staging"]
 
@@ -144,6 +144,8 @@ def lib():
         L.qtos_stream_wait.argtypes = [vp, C.c_int]
         L.qtos_stream_stats.argtypes = [vp, C.POINTER(StreamInfo)]
         L.qtos_stream_end.argtypes = [vp]
+        L.qtos_make_records.argtypes = [vp, vp, vp, C.c_longlong, C.c_longlong, C.c_int, vp]
+        L.qtos_select_best.argtypes = [vp, vp, C.c_int, C.c_int, vp]
         L.qtos_get_trace.argtypes = [vp, C.c_int, dp]
         L.qtos_sample_csv.argtypes = [vp, vp, C.c_int, dp, dp]
         L.qtos_sample_csv_rows.argtypes = [vp, vp, C.c_int, dp, C.c_int, C.c_int, dp]
@@ -366,6 +368,14 @@ class Solver:
     def stream_end(self):
         self._ck(self._L.qtos_stream_end(self._h))
         self._stream_keep = {}
+
+    def make_records(self, d_results_ptr, d_group_ptr, id0, id_stride, n, d_rec_ptr):
+        """selection records of n device-resident results (see qtos_make_records); d_group: int32, d_rec: float64 [n, 5]"""
+        self._ck(self._L.qtos_make_records(self._h, C.c_void_p(d_results_ptr), C.c_void_p(d_group_ptr), int(id0), int(id_stride), int(n), C.c_void_p(d_rec_ptr)))
+
+    def select_best(self, d_rec_ptr, n_rec, n_groups, d_winner_ptr):
+        """winning global id per group (int64 [n_groups] on the device) of n_rec gathered records"""
+        self._ck(self._L.qtos_select_best(self._h, C.c_void_p(d_rec_ptr), int(n_rec), int(n_groups), C.c_void_p(d_winner_ptr)))
 
     def solve_device(self, d_problems_ptr, n, options=None, d_results_ptr=None, d_x_ptr=None):
         """Device-resident variant: raw device pointers (e.g. torch tensor .data_ptr())."""

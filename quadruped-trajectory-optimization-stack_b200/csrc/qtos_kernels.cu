@@ -968,6 +968,55 @@ __global__ void k_height(DevHeightfield hf, const double *xy, int n, double *h_o
 	if (idx_out) { long long c[4]; qtos_height_cell(hf, xy[2 * i], xy[2 * i + 1], c); for (int q = 0; q < 4; ++q) idx_out[4 * i + q] = c[q]; }
 }
 
+/* ------------------------------------------------------------------ best-plan selection (the one exchange step of the path)
+ *
+ * A record = 5 doubles (group, not converged, cost, violation, global id).  The winner of a group is the lexicographic minimum of
+ * (not converged, cost, violation, id) -- identical on every rank and for every GPU count.  k_records builds the records of this
+ * rank's results on the device (non-finite metrics of a status -13 window become +inf); after the all-gather k_select finds the
+ * winners: one CTA, one key after the other over the still-tied candidates, per-group minima by 64-bit atomicMin on the
+ * order-preserving integer image of the doubles (deterministic: a minimum does not depend on the order of the atomics). */
+__device__ __forceinline__ unsigned long long ord_of(double x)
+{
+	const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+	return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ord_inv(unsigned long long o)
+{
+	return __longlong_as_double((long long)((o >> 63) ? (o & 0x7fffffffffffffffull) : ~o));
+}
+
+__global__ void k_records(const qtos_result *res, const int *group, long long id0, long long id_stride, int n, double *rec)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const qtos_result R = res[i];
+	const double inf = __longlong_as_double(0x7ff0000000000000ll);
+	double *r = rec + 5 * (size_t)i;
+	r[0] = (double)group[i];
+	r[1] = R.status != 0 ? 1.0 : 0.0;
+	r[2] = R.cost == R.cost ? R.cost : inf;
+	r[3] = R.constr_viol == R.constr_viol ? R.constr_viol : inf;
+	r[4] = (double)(id0 + id_stride * i);
+}
+
+__global__ void __launch_bounds__(1024)
+k_select(const double *rec, int n_rec, int n_groups, unsigned long long *best, unsigned char *tied, long long *winner)
+{
+	const int tid = threadIdx.x;
+	for (int i = tid; i < n_rec; i += blockDim.x) { const int g = (int)rec[5 * (size_t)i]; tied[i] = g >= 0 && g < n_groups; }
+	for (int col = 1; col <= 4; ++col) {
+		for (int g = tid; g < n_groups; g += blockDim.x) best[g] = ~0ull;
+		__threadfence_block(); __syncthreads();
+		for (int i = tid; i < n_rec; i += blockDim.x)
+			if (tied[i]) atomicMin(&best[(int)rec[5 * (size_t)i]], ord_of(rec[5 * (size_t)i + col]));
+		__threadfence_block(); __syncthreads();
+		for (int i = tid; i < n_rec; i += blockDim.x)
+			if (tied[i] && ord_of(rec[5 * (size_t)i + col]) != best[(int)rec[5 * (size_t)i]]) tied[i] = 0;
+		__syncthreads();
+	}
+	for (int g = tid; g < n_groups; g += blockDim.x) winner[g] = best[g] == ~0ull ? -1 : (long long)ord_inv(best[g]);
+}
+
 /* test/parity entry: g(x) and dense Jacobian at caller-provided x (fixed entries of x are overwritten) */
 __global__ void __launch_bounds__(QTOS_THREADS)
 k_eval_dense(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *hfs, int n_hf,

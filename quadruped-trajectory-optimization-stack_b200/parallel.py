@@ -91,3 +91,23 @@ def select_best(rec_local, device=None):
     grp, win = argmin_per_group_torch(out)
     gw = torch.stack((grp, win)).cpu().numpy()
     return dict(zip(gw[0].tolist(), gw[1].tolist())), out
+
+
+def select_best_device(solver, d_res, d_group, rank, world, n_groups):
+    """The selection without a host round trip: records from the device-resident results (k_records), one all-gather over
+    NCCL, winners by the library's hand-written kernel (k_select).  d_res: uint8 [n, sizeof(qtos_result)], d_group: int32 [n]
+    with dense group ids in [0, n_groups); candidate i of this rank has global id rank + world * i (shard_indices).
+    Returns the winning global ids as an int64 tensor [n_groups] on the device (-1 for an empty group)."""
+    n = d_res.shape[0]
+    dev = d_res.device
+    rec = torch.empty((n, 5), dtype=torch.float64, device=dev)
+    solver.make_records(d_res.data_ptr(), d_group.data_ptr(), rank, world, n, rec.data_ptr())      # synchronises the solver's stream
+    if dist.is_available() and dist.is_initialized() and world > 1:
+        allrec = torch.empty((world * n, 5), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allrec, rec)
+        torch.cuda.current_stream(dev).synchronize()           # the solver's kernels run on its own stream
+    else:
+        allrec = rec
+    win = torch.empty(n_groups, dtype=torch.int64, device=dev)
+    solver.select_best(allrec.data_ptr(), allrec.shape[0], n_groups, win.data_ptr())
+    return win

@@ -536,3 +536,29 @@ def test_second_attempt_rescues_failed_line_searches(solvers, oracle):
         po = oracle_problem(oracle, so, p[i], grid, res)
         xo, ro = po.solve_ipopt()
         assert ro.status == 0
+
+
+def test_device_side_selection_equals_the_sorted_reference():
+    """k_records + k_select (the hand-written selection kernels) against parallel.argmin_per_group_sorted on records with ties
+    on every key, non-converged groups, NaN metrics (status -13) and an empty group."""
+    import torch
+    from qtos_b200 import parallel
+    S = Q.Solver(Q.default_shape(*SHAPES["S2"]), max_batch=1)
+    rng = np.random.default_rng(3)
+    n, n_groups = 5000, 700
+    r = np.zeros(n, dtype=Q.RESULT_DTYPE)
+    r["status"] = rng.choice([0, 0, 0, -1, -2, -13], n)
+    r["cost"] = np.round(rng.uniform(0, 3, n), 1)                       # many exact ties
+    r["constr_viol"] = np.round(rng.uniform(0, 1e-4, n), 5)
+    bad = r["status"] == -13
+    r["cost"][bad] = np.nan; r["constr_viol"][bad] = np.nan
+    group = rng.integers(0, n_groups - 1, n).astype(np.int32)           # group n_groups - 1 stays empty
+    group[:40] = 5; r["status"][:40] = -1                                # a group where nobody converged
+    d_res = torch.from_numpy(r.view(np.uint8).reshape(n, -1)).cuda()
+    d_group = torch.from_numpy(group).cuda()
+    win = parallel.select_best_device(S, d_res, d_group, rank=3, world=8, n_groups=n_groups).cpu().numpy()
+    want = parallel.argmin_per_group_sorted(parallel.make_records(r, 3 + 8 * np.arange(n), group))
+    assert win[n_groups - 1] == -1 and len(want) == n_groups - 1
+    for g, w in want.items():
+        assert win[g] == w, (g, win[g], w)
+    S.close()
