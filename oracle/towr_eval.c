@@ -381,6 +381,13 @@ void orc_eval_g(orc_problem *p, const double *x, double *g)
 			for (int d = 0; d < 3; ++d) g[row0 + 3 * j + d] = a0[d] - a1[d];
 		}
 	}
+	/* base motion (optional), ref: src/base_motion_constraint.cc:60-66: rows AX AY AZ = Euler angles, LX LY LZ = position */
+	for (int k = 0; k < p->n_brom; ++k) {
+		double b[3], e[3];
+		spline_point(&p->base_lin, p->t_brom[k], b, NULL, NULL);
+		spline_point(&p->base_ang, p->t_brom[k], e, NULL, NULL);
+		for (int d = 0; d < 3; ++d) { g[p->row_base_rom + 6 * k + d] = e[d]; g[p->row_base_rom + 6 * k + 3 + d] = b[d]; }
+	}
 	/* range of motion, ref: src/range_of_motion_constraint.cc:59-69 */
 	for (int ee = 0; ee < ORC_NEE; ++ee)
 		for (int k = 0; k < p->n_rom; ++k) {
@@ -543,6 +550,18 @@ void orc_eval_jac(orc_problem *p, const double *x, double *J, unsigned char *mas
 				for (int q = 0; q < a1.n; ++q) jadd(&o, row0 + 3 * j + dim, a1.col[q], -a1.v[q]);
 			}
 	}
+	/* base motion (optional), ref: src/base_motion_constraint.cc:76-86: GetJacobianWrtNodes(t, kPos) of both base splines */
+	for (int k = 0; k < p->n_brom; ++k)
+		for (int w = 0; w < 2; ++w) {
+			const orc_spline *s = w ? &p->base_lin : &p->base_ang;
+			int id; double tl;
+			locate(s, p->t_brom[k], &id, &tl);
+			for (int dim = 0; dim < 3; ++dim) {
+				jrow jr;
+				spline_jac_row(s, id, tl, kPos, dim, &jr);
+				for (int q = 0; q < jr.n; ++q) jadd(&o, p->row_base_rom + 6 * k + 3 * w + dim, jr.col[q], jr.v[q]);
+			}
+		}
 	/* range of motion, ref: src/range_of_motion_constraint.cc:85-109 */
 	for (int ee = 0; ee < ORC_NEE; ++ee)
 		for (int k = 0; k < p->n_rom; ++k) {

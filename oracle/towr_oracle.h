@@ -58,6 +58,10 @@ typedef struct {
 	/* gait + horizon, ref: src/main.cpp:299-306,424-433 */
 	int    combo;
 	double duration;
+	/* optional BaseMotionConstraint (Parameters::BaseRom, off on the reference's path), ref: src/base_motion_constraint.cc:38-93,
+	 * src/parameters.cc:51: rows appended after the swing sets, dt = duration_base_polynomial / 4 */
+	int    base_rom;
+	double dt_base_rom;
 } orc_shape;
 
 typedef struct {
@@ -94,6 +98,8 @@ typedef struct orc_problem {
 	    row_rom[ORC_NEE], row_force[ORC_NEE], row_swing[ORC_NEE];
 	int n_dyn, n_rom;         /* sample counts */
 	double *t_dyn, *t_rom;
+	int row_base_rom, n_brom; /* BaseMotionConstraint rows (6 per sample: AX AY AZ LX LY LZ), -1 / 0 when off */
+	double *t_brom;
 } orc_problem;
 
 /* ---- problem construction (towr_problem.c) ---- */

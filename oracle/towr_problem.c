@@ -259,6 +259,7 @@ void orc_default_shape(orc_shape *s)
 	s->ee_polys_per_swing = 2;
 	s->dt_dynamic = 0.1;
 	s->dt_rom = 0.08;
+	s->base_rom = 0; s->dt_base_rom = 0.1 / 4.0;
 	s->combo = ORC_CUSTOM;
 	s->duration = 5.0;
 }
@@ -376,6 +377,11 @@ orc_problem *orc_problem_create(const orc_shape *shape, const orc_instance *inst
 		for (int nd = 0; nd < p->ee_motion[ee].n_nodes; ++nd) cnt += !is_const_node(&p->ee_motion[ee], nd);
 		p->row_swing[ee] = row; row += 4 * cnt;
 	}
+	p->row_base_rom = -1; p->n_brom = 0; p->t_brom = NULL;
+	if (shape->base_rom) {                                   /* appended like constraints_.push_back(BaseRom) would */
+		p->t_brom = make_times(p->T, shape->dt_base_rom, &p->n_brom);
+		p->row_base_rom = row; row += 6 * p->n_brom;
+	}
 	p->m = row;
 	p->gl = (double *)calloc(p->m, sizeof(double));
 	p->gu = (double *)calloc(p->m, sizeof(double));
@@ -403,6 +409,14 @@ orc_problem *orc_problem_create(const orc_shape *shape, const orc_instance *inst
 			p->gl[r] = 0.0;       p->gu[r] = ORC_INF; r++;
 		}
 	}
+	/* BaseMotionConstraint bounds, ref: src/base_motion_constraint.cc:47-57: roll, pitch within +-0.01 rad, yaw and x, y free,
+	 * z within [z_init - 0.02, z_init + 0.1], z_init = the base spline's initial height */
+	for (int k = 0; k < p->n_brom; ++k) {
+		double *lo = p->gl + p->row_base_rom + 6 * k, *hi = p->gu + p->row_base_rom + 6 * k;
+		lo[0] = lo[1] = -0.01; hi[0] = hi[1] = 0.01;
+		lo[2] = lo[3] = lo[4] = -ORC_INF; hi[2] = hi[3] = hi[4] = ORC_INF;
+		lo[5] = inst->start_pos[2] - 0.02; hi[5] = inst->start_pos[2] + 0.1;
+	}
 	return p;
 }
 
@@ -411,7 +425,7 @@ void orc_problem_free(orc_problem *p)
 	if (!p) return;
 	spline_free(&p->base_lin); spline_free(&p->base_ang);
 	for (int ee = 0; ee < ORC_NEE; ++ee) { spline_free(&p->ee_motion[ee]); spline_free(&p->ee_force[ee]); }
-	free(p->x0); free(p->xl); free(p->xu); free(p->gl); free(p->gu); free(p->t_dyn); free(p->t_rom);
+	free(p->x0); free(p->xl); free(p->xu); free(p->gl); free(p->gu); free(p->t_dyn); free(p->t_rom); free(p->t_brom);
 	free(p);
 }
 
