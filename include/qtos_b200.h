@@ -54,6 +54,11 @@ typedef struct {
 	double dt_rom;
 	int    combo;                     /* QTOS_C0 .. QTOS_CUSTOM */
 	double duration;
+	int    base_rom;                  /* 1: add TOWR's optional BaseMotionConstraint (Parameters::BaseRom, off on the reference's path;
+	                                     ref: base_motion_constraint.cc:38-93) after the swing sets: roll, pitch within +-0.01 rad and
+	                                     z(t) - z(0) within [-0.02, 0.1] at every dt_base_rom; yaw, x, y rows are kept unbounded like the
+	                                     reference's.  The z row is stated relative to the start height, so its bounds are the shape's */
+	double dt_base_rom;               /* duration_base_polynomial / 4 (ref: parameters.cc:51) */
 } qtos_shape;
 
 /* one local-plan window = the flags of ./main (ref: main.cpp:163-306) */

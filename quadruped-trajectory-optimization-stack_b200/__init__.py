@@ -61,7 +61,8 @@ class Shape(C.Structure):
                 ("mu", C.c_double), ("force_limit", C.c_double), ("t_swing_avg", C.c_double),
                 ("dt_base_poly", C.c_double), ("force_polys_per_stance", C.c_int),
                 ("ee_polys_per_swing", C.c_int), ("dt_dynamic", C.c_double),
-                ("dt_rom", C.c_double), ("combo", C.c_int), ("duration", C.c_double)]
+                ("dt_rom", C.c_double), ("combo", C.c_int), ("duration", C.c_double),
+                ("base_rom", C.c_int), ("dt_base_rom", C.c_double)]
 
 
 class Options(C.Structure):

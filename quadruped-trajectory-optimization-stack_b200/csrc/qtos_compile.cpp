@@ -328,6 +328,15 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 		int cnt = 0; for (int nd = 0; nd < spl[2 + ee].n_nodes(); ++nd) cnt += !spl[2 + ee].const_node(nd);
 		row_swing[ee] = row; H->row_off[ro++] = row; row += 4 * cnt;
 	}
+	/* optional BaseMotionConstraint (Parameters::BaseRom; ref: base_motion_constraint.cc:38-93), appended like
+	 * constraints_.push_back(BaseRom) would: six rows per sample, AX AY AZ LX LY LZ */
+	std::vector<double> t_brom;
+	const int row_brom = row;
+	if (sh.base_rom) {
+		if (!(sh.dt_base_rom > 0.0)) return fail("dt_base_rom must be positive");
+		t_brom = sample_times(T, sh.dt_base_rom);
+		H->row_off[ro++] = row; row += 6 * (int)t_brom.size();
+	}
 	H->row_off[ro] = row;
 	const int m = row;
 	H->m = m;
@@ -514,6 +523,24 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 			r += 4;
 		}
 	}
+	/* base motion (ref: base_motion_constraint.cc:47-86): rows AX, AY = roll, pitch within +-0.01 rad; AZ, LX, LY unbounded; LZ within
+	 * [z_init - 0.02, z_init + 0.1] with z_init the base spline's initial height.  The bounds of a shape are shared by all its
+	 * problems, so the LZ row is stated as z(t) - z(0) in [-0.02, 0.1]: z(0) is the (fixed) start-height variable */
+	for (size_t k = 0; k < t_brom.size(); ++k)
+		for (int w = 0; w < 2; ++w) {               /* w = 0: angular rows first (AX AY AZ), then linear */
+			const int sp = w ? 0 : 1;
+			int id; double tl, wt[4];
+			locate(spl[sp].dur, t_brom[k], &id, &tl);
+			hermite_weights(spl[sp].dur[id], tl, 0, wt);
+			for (int d = 0; d < 3; ++d) {
+				LinRow lr; lr.row = row_brom + 6 * (int)k + 3 * w + d;
+				for (int q = 0; q < 4; ++q) lin_add(lr, H->var_off[sp] + (id + q / 2) * 6 + (q % 2) * 3 + d, wt[q]);
+				if (w == 1 && d == 2) { lin_add(lr, H->var_off[0] + 2, -1.0); H->gl[lr.row] = -0.02; H->gu[lr.row] = 0.1; }
+				else if (w == 0 && d < 2) { H->gl[lr.row] = -0.01; H->gu[lr.row] = 0.01; }
+				else { H->gl[lr.row] = -INF; H->gu[lr.row] = INF; }
+				lin.push_back(lr); const_elem({lr});
+			}
+		}
 	for (int r = 0; r < m; ++r) if (H->row_elem[r] < 0) return fail("internal: row without element");
 	/* row flags */
 	H->row_flags.assign(m, 0); H->n_eq = H->n_ineq = H->n_bounds = 0;

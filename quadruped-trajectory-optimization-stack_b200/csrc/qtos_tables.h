@@ -79,7 +79,7 @@ struct HostTables {
 	double flops_factor = 0;
 	int max_nodes = 0;             /* leading dimension of node_var */
 	int n_nodes[10] = {0}, n_polys[10] = {0}, var_off[11] = {0};
-	int row_off[20] = {0};
+	int row_off[24] = {0};
 	/* splines: 0 base-lin, 1 base-ang, 2..5 foot motion, 6..9 foot force */
 	std::vector<double> dur[10];
 	std::vector<int16_t> node_var;          /* [10][max_nodes][6] full variable index or -1 */

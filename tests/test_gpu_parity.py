@@ -562,3 +562,41 @@ def test_device_side_selection_equals_the_sorted_reference():
     for g, w in want.items():
         assert win[g] == w, (g, win[g], w)
     S.close()
+
+
+def test_base_motion_constraint_option(oracle):
+    """qtos_shape.base_rom: TOWR's optional BaseMotionConstraint (Parameters::BaseRom, base_motion_constraint.cc:38-93; SURVEY 8f rank 3,
+    the part that does not need duration variables).  82 samples x 6 rows are appended after the swing sets; values, bounds and
+    Jacobian equal the oracle's (the z row is stated relative to the fixed start height, so value and bounds shift together),
+    and the solves agree with the oracle's Ipopt port."""
+    sh = Q.default_shape("C1", 2.0); sh.base_rom = 1
+    so = oracle.default_shape("C1", 2.0); so.base_rom = 1
+    S = Q.Solver(sh, max_batch=8)
+    assert S.n_cons == 892 + 82 * 6
+    grid, res = HF.rough_terrain(7)
+    hid = S.upload_heightfield(grid, res)
+    p = workloads.multistart_problems(8, grid, res, seed=7, hf_id=hid)
+    x0, xl, xu, gl, gu = S.initial(p)
+    rng = np.random.default_rng(0)
+    for i in range(2):
+        po = oracle_problem(oracle, so, p[i], grid, res)
+        oxl, oxu, ogl, ogu = po.bounds()
+        x = x0[i] + 0.02 * rng.standard_normal(S.n_vars); x[oxl == oxu] = oxl[oxl == oxu]
+        g, J = S.eval(p[i:i + 1], x[None])
+        og, oJ = po.g(x), po.jac(x); oJ[:, oxl == oxu] = 0
+        shift = np.zeros(S.n_cons); shift[892 + 5::6] = p["start_pos"][i, 2]          # the LZ rows
+        assert np.abs(g[0] + shift - og).max() < G_TOL and np.abs(J[0] - oJ).max() < J_TOL
+        assert np.allclose(np.clip(gl[i], -1e20, 1e20) + shift, ogl, atol=1e-15) and np.allclose(np.clip(gu[i], -1e20, 1e20) + shift, ogu, atol=1e-15)
+    r, x, rows = S.solve(p, csv=True)
+    close = 0
+    for i in range(8):
+        po = oracle_problem(oracle, so, p[i], grid, res)
+        xo, ro = po.solve_ipopt()
+        assert r["status"][i] == ro.status
+        if ro.status == 0:
+            assert r["constr_viol"][i] <= 1e-4
+            roll_pitch = np.abs(rows[i][::25, 4:6]).max(); dz = rows[i][::25, 3] - p["start_pos"][i, 2]
+            assert roll_pitch <= 0.01 + 1e-4 and dz.min() >= -0.02 - 1e-4 and dz.max() <= 0.1 + 1e-4      # the constraint holds at its samples
+        close += int(r["iters"][i] == ro.iters and np.abs(rows[i][:, 1:19] - po.csv(xo)[:, 1:19]).max() < TRAJ_TOL_M)
+    assert (r["status"] == 0).sum() >= 6 and close >= 6
+    S.close()

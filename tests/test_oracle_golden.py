@@ -243,3 +243,22 @@ def test_every_constraint_family_on_the_golden_plans(oracle, golden_csv, towr_lo
     x, r = p.solve_ipopt()
     g = p.g(x); _, _, gl, gu = p.bounds()
     assert r.status == 0 and np.maximum(gl - g, g - gu).max() <= 1e-4
+
+
+def test_optional_base_motion_constraint(oracle):
+    """Parameters::BaseRom (off on the reference's path; base_motion_constraint.cc:38-93, parameters.cc:51): row count
+    6 x (floor(T / 0.025) + 2) appended after the swing sets, bounds as in the constructor, Jacobian = finite differences."""
+    sh = oracle.default_shape("Custom", 5.0); sh.base_rom = 1
+    p = oracle.Problem(sh, oracle.make_instance(start_pos=(0.1, 0.0, 0.26)), oracle.Terrain(np.zeros((300, 300)), 0.02))
+    assert p.m == 1730 + 6 * 202
+    _, _, gl, gu = p.bounds()
+    blk_lo, blk_hi = gl[1730:1736], gu[1730:1736]
+    assert list(blk_lo[:2]) == [-0.01, -0.01] and list(blk_hi[:2]) == [0.01, 0.01] and np.all(blk_lo[2:5] <= -1e19) and np.all(blk_hi[2:5] >= 1e19)
+    assert abs(blk_lo[5] - 0.24) < 1e-15 and abs(blk_hi[5] - 0.36) < 1e-15
+    x = p.x0() + 0.01 * np.random.default_rng(2).standard_normal(p.n)
+    J, g = p.jac(x), p.g(x)
+    assert np.allclose(g[1730 + 6 * 40 + 3:1730 + 6 * 40 + 6], p.csv(x)[1000, 1:4])        # sample 40 = t = 1.0 s: base position
+    assert np.allclose(g[1730 + 6 * 40:1730 + 6 * 40 + 3], p.csv(x)[1000, 4:7])            # and Euler angles
+    for c in (3, 100, 309, 400):
+        xp, xm = x.copy(), x.copy(); xp[c] += 1e-6; xm[c] -= 1e-6
+        assert np.abs((p.g(xp) - p.g(xm)) / 2e-6 - J[:, c])[1730:].max() < 1e-8
