@@ -30,7 +30,7 @@ class Shape(C.Structure):
                 ("dt_base_poly", C.c_double), ("force_polys_per_stance", C.c_int),
                 ("ee_polys_per_swing", C.c_int), ("dt_dynamic", C.c_double),
                 ("dt_rom", C.c_double), ("combo", C.c_int), ("duration", C.c_double),
-                ("base_rom", C.c_int), ("dt_base_rom", C.c_double)]
+                ("base_rom", C.c_int), ("dt_base_rom", C.c_double), ("terrain_gradients", C.c_int)]
 
 
 class Instance(C.Structure):
@@ -101,6 +101,7 @@ def lib():
         L.orc_height.restype = C.c_double
         L.orc_height.argtypes = [C.POINTER(Heightfield), C.c_double, C.c_double]
         L.orc_height_cell.argtypes = [C.POINTER(Heightfield), C.c_double, C.c_double, C.POINTER(C.c_longlong)]
+        L.orc_height_deriv.argtypes = [C.POINTER(Heightfield), C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.orc_eval_g.argtypes = [C.c_void_p, dp, dp]
         L.orc_eval_jac.argtypes = [C.c_void_p, dp, dp, C.POINTER(C.c_ubyte)]
         L.orc_csv_rows.argtypes = [C.c_void_p, C.c_double]

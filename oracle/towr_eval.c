@@ -343,6 +343,19 @@ static void dyn_update(orc_problem *p, double t, dyn_state *d)
 	mat3_mul(d->ang.R, Ib, RI); mat3_T(d->ang.R, Rt); mat3_mul(RI, Rt, d->Iw);
 }
 
+
+/* contact basis at a foothold, ref: src/height_map.cc:95-141 (GetNormalizedBasis of Normal, Tangent1, Tangent2); with the
+ * reference's zero height derivatives this is (ez, ex, ey) */
+static void contact_basis(const orc_problem *p, double x, double y, double n[3], double t1[3], double t2[3])
+{
+	double hx = 0.0, hy = 0.0;
+	if (p->shape.terrain_gradients) orc_height_deriv(&p->hf, x, y, &hx, &hy);
+	const double nn = sqrt(hx * hx + hy * hy + 1.0), n1 = sqrt(1.0 + hx * hx), n2 = sqrt(1.0 + hy * hy);
+	n[0] = -hx / nn; n[1] = -hy / nn; n[2] = 1.0 / nn;
+	t1[0] = 1.0 / n1; t1[1] = 0.0; t1[2] = hx / n1;
+	t2[0] = 0.0; t2[1] = 1.0 / n2; t2[2] = hy / n2;
+}
+
 void orc_eval_g(orc_problem *p, const double *x, double *g)
 {
 	orc_set_x(p, x);
@@ -406,7 +419,12 @@ void orc_eval_g(orc_problem *p, const double *x, double *g)
 		int row = p->row_force[ee];
 		for (int nd = 0; nd < s->n_nodes; ++nd) {
 			if (is_const_node(s, nd)) continue;
-			const double n[3] = {-0.0, -0.0, 1.0}, t1[3] = {1.0, 0.0, 0.0}, t2[3] = {0.0, 1.0, 0.0};
+			double n[3] = {-0.0, -0.0, 1.0}, t1[3] = {1.0, 0.0, 0.0}, t2[3] = {0.0, 1.0, 0.0};
+			if (sh->terrain_gradients) {
+				const orc_spline *mo = &p->ee_motion[ee];
+				const int en = node_at_start_of_phase(mo, phase_of_node(s, nd));
+				contact_basis(p, VAL(mo, en, 0, X), VAL(mo, en, 0, Y), n, t1, t2);
+			}
 			const double *f = &VAL(s, nd, 0, 0);
 			double fn = 0, a1 = 0, a2 = 0, b1 = 0, b2 = 0;
 			for (int i = 0; i < 3; ++i) {
@@ -471,9 +489,11 @@ void orc_eval_jac(orc_problem *p, const double *x, double *J, unsigned char *mas
 		const orc_spline *s = &p->ee_motion[ee];
 		for (int nd = 1; nd < s->n_nodes; ++nd) {
 			int row = p->row_terrain[ee] + nd - 1;
+			double hx = 0.0, hy = 0.0;
+			if (p->shape.terrain_gradients) orc_height_deriv(&p->hf, VAL(s, nd, 0, X), VAL(s, nd, 0, Y), &hx, &hy);
 			jset(&o, row, s->offset + OPT(s, nd, 0, Z), 1.0);
-			jset(&o, row, s->offset + OPT(s, nd, 0, X), -0.0);
-			jset(&o, row, s->offset + OPT(s, nd, 0, Y), -0.0);
+			jset(&o, row, s->offset + OPT(s, nd, 0, X), -hx);
+			jset(&o, row, s->offset + OPT(s, nd, 0, Y), -hy);
 		}
 	}
 	/* dynamic, ref: src/dynamic_constraint.cc:73-116 */
@@ -597,7 +617,11 @@ void orc_eval_jac(orc_problem *p, const double *x, double *J, unsigned char *mas
 		int row = p->row_force[ee];
 		for (int nd = 0; nd < s->n_nodes; ++nd) {
 			if (is_const_node(s, nd)) continue;
-			const double n[3] = {-0.0, -0.0, 1.0}, t1[3] = {1.0, 0.0, 0.0}, t2[3] = {0.0, 1.0, 0.0};
+			double n[3] = {-0.0, -0.0, 1.0}, t1[3] = {1.0, 0.0, 0.0}, t2[3] = {0.0, 1.0, 0.0};
+			if (sh->terrain_gradients) {
+				const int en = node_at_start_of_phase(mo, phase_of_node(s, nd));
+				contact_basis(p, VAL(mo, en, 0, X), VAL(mo, en, 0, Y), n, t1, t2);
+			}
 			for (int dim = 0; dim < 3; ++dim) {
 				int col = s->offset + OPT(s, nd, 0, dim);
 				jset(&o, row + 0, col, n[dim]);

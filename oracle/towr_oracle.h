@@ -62,6 +62,9 @@ typedef struct {
 	 * src/parameters.cc:51: rows appended after the swing sets, dt = duration_base_polynomial / 4 */
 	int    base_rom;
 	double dt_base_rom;
+	/* optional: the terrain derivatives the reference carries commented out (ref: src/custom_terrain.cpp:101-124,133-156) in the
+	 * terrain rows' Jacobian and in the force rows' contact basis (ref: src/height_map.cc:95-141, src/force_constraint.cc:67-135) */
+	int    terrain_gradients;
 } orc_shape;
 
 typedef struct {
@@ -117,6 +120,7 @@ void orc_get_layout(const orc_problem *p, int *var_offsets /*10+1*/, int *row_of
 /* ---- terrain (towr_terrain.c) ---- */
 double orc_height(const orc_heightfield *hf, double x, double y);
 void   orc_height_cell(const orc_heightfield *hf, double x, double y, long long idx[4]);
+void   orc_height_deriv(const orc_heightfield *hf, double x, double y, double *hx, double *hy);
 
 /* ---- evaluation (towr_eval.c) ---- */
 void orc_set_x(orc_problem *p, const double *x);

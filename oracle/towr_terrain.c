@@ -55,3 +55,20 @@ double orc_height(const orc_heightfield *hf, double x, double y)
 	const double w1 = u0 * z01 + u1 * z11;
 	return w0 * (y1 - y) + w1 * (y - y0);
 }
+
+/* First derivatives of the bilinear surface: the code the reference carries commented out in GetHeightDerivWrtX / WrtY
+ * (ref: src/custom_terrain.cpp:101-124,133-156), same cell selection as the height.  Used only with orc_shape.terrain_gradients
+ * (SURVEY 8f rank 4); second derivatives stay zero like the reference's HeightMap base class. */
+void orc_height_deriv(const orc_heightfield *hf, double x, double y, double *hx, double *hy)
+{
+	long long c[4];
+	orc_height_cell(hf, x, y, c);
+	const double res = hf->res;
+	const double x0 = (double)c[0] * res + MESH_X_OFFSET, x1 = (double)c[2] * res + MESH_X_OFFSET;
+	const double y0 = (double)c[1] * res + MESH_Y_OFFSET, y1 = (double)c[3] * res + MESH_Y_OFFSET;
+	const double z00 = hf->h[c[0] * hf->ny + c[1]], z01 = hf->h[c[0] * hf->ny + c[3]];
+	const double z10 = hf->h[c[2] * hf->ny + c[1]], z11 = hf->h[c[2] * hf->ny + c[3]];
+	const double s = 1 / (res * res);
+	*hx = s * ((-z00 + z10) * (y1 - y) + (-z01 + z11) * (y - y0));
+	*hy = s * (z00 * (x - x1) + z10 * (x0 - x) + z01 * (x1 - x) + z11 * (x - x0));
+}

@@ -262,3 +262,25 @@ def test_optional_base_motion_constraint(oracle):
     for c in (3, 100, 309, 400):
         xp, xm = x.copy(), x.copy(); xp[c] += 1e-6; xm[c] -= 1e-6
         assert np.abs((p.g(xp) - p.g(xm)) / 2e-6 - J[:, c])[1730:].max() < 1e-8
+
+
+def test_optional_terrain_gradients_in_the_oracle(oracle, golden_hf):
+    """orc_shape.terrain_gradients (oracle only): the bilinear derivative the reference carries commented out
+    (custom_terrain.cpp:101-124,133-156) equals finite differences of GetHeight inside a cell, enters the terrain rows'
+    Jacobian and tilts the contact basis of the force rows.  On flat ground nothing changes.  DESIGN.md section 7 records why it is
+    not built into the product: on the bench's plateau terrain 10 of 64 windows converge with it against 64 of 64 without."""
+    import ctypes as C
+    grid, res = golden_hf["exp_5_towr"], float(golden_hf["exp_5_res"])
+    ter = oracle.Terrain(grid, res)
+    hx, hy = C.c_double(), C.c_double()
+    for (x, y) in ((0.4321, 0.1234), (1.017, -0.333), (0.905, 0.0501)):
+        oracle.lib().orc_height_deriv(C.byref(ter.c), x, y, C.byref(hx), C.byref(hy))
+        e = 1e-7
+        assert abs(hx.value - (ter.height(x + e, y) - ter.height(x - e, y)) / (2 * e)) < 1e-6
+        assert abs(hy.value - (ter.height(x, y + e) - ter.height(x, y - e)) / (2 * e)) < 1e-6
+    sh0, sh1 = oracle.default_shape("C1", 2.0), oracle.default_shape("C1", 2.0)
+    sh1.terrain_gradients = 1
+    flat = oracle.Terrain(np.zeros((150, 150)), 0.02)
+    p0, p1 = oracle.Problem(sh0, oracle.make_instance(), flat), oracle.Problem(sh1, oracle.make_instance(), flat)
+    x = p0.x0() + 0.01 * np.random.default_rng(0).standard_normal(p0.n)
+    assert np.array_equal(p0.g(x), p1.g(x)) and np.array_equal(p0.jac(x), p1.jac(x))
