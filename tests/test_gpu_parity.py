@@ -600,3 +600,21 @@ def test_base_motion_constraint_option(oracle):
         close += int(r["iters"][i] == ro.iters and np.abs(rows[i][:, 1:19] - po.csv(xo)[:, 1:19]).max() < TRAJ_TOL_M)
     assert (r["status"] == 0).sum() >= 6 and close >= 6
     S.close()
+
+
+def test_more_windows_than_slots_flow_through_the_pool():
+    """qtos_solve_batch with n > max_batch runs the windows through the slots as a pool (not chunk after chunk); per-window
+    results equal the one-batch solve bit for bit, CSV sampling included."""
+    grid, res = HF.rough_terrain(1234)
+    big = Q.Solver(Q.default_shape(*SHAPES["S2"]), max_batch=96)
+    small = Q.Solver(Q.default_shape(*SHAPES["S2"]), max_batch=20)
+    p = workloads.multistart_problems(96, grid, res, hf_id=big.upload_heightfield(grid, res))
+    assert small.upload_heightfield(grid, res) == p["hf_id"][0]
+    r0, x0, _ = big.solve(p)
+    r1, x1, rows = small.solve(p, csv=True)                       # 96 windows through 20 slots
+    assert np.array_equal(x1, x0) and np.array_equal(r1["iters"], r0["iters"]) and np.array_equal(r1["status"], r0["status"])
+    assert np.array_equal(r1["cost"], r0["cost"]) and rows.shape == (96, 2001, 37)
+    assert np.array_equal(rows[5], big.sample_csv(p[5:6], x0[5:6])[0])
+    r2, x2, _ = small.solve(p, Q.default_options(algorithm=Q.ALG_FAST))      # the FAST algorithm still goes chunk by chunk
+    assert set(r2["status"]) <= {0, -1, -2}
+    big.close(); small.close()
