@@ -224,8 +224,10 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the solver has no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_group = dist.new_group(backend="gloo")          # host-side line-up before every NCCL all-gather (parallel.select_best_device)
     dev = torch.device("cuda", local)
     n_total = PER_GPU * world
     idx = parallel.shard_indices(n_total, rank, world)
@@ -266,7 +268,7 @@ def run_gpu(args):
     def finish(r):
         """the step's result: per-candidate records -> best plan per group (all-gather when N > 1)"""
         rec = parallel.make_records(r, idx, p["group"])
-        winners, _ = parallel.select_best(rec, device=dev)
+        winners, _ = parallel.select_best(rec, device=dev, host_group=host_group)
         return winners
 
     tickets = {}
@@ -280,7 +282,7 @@ def run_gpu(args):
     def collect_device(k):
         S.stream_wait(tickets.pop(k))
         # the step's result: best plan per group, selected on the device (k_records -> all-gather -> k_select), 32 KB of winners
-        win = parallel.select_best_device(S, d_res[k], d_group, rank, world, n_groups).cpu()
+        win = parallel.select_best_device(S, d_res[k], d_group, rank, world, n_groups, host_group).cpu()
         assert int((win < 0).sum()) == 0
         return d_res[k].cpu().numpy().view(Q.RESULT_DTYPE).reshape(n)     # statuses / iteration counts for the line's statistics
 

@@ -76,7 +76,7 @@ def argmin_per_group_torch(rec):
     return grp, best.to(torch.int64)
 
 
-def select_best(rec_local, device=None):
+def select_best(rec_local, device=None, host_group=None):
     """all-gather the records of every rank (equal counts per rank) and pick the winner of each group
     on every rank identically.  Returns (winners dict, gathered records or None).  With a process group the
     selection runs on the gathered tensor where it lands (on the GPU under NCCL): only the winners come back."""
@@ -86,6 +86,8 @@ def select_best(rec_local, device=None):
     t = torch.from_numpy(np.ascontiguousarray(rec_local))
     if device is not None:
         t = t.to(device)
+    if host_group is not None:
+        dist.barrier(group=host_group)                 # line the ranks up on the host: a waiting NCCL kernel spins on the GPU
     out = torch.empty((world * t.shape[0], t.shape[1]), dtype=t.dtype, device=t.device)
     dist.all_gather_into_tensor(out, t)
     grp, win = argmin_per_group_torch(out)
@@ -93,16 +95,20 @@ def select_best(rec_local, device=None):
     return dict(zip(gw[0].tolist(), gw[1].tolist())), out
 
 
-def select_best_device(solver, d_res, d_group, rank, world, n_groups):
+def select_best_device(solver, d_res, d_group, rank, world, n_groups, host_group=None):
     """The selection without a host round trip: records from the device-resident results (k_records), one all-gather over
     NCCL, winners by the library's hand-written kernel (k_select).  d_res: uint8 [n, sizeof(qtos_result)], d_group: int32 [n]
     with dense group ids in [0, n_groups); candidate i of this rank has global id rank + world * i (shard_indices).
+    `host_group` (a gloo process group) lines the ranks up on the host first: an NCCL kernel that waits for a late rank spins ON
+    the GPU beside the solver's kernels, a host barrier does not.
     Returns the winning global ids as an int64 tensor [n_groups] on the device (-1 for an empty group)."""
     n = d_res.shape[0]
     dev = d_res.device
     rec = torch.empty((n, 5), dtype=torch.float64, device=dev)
     solver.make_records(d_res.data_ptr(), d_group.data_ptr(), rank, world, n, rec.data_ptr())      # synchronises the solver's stream
     if dist.is_available() and dist.is_initialized() and world > 1:
+        if host_group is not None:
+            dist.barrier(group=host_group)
         allrec = torch.empty((world * n, 5), dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(allrec, rec)
         torch.cuda.current_stream(dev).synchronize()           # the solver's kernels run on its own stream
