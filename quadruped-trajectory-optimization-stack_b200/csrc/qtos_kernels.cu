@@ -1,20 +1,21 @@
 /*
  * qtos_kernels.cu -- sm_100a kernels of the batched interior-point gait-plan solver.
  *
- * One thread block per problem (k_jac: one thread per sample); a batch iteration is five launches
- * (jac_dyn, jac_rom -> prepare -> factor -> step), all on the context's stream:
- *   k_init      x0, fixed variables, g(x0), J(x0), row scaling, slack/multiplier init
- *               (ref: nlp_formulation.cc:100-190; Ipopt initialisation)
- *   k_jac       dynamics + range-of-motion Jacobian element blocks at x
- *   k_prepare   J'y, error measures, termination test, barrier update, Sigma, rhs = -J'w
- *   k_factor    per block row: assemble sigma I + J' D J (owner-computes gather) into shared memory,
- *               left-looking Cholesky on 16x16 blocks with FP64 tensor-core MMAs, forward
- *               substitution; then the backward substitution -> dx
- *   k_step      step recovery, fraction-to-boundary, l1-merit backtracking
- *               line search with in-kernel g(x) evaluations, iterate update
- *   k_csv       1 kHz trajectory sampler (ref: main.cpp:92-131)
+ * One thread block per problem (k_jac: one thread per sample; k_asm: one block per problem and block row).  All launches of a
+ * solve go to the context's stream (k_jac_rom beside k_jac_dyn on a second one).  Kernels shared by both algorithms:
+ *   k_init      x0, fixed variables, g(x0), constant J elements; after the first k_jac: row scaling, slack / multiplier
+ *               and algorithm-state initialisation (ref: nlp_formulation.cc:100-190; Ipopt initialisation)
+ *   k_jac_*     dynamics + range-of-motion Jacobian element blocks at x
+ *   k_asm       M = sigma I + J' D J, one block row per CTA, owner-computes gather into shared memory
+ *   k_factor    left-looking block-skyline Cholesky on 16x16 blocks with FP64 tensor-core MMAs (DMMA m8n8k4);
+ *               <., 0>: forward substitution of one right-hand side fused, then the backward substitution -> dx
+ *               <., 1>: the 16 right-hand sides of the IPOPT path forward-substituted as one more block row, plus their Gram matrix
+ *   k_csv       1 kHz trajectory sampler, any row range (ref: main.cpp:92-131)
  *   k_height    batched heightfield queries (ref: custom_terrain.cpp:51-94)
- * The interior-point algorithm is the one restated in oracle/towr_ipm.c (test oracle).
+ *   k_results, k_cost, k_admit, k_records, k_select   results, post-hoc plan cost, pool admission, best-plan selection
+ * QTOS_ALG_FAST (oracle/towr_ipm.c):  k_prepare (J'y, error measures, termination, monotone barrier update, Sigma, rhs = -J'w)
+ *   and k_step (step recovery, fraction to the boundary, l1-merit backtracking with in-kernel g(x), iterate update).
+ * QTOS_ALG_IPOPT (oracle/towr_ipopt.c), the default: kip_prepare, kip_solve, kip_step in qtos_ipopt.cuh.
  */
 #include "qtos_device.cuh"
 
@@ -775,8 +776,8 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld, int max_w)
 
 /* ------------------------------------------------------------------ k_step */
 
-/* three CTAs per SM (<= 85 registers): the evaluation inside the line search is latency-bound, occupancy pays more
- * than the 24 bytes of spill cost (17.8 -> 9.1 ms per bench step) */
+/* MINB resident CTAs per SM (four for narrow shapes, three for wide ones; see the launch site): the evaluation inside the line
+ * search is latency-bound, occupancy pays more than the spills cost (17.8 -> 9.1 ms per bench step at three, 9.0 at four) */
 template <int MINB>
 __global__ void __launch_bounds__(QTOS_THREADS, MINB)
 k_step(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *hfs, int n_hf, qtos_options opt)
