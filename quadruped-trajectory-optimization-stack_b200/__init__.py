@@ -33,7 +33,7 @@ def _sources():
 
 
 def _deps():
-    d = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)]
+    d = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".h", ".inc"))]
     d.append(os.path.join(_ROOT, "include", "qtos_b200.h"))
     return d
 
@@ -42,16 +42,21 @@ def build(force=False, verbose=False):
     """Compile csrc/ for sm_100a with nvcc into libqtos_b200.so (in-tree)."""
     if os.environ.get("QTOS_LIB"):          # development: load an experimental build of the same sources
         return os.environ["QTOS_LIB"]
-    stale = force or not os.path.exists(_SO) or any(
-        os.path.getmtime(s) > os.path.getmtime(_SO) for s in _deps() if os.path.exists(s))
-    if stale:
-        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        if not os.path.exists(nvcc):
-            if os.path.exists(_SO):
-                return _SO          # GPU box without sources newer than the shipped library
-            raise RuntimeError("nvcc not found and libqtos_b200.so is missing")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + _sources() + ["-o", _SO]
-        subprocess.check_call(cmd, cwd=_CSRC)
+    import fcntl
+    with open(os.path.join(_HERE, ".build.lock"), "w") as lock:      # one process of a torchrun group compiles, the others wait
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        stale = force or not os.path.exists(_SO) or any(
+            os.path.getmtime(s) > os.path.getmtime(_SO) for s in _deps() if os.path.exists(s))
+        if stale:
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            if not os.path.exists(nvcc):
+                if os.path.exists(_SO):
+                    return _SO          # GPU box without sources newer than the shipped library
+                raise RuntimeError("nvcc not found and libqtos_b200.so is missing")
+            tmp = _SO + ".tmp%d" % os.getpid()
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + _sources() + ["-o", tmp]
+            subprocess.check_call(cmd, cwd=_CSRC)
+            os.replace(tmp, _SO)        # readers never see a half-written library
     return _SO
 
 
