@@ -7,10 +7,11 @@ around the start and goal of every failed probe (ref: QTOS/generateHeightField.p
 whole probe set is ONE `Solver.solve` batch on the GPU; the host logic either side of it is restated
 so the resulting `bool_map` is the one the reference builds:
 
-  probe_set            ref: generateHeightField.py:303-342 (probe_map; same float accumulation and
-                            round(., 2) calls, so coordinates are bit-identical)
-  neighbors_danger     ref: generateHeightField.py:282-301
-  hull_offsets         ref: generateHeightField.py:226-263 (find_convex_hull; scipy ConvexHull + scan lines)
+  probe_set            ref: generateHeightField.py:303-342 (probe_map), stated as two 1-D coordinate tables (the
+                            reference's add-then-round(., 2) walk along each axis, so coordinates are bit-identical)
+                            and a mask over the (row, column pair) grid instead of the nested cell loop
+  danger_mask          ref: generateHeightField.py:282-301 (neighbors_danger) for all cells at once
+  hull_offsets         ref: generateHeightField.py:226-263 (find_convex_hull; scipy ConvexHull, all scan lines at once)
   probe_problems       ref: generateHeightField.py:365-373 (state_config) + QTOS/utils.py:644-670 (cmd_args)
                             + solver/towr/src/main.cpp:163-306 (the flags ./main would parse)
   mark                 ref: generateHeightField.py:386-404 (success clears start/mid/goal, failure sets the
@@ -31,77 +32,96 @@ ORIGIN_SHIFT = 1.0          # ref: generateHeightField.py:205-206
 PROBE_RUNTIME = 5.0         # `-r 5.0`, accepted and ignored by the GPU solver
 
 
+_SCAN = ((1, 0), (-1, 0), (0, 1), (0, -1), (1, 1), (1, -1), (-1, -1), (-1, 1))     # ref :282-301: the order decides
+
+
+def danger_mask(m, sz=1):
+    """danger_mask(m)[ix, iy] == the reference's neighbors_danger(ix, iy) for every cell at once: the 8 neighbours are
+    looked at in the reference's order and the FIRST decisive one settles the cell -- a neighbour outside the map says
+    False (the reference returns from inside its loop), a raised one says True."""
+    m = np.asarray(m)
+    nx, ny = m.shape
+    ix, iy = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    verdict = np.zeros(m.shape, dtype=bool)
+    open_ = np.ones(m.shape, dtype=bool)
+    for dx, dy in _SCAN:
+        jx, jy = ix + sz * dx, iy + sz * dy
+        inside = (jx >= 0) & (jx < nx) & (jy >= 0) & (jy < ny)
+        raised = np.zeros(m.shape, dtype=bool)
+        raised[inside] = m[jx[inside], jy[inside]] > 0
+        verdict |= open_ & raised
+        open_ &= inside & ~raised
+    return verdict
+
+
 def neighbors_danger(m, ix, iy, sz=1):
-    """True when one of the 8 neighbours is raised; a neighbour outside the map ends the scan with
-    False (the reference returns from inside the loop, order of the offsets matters)."""
-    for dx, dy in ((sz, 0), (-sz, 0), (0, sz), (0, -sz), (sz, sz), (sz, -sz), (-sz, -sz), (-sz, sz)):
-        if dx + ix >= m.shape[0] or dx + ix < 0:
-            return False
-        elif dy + iy >= m.shape[1] or dy + iy < 0:
-            return False
-        elif m[dx + ix][dy + iy] > 0:
-            return True
-    return False
+    """one cell of danger_mask (kept for callers that ask about single cells)."""
+    return bool(danger_mask(m, sz)[ix, iy])
+
+
+def _rounded_walk(first, step, n):
+    """the reference's coordinate bookkeeping along one axis: add `step`, round to 2 decimals, n times (plain Python
+    floats -- the rounding after every step is what makes the probe coordinates bit-identical to the reference's)."""
+    out, v = [], first
+    for _ in range(n):
+        v = round(v + step, 2)
+        out.append(v)
+    return out
 
 
 def probe_set(m, multi_map_shift=1, mesh_resolution=0.1):
-    """-> dict of arrays in queue order: start[n,3], goal[n,3] (world x, y, map height), idx_start[n,2],
-    idx_goal[n,2].  Plain Python floats on purpose: the reference accumulates and rounds step by step."""
+    """-> dict of arrays in queue order: start[n,3], goal[n,3] (world x, y, map height), idx_start[n,2], idx_goal[n,2].
+
+    The reference walks rows (outer) and column PAIRS (inner): probe (ix, k) runs from cell (ix, 2k) to cell (ix, 2k + 2)
+    and is queued when either end has a raised neighbour.  Its coordinates do not depend on the map: y advances by one
+    resolution step per row, x_goal by two per column pair, and every probe starts where the previous one of its row
+    ended (the first starts one step in), each value rounded to 2 decimals as it is formed.  So the coordinates are two
+    1-D tables and the queue is a mask over the (row, pair) grid, read in row-major order."""
     m = np.asarray(m)
     step = mesh_resolution
-    x_start = -mesh_resolution * (m.shape[1] / 2) - mesh_resolution / 2 + ((multi_map_shift - 1) * ORIGIN_SHIFT)
-    y_start = -mesh_resolution * (m.shape[1] / 2) - mesh_resolution / 2 + ((multi_map_shift - 1) * ORIGIN_SHIFT)
-    x_goal = -mesh_resolution * (m.shape[1] / 2) + mesh_resolution / 2 + ((multi_map_shift - 1) * ORIGIN_SHIFT)
-    y_goal = -mesh_resolution * (m.shape[1] / 2) - mesh_resolution / 2 + ((multi_map_shift - 1) * ORIGIN_SHIFT)
-    _x_start, _y_start, _x_goal, _y_goal = x_start, y_start, x_goal, y_goal
-    ix, iy, iy_off = 0, 0, 2
-    S, G, IS, IG = [], [], [], []
-    for _ in range(m.shape[0]):
-        _y_start += step
-        _y_goal += step
-        _x_start, _x_goal = x_start, x_goal
-        for y in range(m.shape[1] // 2 - 1):
-            if y == 0:
-                _x_start += step
-                iy, iy_off = 0, 2
-            else:
-                _x_start = _x_goal
-            _x_goal += 2 * step
-            _x_start, _y_start = round(_x_start, 2), round(_y_start, 2)
-            _x_goal, _y_goal = round(_x_goal, 2), round(_y_goal, 2)
-            if neighbors_danger(m, ix, iy) or neighbors_danger(m, ix, iy_off):
-                S.append((_x_start, _y_start, float(m[ix][iy])))
-                G.append((_x_goal, _y_goal, float(m[ix][iy_off])))
-                IS.append((ix, iy))
-                IG.append((ix, iy_off))
-            iy += 2
-            iy_off += 2
-        ix += 1
-    return {"start": np.array(S, dtype=np.float64).reshape(-1, 3), "goal": np.array(G, dtype=np.float64).reshape(-1, 3),
-            "idx_start": np.array(IS, dtype=np.int64).reshape(-1, 2), "idx_goal": np.array(IG, dtype=np.int64).reshape(-1, 2)}
+    nrow, npair = m.shape[0], max(m.shape[1] // 2 - 1, 0)
+    shift = (multi_map_shift - 1) * ORIGIN_SHIFT
+    half = mesh_resolution * (m.shape[1] / 2)            # the reference uses shape[1] for both axes
+    lo, hi = -half - mesh_resolution / 2 + shift, -half + mesh_resolution / 2 + shift
+    ys = _rounded_walk(lo, step, nrow)                   # y of row ix (start and goal alike)
+    xg = _rounded_walk(hi, 2 * step, npair)              # x_goal of pair k
+    xs = ([round(lo + step, 2)] + xg[:-1]) if npair else []
+    risky = danger_mask(m)
+    cols = 2 * np.arange(npair)
+    queued = risky[:, cols] | risky[:, cols + 2] if npair else np.zeros((nrow, 0), dtype=bool)
+    ix, k = np.nonzero(queued)                           # row-major = the reference's queue order
+    iy, iy_off = 2 * k, 2 * k + 2
+    ys, xs, xg = np.array(ys, dtype=np.float64), np.array(xs, dtype=np.float64), np.array(xg, dtype=np.float64)
+    start = np.stack([xs[k], ys[ix], m[ix, iy].astype(np.float64)], axis=1) if len(ix) else np.zeros((0, 3))
+    goal = np.stack([xg[k], ys[ix], m[ix, iy_off].astype(np.float64)], axis=1) if len(ix) else np.zeros((0, 3))
+    return {"start": start.reshape(-1, 3), "goal": goal.reshape(-1, 3),
+            "idx_start": np.stack([ix, iy], axis=1).astype(np.int64).reshape(-1, 2),
+            "idx_goal": np.stack([ix, iy_off], axis=1).astype(np.int64).reshape(-1, 2)}
 
 
 def hull_offsets(points):
-    """cells of the filled convex hull of `points`, relative to the centre of its bounding box."""
+    """cells of the filled convex hull of `points`, relative to the centre of its bounding box (ref :226-263): every scan
+    line y is filled between the smallest and the largest of its cuts with the hull's non-horizontal edges, a cut being
+    the edge's x at y truncated towards zero; lines with fewer than two cuts stay empty.  All lines and edges at once."""
     from scipy.spatial import ConvexHull
-    points = np.array(points)
-    hv = points[ConvexHull(points).vertices]
-    min_x, max_x = np.min(hv[:, 0]), np.max(hv[:, 0])
-    min_y, max_y = np.min(hv[:, 1]), np.max(hv[:, 1])
-    grid = np.zeros((max_y - min_y + 1, max_x - min_x + 1), dtype=int)
-    for y in range(min_y, max_y + 1):
-        cuts = []
-        for i in range(len(hv)):
-            x1, y1 = hv[i]
-            x2, y2 = hv[(i + 1) % len(hv)]
-            if y1 == y2:
-                continue
-            if y1 <= y <= y2 or y2 <= y <= y1:
-                cuts.append(int(x1 + (x2 - x1) * (y - y1) / (y2 - y1)))
-        cuts.sort()
-        if len(cuts) >= 2:
-            grid[y - min_y, cuts[0] - min_x:cuts[-1] - min_x + 1] = 1
-    return np.argwhere(grid == 1) - np.array([grid.shape[0] // 2, grid.shape[1] // 2])
+    pts = np.asarray(points)
+    hv = pts[ConvexHull(pts).vertices]
+    a, b = hv, np.roll(hv, -1, axis=0)                   # edges a -> b
+    x0, y0 = int(hv[:, 0].min()), int(hv[:, 1].min())
+    w, h = int(hv[:, 0].max()) - x0 + 1, int(hv[:, 1].max()) - y0 + 1
+    y = (y0 + np.arange(h))[:, None]                     # [line, edge]
+    ya, yb, xa, xb = a[None, :, 1], b[None, :, 1], a[None, :, 0], b[None, :, 0]
+    slanted = ya != yb
+    hit = slanted & (((ya <= y) & (y <= yb)) | ((yb <= y) & (y <= ya)))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cut = np.trunc(xa + (xb - xa) * (y - ya) / np.where(slanted, yb - ya, 1)).astype(np.int64)
+    big = np.iinfo(np.int64).max
+    left = np.where(hit, cut, big).min(axis=1)
+    right = np.where(hit, cut, -big).max(axis=1)
+    filled = hit.sum(axis=1) >= 2
+    xcol = x0 + np.arange(w)[None, :]
+    grid = filled[:, None] & (xcol >= left[:, None]) & (xcol <= right[:, None])
+    return np.argwhere(grid) - np.array([h // 2, w // 2])
 
 
 def diamond(scale=1):
@@ -130,24 +150,23 @@ def probe_problems(probes, hf_id=0):
     return p
 
 
+def _stamp(out, cx, cy, offsets):
+    q = offsets + np.array([cx, cy])
+    ok = (q[:, 0] >= 0) & (q[:, 0] < out.shape[0]) & (q[:, 1] >= 0) & (q[:, 1] < out.shape[1])
+    out[q[ok, 0], q[ok, 1]] = 1
+
+
 def mark(shape, probes, feasible, offsets_start, offsets_end=None):
-    """bool_map after the probes have been applied in queue order."""
+    """bool_map after the probes have been applied in queue order (a later probe overwrites an earlier one's cells)."""
     offsets_end = offsets_start if offsets_end is None else offsets_end
+    offsets_start, offsets_end = np.asarray(offsets_start).reshape(-1, 2), np.asarray(offsets_end).reshape(-1, 2)
     out = np.zeros(shape, dtype=np.float32)        # the reference's shared int array is used as float32
-    for k in range(len(probes["idx_start"])):
-        sx, sy = (int(v) for v in probes["idx_start"][k])
-        gx, gy = (int(v) for v in probes["idx_goal"][k])
-        if feasible[k]:
-            out[sx, sy] = 0
-            out[sx, sy + 1] = 0
-            out[gx, gy] = 0
+    for (sx, sy), (gx, gy), ok in zip(probes["idx_start"].tolist(), probes["idx_goal"].tolist(), feasible):
+        if ok:
+            out[sx, sy] = out[sx, sy + 1] = out[gx, gy] = 0
         else:
-            for dx, dy in offsets_start:
-                if 0 <= sx + dx < shape[0] and 0 <= sy + dy < shape[1]:
-                    out[sx + dx, sy + dy] = 1
-            for dx, dy in offsets_end:
-                if 0 <= gx + dx < shape[0] and 0 <= gy + dy < shape[1]:
-                    out[gx + dx, gy + dy] = 1
+            _stamp(out, sx, sy, offsets_start)
+            _stamp(out, gx, gy, offsets_end)
     return out.astype("int")
 
 
