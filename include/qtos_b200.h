@@ -59,6 +59,12 @@ typedef struct {
 	                                     z(t) - z(0) within [-0.02, 0.1] at every dt_base_rom; yaw, x, y rows are kept unbounded like the
 	                                     reference's.  The z row is stated relative to the start height, so its bounds are the shape's */
 	double dt_base_rom;               /* duration_base_polynomial / 4 (ref: parameters.cc:51) */
+	double cost_force_z;              /* weight of TOWR's optional ForcesCostID term: sum over the force nodes of weight * f_z^2, and */
+	double cost_ee_vel_xy;            /* of EEMotionCostID: sum over the foot-motion nodes of weight * (v_x^2 + v_y^2)
+	                                     (Parameters::costs_, empty on the reference's path: parameters.cc:62-63; nlp_formulation.cc:343-376;
+	                                     node_cost.cc:53-83).  0 = the term is absent.  With a weight set the objective is minimised by
+	                                     QTOS_ALG_IPOPT exactly as Ipopt would (gradient in the dual infeasibility, the limited-memory pairs,
+	                                     the barrier function of the filter line search); QTOS_ALG_FAST refuses such a shape */
 } qtos_shape;
 
 /* one local-plan window = the flags of ./main (ref: main.cpp:163-306) */

@@ -30,7 +30,8 @@ class Shape(C.Structure):
                 ("dt_base_poly", C.c_double), ("force_polys_per_stance", C.c_int),
                 ("ee_polys_per_swing", C.c_int), ("dt_dynamic", C.c_double),
                 ("dt_rom", C.c_double), ("combo", C.c_int), ("duration", C.c_double),
-                ("base_rom", C.c_int), ("dt_base_rom", C.c_double), ("terrain_gradients", C.c_int)]
+                ("base_rom", C.c_int), ("dt_base_rom", C.c_double), ("terrain_gradients", C.c_int),
+                ("cost_force_z", C.c_double), ("cost_ee_vel_xy", C.c_double)]
 
 
 class Instance(C.Structure):
@@ -72,7 +73,8 @@ class IpoptResult(C.Structure):
                 ("tr_inf_pr", C.c_double * 256), ("tr_inf_du", C.c_double * 256), ("tr_mu", C.c_double * 256),
                 ("tr_dnorm", C.c_double * 256), ("tr_alpha_pr", C.c_double * 256), ("tr_alpha_du", C.c_double * 256),
                 ("tr_ls", C.c_int * 256), ("tr_pairs", C.c_int * 256), ("tr_free", C.c_int * 256),
-                ("tr_tag", C.c_char * 256), ("chol_fix", C.c_int), ("n_regularized", C.c_int), ("retried", C.c_int)]
+                ("tr_tag", C.c_char * 256), ("chol_fix", C.c_int), ("n_regularized", C.c_int), ("retried", C.c_int),
+                ("objective", C.c_double)]
 
 
 def build(force=False):
@@ -104,6 +106,8 @@ def lib():
         L.orc_height_deriv.argtypes = [C.POINTER(Heightfield), C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.orc_eval_g.argtypes = [C.c_void_p, dp, dp]
         L.orc_eval_jac.argtypes = [C.c_void_p, dp, dp, C.POINTER(C.c_ubyte)]
+        L.orc_eval_cost.restype = C.c_double
+        L.orc_eval_cost.argtypes = [C.c_void_p, dp, dp]
         L.orc_csv_rows.argtypes = [C.c_void_p, C.c_double]
         L.orc_sample_csv.argtypes = [C.c_void_p, dp, C.c_double, dp]
         L.orc_write_csv.argtypes = [C.c_void_p, dp, C.c_double, C.c_char_p]
@@ -216,6 +220,14 @@ class Problem:
             return J, mask
         lib().orc_eval_jac(self.h, _dp(x), _dp(J), None)
         return J
+
+    def cost(self, x, with_grad=False):
+        """objective (the NodeCost terms of the shape; 0 when none) and optionally its gradient"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if with_grad:
+            g = np.zeros(self.n)
+            return lib().orc_eval_cost(self.h, _dp(x), _dp(g)), g
+        return lib().orc_eval_cost(self.h, _dp(x), None)
 
     def csv(self, x, dt=0.001):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -123,6 +123,13 @@ class IpoptEmulator:
         self.dU = np.where(self.hasU, du * sc[self.iq], np.inf)
         self.gl_raw, self.gu_raw = gl, gu
         self.n_bounds = int(self.hasL.sum() + self.hasU.sum())
+        # optional cost terms (f == 0 on the reference's path): gradient-based objective scaling at the starting point
+        self.has_cost = hasattr(problem, "cost") and (problem.shape.cost_force_z != 0.0 or problem.shape.cost_ee_vel_xy != 0.0)
+        self.df = 1.0
+        if self.has_cost:
+            g0 = np.abs(problem.cost(self.x_full, with_grad=True)[1][self.free]).max()
+            if g0 > o.nlp_scaling_max_gradient:
+                self.df = max(o.nlp_scaling_max_gradient / g0, o.nlp_scaling_min_value)
 
     # ---- problem functions in Ipopt's scaled space
     def full(self, x):
@@ -133,6 +140,14 @@ class IpoptEmulator:
     def cd(self, x):
         g = self.p.g(self.full(x))
         return self.sc[self.eq] * (g[self.eq] - self.gl_eq), self.sc[self.iq] * g[self.iq], g
+
+    def f(self, x, with_grad=False):
+        if not self.has_cost:
+            return (0.0, np.zeros(self.n)) if with_grad else 0.0
+        if with_grad:
+            v, g = self.p.cost(self.full(x), with_grad=True)
+            return self.df * v, self.df * g[self.free]
+        return self.df * self.p.cost(self.full(x))
 
     def jac(self, x):
         J = self.p.jac(self.full(x))[:, self.free] * self.sc[:, None]
@@ -180,6 +195,7 @@ class IpoptEmulator:
         x = self.x_full[self.free].copy()
         c, d, graw = self.cd(x)
         Jc, Jd = self.jac(x)
+        fval, gf = self.f(x, with_grad=True)
         # slack initialisation (DefaultIterateInitializer::push_variables)
         both = hasL & hasU
         width = np.where(both, dU - dL, np.inf)
@@ -220,9 +236,9 @@ class IpoptEmulator:
             sL, sU = slacks(s)
             # ---- L-BFGS update (LimMemQuasiNewtonUpdater::UpdateHessian)
             if last is not None:
-                lx, lJc, lJd = last
+                lx, lJc, lJd, lgf = last
                 s_new = x - lx
-                y_new = (Jc.T @ yc + Jd.T @ yd) - (lJc.T @ yc + lJd.T @ yd)
+                y_new = (gf + Jc.T @ yc + Jd.T @ yd) - (lgf + lJc.T @ yc + lJd.T @ yd)
                 sTy = float(s_new @ y_new)
                 snrm, ynrm = np.linalg.norm(s_new), np.linalg.norm(y_new)
                 skipping = sTy <= np.sqrt(np.finfo(float).eps) * snrm * ynrm
@@ -236,7 +252,7 @@ class IpoptEmulator:
                     if len(S) > o.lm_history:
                         S.pop(0); Y.pop(0)
                     sigma_w = min(max(sTy / float(s_new @ s_new), o.lm_init_val_min), o.lm_init_val_max)
-            last = (x.copy(), Jc, Jd)
+            last = (x.copy(), Jc, Jd, gf)
             W = sigma_w * np.eye(n)
             self._sigma_w, self._Bl, self._Mid = sigma_w, None, None
             if S:
@@ -250,7 +266,7 @@ class IpoptEmulator:
                 self._Bl, self._Mid = Bl, Mid
 
             # ---- error measures (IpoptCalculatedQuantities)
-            glx = Jc.T @ yc + Jd.T @ yd
+            glx = gf + Jc.T @ yc + Jd.T @ yd
             gls = -yd.copy()
             gls[hasL] -= vL
             gls[hasU] += vU
@@ -272,8 +288,8 @@ class IpoptEmulator:
                 print("%4d %.2e %.2e %5.1f %.2e %.2e %.2e%s %2d  E=%.2e sw=%.3g np=%d %s" % (
                     it, viol, dual_inf, np.log10(mu), dnorm, alpha_du, alpha_pr, step_tag, ls_count, nlp_error,
                     sigma_w, len(S), "" if free_mode else "F"))
-            # unscaled dual/compl equal the scaled ones (objective scaling 1)
-            if nlp_error <= o.tol and dual_inf <= o.dual_inf_tol and viol <= o.constr_viol_tol and compl <= o.compl_inf_tol:
+            # the absolute tolerances apply to the unscaled problem: dual infeasibility and complementarity carry the objective's scale
+            if nlp_error <= o.tol and dual_inf / self.df <= o.dual_inf_tol and viol <= o.constr_viol_tol and compl / self.df <= o.compl_inf_tol:
                 status = 0
                 break
             if it >= o.max_iter:
@@ -292,15 +308,15 @@ class IpoptEmulator:
                 mu_max = o.mu_max_fact * avrg_compl
 
             def amu_acceptable(th):
-                # f == 0: an entry (-margin, theta_k - margin) is passed only by a smaller violation
+                # with f == 0 an entry (-margin, theta_k - margin) is passed only by a smaller violation
                 for (ef, eth) in amu_filter:
-                    if not (0.0 <= ef or th <= eth):
+                    if not (fval <= ef or th <= eth):
                         return False
                 return True
 
             def remember():
                 m_ = o.filter_margin_fact * min(o.filter_max_margin, theta)
-                amu_filter.append((0.0 - m_, theta - m_))
+                amu_filter.append((fval - m_, theta - m_))
 
             def barrier_error():
                 cm = max(np.abs(sL * vL - mu).max() if len(sL) else 0.0, np.abs(sU * vU - mu).max() if len(sU) else 0.0)
@@ -422,8 +438,8 @@ class IpoptEmulator:
                 a, b = slacks(s_)
                 return -mu * (np.log(a).sum() + np.log(b).sum())
 
-            phi0 = barrier(s)
-            gBD = -mu * (float((ds[hasL] / sL).sum()) - float((ds[hasU] / sU).sum()))
+            phi0 = barrier(s) + fval
+            gBD = -mu * (float((ds[hasL] / sL).sum()) - float((ds[hasU] / sU).sum())) + float(gf @ dx)
             if theta_max < 0:
                 theta_max = o.theta_max_fact * max(1.0, theta)
                 theta_min = o.theta_min_fact * max(1.0, theta)
@@ -450,7 +466,7 @@ class IpoptEmulator:
                 xt, st = x + alpha * dx, s + alpha * ds
                 ct, dt_, gt = self.cd(xt)
                 th_t = np.abs(ct).sum() + np.abs(dt_ - st).sum()
-                ph_t = barrier(st)
+                ph_t = barrier(st) + self.f(xt)
                 ok = False
                 if th_t <= theta_max and np.isfinite(ph_t):
                     switching = gBD < 0 and alpha * (-gBD) ** o.s_phi > o.delta * theta ** o.s_theta
@@ -495,10 +511,12 @@ class IpoptEmulator:
             vL = np.minimum(np.maximum(vL, mu_c / (o.kappa_sigma * sL)), o.kappa_sigma * mu_c / sL)
             vU = np.minimum(np.maximum(vU, mu_c / (o.kappa_sigma * sU)), o.kappa_sigma * mu_c / sU)
             Jc, Jd = self.jac(x)
+            fval, gf = self.f(x, with_grad=True)
             it += 1
 
         res.status, res.iters = status, it
         res.x = self.full(x)
         res.constr_viol = viol
         res.nlp_error = nlp_error
+        res.objective = fval / self.df
         return res

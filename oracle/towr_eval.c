@@ -356,6 +356,36 @@ static void contact_basis(const orc_problem *p, double x, double y, double n[3],
 	t2[0] = 0.0; t2[1] = 1.0 / n2; t2[2] = hy / n2;
 }
 
+/* One NodeCost term: weight * value^2 summed over the NODES of a spline (ref: src/node_cost.cc:53-63), gradient
+ * 2 * weight * value added to the node's variable once per node that maps to it (ref: src/node_cost.cc:66-83). */
+static double node_cost(const orc_spline *s, int deriv, int dim, double weight, double *grad)
+{
+	double c = 0.0;
+	for (int nd = 0; nd < s->n_nodes; ++nd) {
+		const double v = VAL(s, nd, deriv, dim);
+		c += weight * pow(v, 2);
+		if (grad && OPT(s, nd, deriv, dim) >= 0) grad[s->offset + OPT(s, nd, deriv, dim)] += weight * 2.0 * v;
+	}
+	return c;
+}
+
+/* ref: src/nlp_formulation.cc:343-376 (GetCost: ForcesCostID -> force z, EEMotionCostID -> foot velocity x and y) */
+double orc_eval_cost(orc_problem *p, const double *x, double *grad)
+{
+	orc_set_x(p, x);
+	if (grad) memset(grad, 0, sizeof(double) * p->n);
+	const orc_shape *sh = &p->shape;
+	double f = 0.0;
+	for (int ee = 0; ee < ORC_NEE; ++ee) {
+		if (sh->cost_force_z != 0.0) f += node_cost(&p->ee_force[ee], 0, Z, sh->cost_force_z, grad);
+		if (sh->cost_ee_vel_xy != 0.0) {
+			f += node_cost(&p->ee_motion[ee], 1, X, sh->cost_ee_vel_xy, grad);
+			f += node_cost(&p->ee_motion[ee], 1, Y, sh->cost_ee_vel_xy, grad);
+		}
+	}
+	return f;
+}
+
 void orc_eval_g(orc_problem *p, const double *x, double *g)
 {
 	orc_set_x(p, x);

@@ -178,6 +178,7 @@ static int ipopt_attempt(orc_problem *p, const orc_ipopt_options *o, double *x, 
 	DV(ds, m); DV(dy, m); DV(dvL, m); DV(dvU, m); DV(tL, m); DV(tU, m); DV(uL, m); DV(uU, m);
 	DV(glx, n); DV(a_dx, n); DV(c_dx, n); DV(dx, n); DV(vtmp, n); DV(tmp, n); DV(last_x, n); DV(gJold, n); DV(xf, n);
 	DV(M, S->skyptr[n]); DV(xt, na);
+	DV(gfull, na); DV(gf, n);
 	DV(Sm, (size_t)LM_MAX * n); DV(Ym, (size_t)LM_MAX * n); DV(Bl, (size_t)2 * LM_MAX * n); DV(Z, (size_t)2 * LM_MAX * n);
 	unsigned char *iseq = (unsigned char *)calloc(m, 1), *hasL = (unsigned char *)calloc(m, 1), *hasU = (unsigned char *)calloc(m, 1);
 
@@ -218,6 +219,16 @@ static int ipopt_attempt(orc_problem *p, const orc_ipopt_options *o, double *x, 
 		vL[i] = hasL[i] ? 1.0 : 0.0; vU[i] = hasU[i] ? 1.0 : 0.0;
 	}
 	for (int i = 0; i < n; ++i) xf[i] = x[S->var_of[i]];
+	/* optional cost terms (orc_shape.cost_*; f == 0 on the reference's path): objective scaling like the rows',
+	 * min(1, 100 / ||grad f(x0)||_inf) over the free variables */
+	const int has_cost = p->shape.cost_force_z != 0.0 || p->shape.cost_ee_vel_xy != 0.0;
+	double df = 1.0, fval = 0.0;
+	if (has_cost) {
+		orc_eval_cost(p, x, gfull);
+		double mx = 0.0;
+		for (int i = 0; i < n; ++i) mx = dmax(mx, fabs(gfull[S->var_of[i]]));
+		if (mx > 100.0) df = dmax(100.0 / mx, 1e-8);
+	}
 
 	kkt_t K; memset(&K, 0, sizeof(K));
 	K.S = S; K.n = n; K.m = m; K.jv = jv; K.iseq = iseq; K.hasL = hasL; K.hasU = hasU; K.Lsky = M; K.Bl = Bl; K.Z = Z;
@@ -230,8 +241,9 @@ static int ipopt_attempt(orc_problem *p, const orc_ipopt_options *o, double *x, 
 	int free_mode = 1;
 	double mu_max = -1.0;
 	const double mu_min = dmin(1e-11, 0.5 * dmin(o->tol, o->compl_inf_tol));
-	double amu_theta_min = 1e300;                         /* AdaptiveMuUpdate's own filter: f == 0, so an entry (-margin,
-	                                                          theta_k - margin) with margin > 0 is passed only by theta <= theta_k - margin */
+	/* AdaptiveMuUpdate's own filter of (f, theta) pairs: a point passes when, against every entry, it is no larger in at least
+	 * one coordinate.  With f == 0 an entry (-margin, theta_k - margin) is passed only by theta <= theta_k - margin. */
+	double amu_f[ORC_FILTER_MAX], amu_th[ORC_FILTER_MAX]; int n_amu = 0;
 	double fphi[ORC_FILTER_MAX], fth[ORC_FILTER_MAX]; int nfilter = 0;   /* line-search filter */
 	double theta_max = -1.0, theta_min = -1.0;
 	int status = -1, it = 0, ls_count = 0;
@@ -245,6 +257,10 @@ static int ipopt_attempt(orc_problem *p, const orc_ipopt_options *o, double *x, 
 		for (int i = 0; i < m; ++i) { if (hasL[i]) sL[i] = s[i] - dL[i]; if (hasU[i]) sU[i] = dU[i] - s[i]; }
 		/* ---- limited-memory update (LimMemQuasiNewtonUpdater::UpdateHessian): s = x+ - x, y = (J+ - J)' lambda+ */
 		JT_TIMES(jv, y, glx);
+		if (has_cost) {                                       /* grad_x L = grad f + J' lambda */
+			fval = df * orc_eval_cost(p, x, gfull);
+			for (int i = 0; i < n; ++i) { gf[i] = df * gfull[S->var_of[i]]; glx[i] += gf[i]; }
+		}
 		if (have_last) {
 			double sTy = 0, sTs = 0, yTy = 0;
 			for (int i = 0; i < n; ++i) { const double sn = xf[i] - last_x[i], yn = glx[i] - gJold[i]; vtmp[i] = sn; tmp[i] = yn; sTy += sn * yn; sTs += sn * sn; yTy += yn * yn; }
@@ -288,12 +304,14 @@ static int ipopt_attempt(orc_problem *p, const orc_ipopt_options *o, double *x, 
 		if (o->verbose) printf("%4d %.2e %.2e %5.1f %.2e %.2e %.2e%c %2d  E=%.2e sw=%.3g np=%d %s\n", it, viol, dual_inf, log10(mu), dnorm,
 		                       alpha_du, alpha_pr, tag, ls_count, nlp_error, sigma_w, n_pairs, free_mode ? "" : "F");
 		if (!(nlp_error == nlp_error) || !(theta == theta)) { status = -13; break; }
-		if (nlp_error <= o->tol && dual_inf <= o->dual_inf_tol && viol <= o->constr_viol_tol && compl <= o->compl_inf_tol) { status = 0; break; }
+		/* the absolute tolerances apply to the unscaled problem: dual infeasibility and complementarity carry the objective's scale */
+		if (nlp_error <= o->tol && dual_inf / df <= o->dual_inf_tol && viol <= o->constr_viol_tol && compl / df <= o->compl_inf_tol) { status = 0; break; }
 		if (it >= o->max_iter) { status = -1; break; }
 
 		/* ---- barrier parameter (AdaptiveMuUpdate::UpdateBarrierParameter) */
 		if (mu_max < 0) mu_max = 1e3 * avrg_compl;
-		const int acceptable = theta <= amu_theta_min;
+		int acceptable = 1;
+		for (int k = 0; k < n_amu; ++k) if (!(fval <= amu_f[k] || theta <= amu_th[k])) { acceptable = 0; break; }
 		if (!free_mode) {
 			if (acceptable) { free_mode = 1; }
 			else {
@@ -313,7 +331,14 @@ static int ipopt_attempt(orc_problem *p, const orc_ipopt_options *o, double *x, 
 		}
 		if (free_mode && acceptable) {                        /* RememberCurrentPointAsAccepted */
 			const double mg = 1e-5 * dmin(1.0, theta);
-			if (mg > 0.0 && theta - mg < amu_theta_min) amu_theta_min = theta - mg;
+			if (mg > 0.0) {
+				const double ef = fval - mg, eth = theta - mg;
+				int w = 0;                                        /* entries the new one dominates leave (Filter::AddEntry) */
+				for (int k = 0; k < n_amu; ++k) if (!(ef <= amu_f[k] && eth <= amu_th[k])) { amu_f[w] = amu_f[k]; amu_th[w] = amu_th[k]; w++; }
+				n_amu = w;
+				if (n_amu == ORC_FILTER_MAX) { memmove(amu_f, amu_f + 1, sizeof(double) * (ORC_FILTER_MAX - 1)); memmove(amu_th, amu_th + 1, sizeof(double) * (ORC_FILTER_MAX - 1)); n_amu--; }
+				amu_f[n_amu] = ef; amu_th[n_amu] = eth; n_amu++;
+			}
 		}
 
 		/* ---- factorization and the two directions; a non-positive pivot or a non-finite direction repeats them with
@@ -454,6 +479,7 @@ static int ipopt_attempt(orc_problem *p, const orc_ipopt_options *o, double *x, 
 			if (hasL[i]) { phi0 -= mu * log(sL[i]); gBD -= mu * ds[i] / sL[i]; }
 			if (hasU[i]) { phi0 -= mu * log(sU[i]); gBD += mu * ds[i] / sU[i]; }
 		}
+		if (has_cost) { phi0 += fval; for (int i = 0; i < n; ++i) gBD += gf[i] * dx[i]; }
 		if (theta_max < 0) { theta_max = 1e4 * dmax(1.0, theta); theta_min = 1e-4 * dmax(1.0, theta); }
 		double alpha_min = 1e-5;
 		if (gBD < 0) {
@@ -477,6 +503,7 @@ static int ipopt_attempt(orc_problem *p, const orc_ipopt_options *o, double *x, 
 				if (hasL[i]) ph_t -= mu * log(st[i] - dL[i]);
 				if (hasU[i]) ph_t -= mu * log(dU[i] - st[i]);
 			}
+			if (has_cost) ph_t += df * orc_eval_cost(p, xt, NULL);
 			int ok = 0;
 			if (th_t <= theta_max && ph_t == ph_t && fabs(ph_t) < 1e300) {
 				const int switching = gBD < 0 && alpha * pow(-gBD, 2.3) > pow(theta, 1.1);
@@ -523,18 +550,20 @@ static int ipopt_attempt(orc_problem *p, const orc_ipopt_options *o, double *x, 
 			if (hasL[i]) vL[i] = dmin(dmax(vL[i], mu_c / (1e10 * sL[i])), 1e10 * mu_c / sL[i]);
 			if (hasU[i]) vU[i] = dmin(dmax(vU[i], mu_c / (1e10 * sU[i])), 1e10 * mu_c / sU[i]);
 		}
-		JT_TIMES(jv, y, gJold);                              /* J(x_k)' lambda_{k+1} for the next limited-memory pair */
+		JT_TIMES(jv, y, gJold);                              /* grad_x L(x_k, lambda_{k+1}) for the next limited-memory pair */
+		if (has_cost) for (int i = 0; i < n; ++i) gJold[i] += gf[i];
 		GATHER_J(jv);
 		it++;
 	}
 	res->status = status; res->iters = it;
+	res->objective = has_cost ? orc_eval_cost(p, x, NULL) : 0.0;
 	(void)n_eq; (void)jv_old;
 	free(Jd); free(jv); free(jv_old); free(sc); free(g); free(gt); free(r); free(rt); free(s); free(st); free(y); free(vL); free(vU);
 	free(dL); free(dU); free(sL); free(sU); free(Sig); free(w); free(rs); free(rcd); free(rvL); free(rvU);
 	free(a_ds); free(a_dy); free(a_dvL); free(a_dvU); free(c_ds); free(c_dy); free(c_dvL); free(c_dvU);
 	free(ds); free(dy); free(dvL); free(dvU); free(tL); free(tU); free(uL); free(uU);
 	free(glx); free(a_dx); free(c_dx); free(dx); free(vtmp); free(tmp); free(last_x); free(gJold); free(xf); free(M); free(xt);
-	free(Sm); free(Ym); free(Bl); free(Z); free(iseq); free(hasL); free(hasU);
+	free(gfull); free(gf); free(Sm); free(Ym); free(Bl); free(Z); free(iseq); free(hasL); free(hasU);
 	orc_free_struct(S);
 	return status;
 }

@@ -65,6 +65,10 @@ typedef struct {
 	/* optional: the terrain derivatives the reference carries commented out (ref: src/custom_terrain.cpp:101-124,133-156) in the
 	 * terrain rows' Jacobian and in the force rows' contact basis (ref: src/height_map.cc:95-141, src/force_constraint.cc:67-135) */
 	int    terrain_gradients;
+	/* optional cost terms (Parameters::costs_, empty on the reference's path; ref: src/parameters.cc:62-63, src/nlp_formulation.cc:343-376,
+	 * src/node_cost.cc:53-83): weight of ForcesCostID (force z of every force node, squared) and of EEMotionCostID (foot velocity
+	 * x and y of every motion node, squared); 0 = the term is absent */
+	double cost_force_z, cost_ee_vel_xy;
 } orc_shape;
 
 typedef struct {
@@ -128,6 +132,8 @@ void orc_eval_g(orc_problem *p, const double *x, double *g);
 /* dense row-major m*n Jacobian; mask (nullable, m*n bytes) gets 1 where the
  * reference's FillJacobianBlock creates a structural entry */
 void orc_eval_jac(orc_problem *p, const double *x, double *J, unsigned char *mask);
+/* objective = sum of the NodeCost terms of orc_shape (0 when none); grad (nullable, n entries) is its gradient */
+double orc_eval_cost(orc_problem *p, const double *x, double *grad);
 
 /* ---- 1 kHz sampler (towr_csv.c) ---- */
 int  orc_csv_rows(const orc_problem *p, double dt);
@@ -192,6 +198,7 @@ typedef struct {
 	int chol_fix;
 	int n_regularized;        /* factorizations repeated with W + delta_w I */
 	int retried;              /* the second attempt ran */
+	double objective;         /* unscaled f at the returned point (0 without cost terms) */
 } orc_ipopt_result;
 
 void orc_ipopt_default_options(orc_ipopt_options *o);

@@ -260,6 +260,7 @@ void orc_default_shape(orc_shape *s)
 	s->dt_dynamic = 0.1;
 	s->dt_rom = 0.08;
 	s->base_rom = 0; s->dt_base_rom = 0.1 / 4.0; s->terrain_gradients = 0;
+	s->cost_force_z = 0.0; s->cost_ee_vel_xy = 0.0;
 	s->combo = ORC_CUSTOM;
 	s->duration = 5.0;
 }

@@ -67,7 +67,8 @@ class Shape(C.Structure):
                 ("dt_base_poly", C.c_double), ("force_polys_per_stance", C.c_int),
                 ("ee_polys_per_swing", C.c_int), ("dt_dynamic", C.c_double),
                 ("dt_rom", C.c_double), ("combo", C.c_int), ("duration", C.c_double),
-                ("base_rom", C.c_int), ("dt_base_rom", C.c_double)]
+                ("base_rom", C.c_int), ("dt_base_rom", C.c_double),
+                ("cost_force_z", C.c_double), ("cost_ee_vel_xy", C.c_double)]
 
 
 class Options(C.Structure):

@@ -304,6 +304,17 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 		fix(0, last, 0, 0, QP_GOAL + 0); fix(0, last, 0, 1, QP_GOAL + 1);
 		for (int ee = 0; ee < QTOS_NEE; ++ee) for (int d = 0; d < 3; ++d) fix(2 + ee, 0, 0, d, QP_EE + 3 * ee + d);
 	}
+	/* optional cost terms (ref: nlp_formulation.cc:343-376, node_cost.cc:53-83): weight * value^2 per NODE, so a variable
+	 * shared by several nodes collects the weight once per node */
+	H->cost_c.clear();
+	if (sh.cost_force_z != 0.0 || sh.cost_ee_vel_xy != 0.0) {
+		H->cost_c.assign(n_all, 0.0);
+		for (int ee = 0; ee < QTOS_NEE; ++ee) {
+			for (int node = 0; node < spl[6 + ee].n_nodes(); ++node) { const int v = nv(6 + ee, node, 0 * 3 + 2); if (v >= 0) H->cost_c[v] += sh.cost_force_z; }
+			for (int node = 0; node < spl[2 + ee].n_nodes(); ++node)
+				for (int d = 0; d < 2; ++d) { const int v = nv(2 + ee, node, 1 * 3 + d); if (v >= 0) H->cost_c[v] += sh.cost_ee_vel_xy; }
+		}
+	}
 	std::vector<int> free_of(n_all, -1), var_of_free;
 	for (int v = 0; v < n_all; ++v) if (H->fix_src[v] < 0) { free_of[v] = (int)var_of_free.size(); var_of_free.push_back(v); }
 	const int n_free = (int)var_of_free.size();

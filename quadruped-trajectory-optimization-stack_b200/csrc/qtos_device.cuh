@@ -43,6 +43,7 @@ struct DevTables {
 	const int *jgc_ptr; const uint2_t *jgc; const int16_t *eq_rows, *iq_rows;
 	const double *csv_t, *csv_tl; const uint8_t *csv_id;
 	const double *dur; int dur_ld;          /* [10][dur_ld] */
+	const double *cost_c;                   /* [n_all] objective coefficients (f = sum cost_c[v] x_v^2), nullptr without cost terms */
 	double nominal[QTOS_NEE][3];
 };
 
@@ -73,7 +74,8 @@ struct DevWork {
 /* IPOPT algorithm state per problem (doubles) */
 enum { IP_MU = 0, IP_TAU, IP_FREE, IP_MU_MAX, IP_AMU_THMIN, IP_TH_MAX, IP_TH_MIN, IP_SIGMA_W, IP_NPAIRS, IP_SKIPPED, IP_HAVE_LAST,
        IP_NFILTER, IP_SIGMA_F, IP_AVRG, IP_ERR, IP_THETA, IP_GL2, IP_PR2, IP_ALPHA_PR, IP_ALPHA_DU, IP_DNORM, IP_LS, IP_TAG,
-       IP_HEAD, IP_ITER, IP_RETRY, IP_DELTA_W, IP_DELTA_LAST, IP_SIGMA_MIN, IP_ITER_BASE, IP_FPHI = 32, IP_FTH = 64, IP_MID = 96, IP_N = 256 };
+       IP_HEAD, IP_ITER, IP_RETRY, IP_DELTA_W, IP_DELTA_LAST, IP_SIGMA_MIN, IP_ITER_BASE, IP_OBJ_SCALE, IP_FVAL, IP_FPHI = 32, IP_FTH = 64, IP_MID = 96,
+       IP_NAMU = 240, IP_AMUF = 256, IP_AMUT = 288, IP_N = 320 };   /* IP_AMUF / IP_AMUT: the barrier update's (f, theta) filter, used with cost terms */
 #define IP_FILTER_MAX 32
 #define IP_LM 6                             /* limited-memory history capacity */
 #define IP_NRHS 16                          /* right-hand sides of the factorization: 6 S + 6 Y columns, affine, centering, 2 spare */

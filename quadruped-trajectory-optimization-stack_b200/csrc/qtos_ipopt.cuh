@@ -79,10 +79,21 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt)
 	/* v: 0 dual_inf (max) 1 primal_inf (max) 2 compl (max) 3 sum|y| 4 sum z 5 viol (max) 6 theta (sum) 7 sum s z 8 sum 0*r
 	 *    9 |grad L|^2 10 |c|^2 11 max |s z - mu| 12 s'y 13 s's 14 y'y */
 	double v[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	/* optional cost terms (qtos_shape.cost_*): f = df sum c_v x_v^2, grad_x L = grad f + J' lambda; f == 0 otherwise */
+	const double df = T.cost_c ? ip[IP_OBJ_SCALE] : 1.0;
+	double fval = 0.0;
+	if (T.cost_c) {
+		double u[1] = {0.0};
+		for (int i = tid; i < T.n_all; i += blockDim.x) u[0] += T.cost_c[i] * x[i] * x[i];
+		const int ops[1] = {0};
+		block_reduce<1>(u, ops, red);
+		fval = df * u[0];
+	}
 	for (int i = tid; i < T.npad; i += blockDim.x) {
-		const double g = jt_gather(T, Jv, y, i);
+		double g = jt_gather(T, Jv, y, i);
 		const int var = T.var_of_perm[i];
 		const double xi = var >= 0 ? x[var] : 0.0;
+		if (T.cost_c && var >= 0) g += 2.0 * df * T.cost_c[var] * xi;
 		glx[i] = g;
 		v[0] = fmax(v[0], fabs(g)); v[9] += g * g;
 		if (have_last) {
@@ -111,7 +122,8 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt)
 	const double nlp_error = fmax(fmax(dual_inf / s_d, primal_inf), compl_ / s_c);
 	const double avrg_compl = v[7] / (double)nbnd;
 	const bool invalid = !(v[8] == 0.0) || !(nlp_error == nlp_error) || !(theta == theta);
-	const bool conv = !invalid && nlp_error <= opt.tol && dual_inf <= opt.dual_inf_tol && viol <= opt.constr_viol_tol && compl_ <= opt.compl_inf_tol;
+	/* the absolute tolerances apply to the unscaled problem: dual infeasibility and complementarity carry the objective's scale */
+	const bool conv = !invalid && nlp_error <= opt.tol && dual_inf / df <= opt.dual_inf_tol && viol <= opt.constr_viol_tol && compl_ / df <= opt.compl_inf_tol;
 	const bool out_of_time = it >= cpu_budget(opt);
 	const bool stop = !retry && (invalid || conv || it >= opt.max_iter || out_of_time);
 	if (tid == 0 && !retry) {
@@ -153,7 +165,14 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt)
 	 *      the free-mode oracle needs the two directions and runs in kip_step */
 	const double mu_min = fmin(1e-11, 0.5 * fmin(opt.tol, opt.compl_inf_tol));
 	if (mu_max < 0.0) mu_max = 1e3 * avrg_compl;
-	const bool acceptable = theta <= amu_thmin;
+	/* AdaptiveMuUpdate's own filter of (f, theta) pairs: a point passes when, against every entry, it is no larger in at least one
+	 * coordinate.  With f == 0 the entries (-margin, theta_k - margin) collapse to their smallest theta (amu_thmin). */
+	bool acceptable = theta <= amu_thmin;
+	const int n_amu = T.cost_c ? (int)ip[IP_NAMU] : 0;
+	if (T.cost_c) {
+		acceptable = true;
+		for (int k = 0; k < n_amu; ++k) if (!(fval <= ip[IP_AMUF + k] || theta <= ip[IP_AMUT + k])) { acceptable = false; break; }
+	}
 	if (retry) { /* done in the first attempt */ }
 	else if (!free_mode) {
 		if (acceptable) free_mode = 1;
@@ -170,10 +189,9 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt)
 		mu = fmin(fmax(0.8 * avrg_compl, mu_min), mu_max);
 		tau = fmax(0.99, 1.0 - mu); nfilter = 0;
 	}
-	if (!retry && free_mode && acceptable) {              /* RememberCurrentPointAsAccepted */
-		const double mg = 1e-5 * fmin(1.0, theta);
-		if (mg > 0.0 && theta - mg < amu_thmin) amu_thmin = theta - mg;
-	}
+	const double amu_mg = 1e-5 * fmin(1.0, theta);
+	const bool remember = !retry && free_mode && acceptable && amu_mg > 0.0;     /* RememberCurrentPointAsAccepted */
+	if (remember && theta - amu_mg < amu_thmin) amu_thmin = theta - amu_mg;
 
 	/* ---- Sigma and the first-pass row weights of the two right-hand sides (PDFullSpaceSolver in condensed form) */
 	const double rho = 1.0 / opt.delta_c;
@@ -229,6 +247,16 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt)
 		ip[IP_SIGMA_W] = sigma_w; ip[IP_SIGMA_F] = sigma_f; ip[IP_NPAIRS] = n_pairs; ip[IP_SKIPPED] = skipped; ip[IP_HEAD] = head;
 		ip[IP_HAVE_LAST] = 1.0; ip[IP_NFILTER] = nfilter; ip[IP_AVRG] = avrg_compl; ip[IP_ERR] = nlp_error; ip[IP_THETA] = theta;
 		ip[IP_GL2] = v[9]; ip[IP_PR2] = v[10];
+		if (T.cost_c) {
+			ip[IP_FVAL] = fval;
+			if (remember) {
+				const double ef = fval - amu_mg, eth = theta - amu_mg;
+				int w = 0;                                 /* entries the new one dominates leave (Filter::AddEntry) */
+				for (int k = 0; k < n_amu; ++k) if (!(ef <= ip[IP_AMUF + k] && eth <= ip[IP_AMUT + k])) { ip[IP_AMUF + w] = ip[IP_AMUF + k]; ip[IP_AMUT + w] = ip[IP_AMUT + k]; w++; }
+				if (w == IP_FILTER_MAX) { for (int k = 1; k < w; ++k) { ip[IP_AMUF + k - 1] = ip[IP_AMUF + k]; ip[IP_AMUT + k - 1] = ip[IP_AMUT + k]; } w--; }
+				ip[IP_AMUF + w] = ef; ip[IP_AMUT + w] = eth; ip[IP_NAMU] = w + 1;
+			}
+		}
 		W.flags[pid] = 0;                              /* k_factor reports a non-positive pivot here */
 		W.active[atomicAdd(W.n_active, 1)] = pid;
 	}
@@ -700,7 +728,11 @@ kip_step(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield
 	/* ---- search direction aff + sigma cen; fraction to the boundary; barrier objective and its directional derivative */
 	/* v: 0 dnorm (max) 1 alpha_max (min) 2 alpha_du (min) 3 phi0 (sum) 4 gBD (sum) */
 	double v[5] = {0.0, 1.0, 1.0, 0.0, 0.0};
-	for (int i = tid; i < T.npad; i += blockDim.x) { const double d = adx[i] + sigma * cdx[i]; b[i] = d; v[0] = fmax(v[0], fabs(d)); }
+	const double df = T.cost_c ? ip[IP_OBJ_SCALE] : 1.0;
+	for (int i = tid; i < T.npad; i += blockDim.x) {
+		const double d = adx[i] + sigma * cdx[i]; b[i] = d; v[0] = fmax(v[0], fabs(d));
+		if (T.cost_c) { const int var = T.var_of_perm[i]; if (var >= 0) v[4] += 2.0 * df * T.cost_c[var] * x[var] * d; }   /* grad f . dx */
+	}
 	for (int i = tid; i < T.m; i += blockDim.x) {
 		const int fl = T.row_flags[i];
 		if (fl & ROW_EQ) continue;
@@ -720,7 +752,7 @@ kip_step(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield
 		}
 	}
 	{ const int ops[5] = {1, 2, 2, 0, 0}; block_reduce<5>(v, ops, red); }
-	const double dnorm = v[0], alpha_max = v[1], alpha_du = v[2], phi0 = v[3], gBD = v[4];
+	const double dnorm = v[0], alpha_max = v[1], alpha_du = v[2], phi0 = v[3] + (T.cost_c ? ip[IP_FVAL] : 0.0), gBD = v[4];
 	/* ---- filter line search (BacktrackingLineSearch + FilterLSAcceptor) */
 	if (theta_max < 0.0) { theta_max = 1e4 * fmax(1.0, theta); theta_min = 1e-4 * fmax(1.0, theta); }
 	double alpha_min = 1e-5;
@@ -755,6 +787,7 @@ kip_step(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield
 			if (fl & ROW_HASL) u[1] -= mu * log(sn - dLb[i]);
 			if (fl & ROW_HASU) u[1] -= mu * log(dUb[i] - sn);
 		}
+		if (T.cost_c) for (int i = tid; i < T.n_all; i += blockDim.x) u[1] += df * T.cost_c[i] * xt[i] * xt[i];
 		{ const int ops[2] = {0, 0}; block_reduce<2>(u, ops, red); }
 		th_t = u[0]; ph_t = u[1];
 		bool ok = false;
@@ -801,9 +834,15 @@ kip_step(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield
 		if (fl & ROW_HASU) { const double su = dUb[i] - s[i]; vU[i] = fmin(fmax(vU[i], mu_c / (1e10 * su)), 1e10 * mu_c / su); }
 	}
 	__syncthreads();
-	/* J(x_k)' lambda_{k+1} for the next limited-memory pair (the Jacobian values are still those of x_k) */
+	/* grad_x L(x_k, lambda_{k+1}) = grad f(x_k) + J(x_k)' lambda_{k+1} for the next limited-memory pair (the Jacobian values are
+	 * still those of x_k, and kip_prepare left x_k in W.lastx) */
 	double *gJold = WS(gJold, T.npad);
-	for (int i = tid; i < T.npad; i += blockDim.x) gJold[i] = jt_gather(T, Jv, y, i);
+	const double *lastx = WS(lastx, T.npad);
+	for (int i = tid; i < T.npad; i += blockDim.x) {
+		double g = jt_gather(T, Jv, y, i);
+		if (T.cost_c) { const int var = T.var_of_perm[i]; if (var >= 0) g += 2.0 * df * T.cost_c[var] * lastx[i]; }
+		gJold[i] = g;
+	}
 	if (tid == 0) {
 		if (!ftype) {
 			if (nfilter == IP_FILTER_MAX) { for (int k = 1; k < IP_FILTER_MAX; ++k) { ip[IP_FPHI + k - 1] = sfphi[k]; ip[IP_FTH + k - 1] = sfth[k]; } nfilter--; }

@@ -174,9 +174,18 @@ scaling:
 		double *ip = WS(ipst, IP_N), *tr = WS(trace, QTOS_TRACE_ITERS * QTOS_TRACE_COLS);
 		const double base = (double)W.iters[pid];          /* 0, or the iterations of the first attempt */
 		for (int i = threadIdx.x; i < IP_N; i += blockDim.x)
-			ip[i] = i == IP_MU || i == IP_FREE || i == IP_SIGMA_W ? 1.0 : (i == IP_MU_MAX || i == IP_TH_MAX || i == IP_TH_MIN ? -1.0 : (i == IP_AMU_THMIN ? 1e300 :
+			ip[i] = i == IP_MU || i == IP_FREE || i == IP_SIGMA_W || i == IP_OBJ_SCALE ? 1.0 : (i == IP_MU_MAX || i == IP_TH_MAX || i == IP_TH_MIN ? -1.0 : (i == IP_AMU_THMIN ? 1e300 :
 			        (i == IP_SIGMA_MIN ? opt.lm_init_val_min : (i == IP_ITER_BASE ? base : 0.0))));
 		for (int i = threadIdx.x; i < QTOS_TRACE_ITERS * QTOS_TRACE_COLS; i += blockDim.x) tr[i] = 0.0;
+		if (T.cost_c) {
+			/* objective scaling like the rows': min(1, 100 / ||grad f(x0)||_inf) over the free variables (f = sum c_v x_v^2) */
+			__shared__ double redc[32];
+			double u[1] = {0.0};
+			for (int v = threadIdx.x; v < T.n_all; v += blockDim.x) if (T.fix_src[v] < 0) u[0] = fmax(u[0], fabs(2.0 * T.cost_c[v] * x[v]));
+			const int ops[1] = {1};
+			block_reduce<1>(u, ops, redc);
+			if (threadIdx.x == 0 && u[0] > 100.0) ip[IP_OBJ_SCALE] = fmax(100.0 / u[0], 1e-8);
+		}
 	}
 }
 

@@ -87,6 +87,7 @@ struct HostTables {
 	std::vector<uint8_t> x0_spline, x0_deriv, x0_dim;   /* [n_all] */
 	std::vector<int16_t> x0_node;                        /* node whose interpolated value wins */
 	std::vector<int8_t>  fix_src;                        /* [n_all] index into P[] or -1 if free */
+	std::vector<double>  cost_c;                         /* [n_all] objective f(x) = sum_v cost_c[v] x_v^2 (NodeCost terms); empty = none */
 	std::vector<int16_t> perm_of_var;                    /* [n_all] permuted free index or -1 */
 	std::vector<int16_t> var_of_perm;                    /* [npad] full index or -1 (padding) */
 	/* rows */

@@ -618,3 +618,45 @@ def test_more_windows_than_slots_flow_through_the_pool():
     r2, x2, _ = small.solve(p, Q.default_options(algorithm=Q.ALG_FAST))      # the FAST algorithm still goes chunk by chunk
     assert set(r2["status"]) <= {0, -1, -2}
     big.close(); small.close()
+
+
+def test_cost_terms_option(oracle):
+    """qtos_shape.cost_force_z / cost_ee_vel_xy: TOWR's optional NodeCost terms (Parameters::costs_, nlp_formulation.cc:343-376,
+    node_cost.cc:53-83) as the objective of QTOS_ALG_IPOPT.  The reference logs no run with an objective, so the
+    chain is emulator (pinned to the logged f == 0 tables) -> C oracle (tests/test_cost_terms.py) -> kernels (here): the GPU
+    prints the C oracle's iteration table for the first iterations, every converged plan is feasible, and where both converge the
+    objectives agree to within 1e-3 of the initial objective (north_star: objective within 1e-3 relative).  With an objective the
+    algorithm needs ~100 iterations and its limited-memory steps reach ||d|| ~ 1e3, so late iterations amplify round-off: in
+    the oracle alone 1-3 of 8 such windows end at the iteration limit or in a failed line search, and WHICH ones is not stable
+    against last-bit changes -- the status comparison is therefore a count, not window by window."""
+    sh = Q.default_shape("C1", 2.0); sh.cost_force_z = 1.0
+    so = oracle.default_shape("C1", 2.0); so.cost_force_z = 1.0
+    S = Q.Solver(sh, max_batch=8)
+    grid, res = HF.rough_terrain(11)
+    flat = np.zeros((40, 20))
+    hf_rough, hf_flat = S.upload_heightfield(grid, res), S.upload_heightfield(flat, 0.1)
+    p = workloads.multistart_problems(8, grid, res, seed=11, hf_id=hf_rough)
+    p["start_pos"][0] = (0, 0, 0.24); p["goal"][0] = (0.5, 0, 0.24); p["ee"][0] = [(0.21, 0.18, 0), (0.21, -0.18, 0), (-0.21, 0.18, 0), (-0.21, -0.18, 0)]
+    p["hf_id"][0] = hf_flat
+    r, x, _ = S.solve(p)
+    tr = S.trace(8)
+    fmt = lambda a: "%.2e %.2e %5.1f %.2e %.2e %.2e%s %d" % (a[0], a[1], np.log10(a[2]), a[3], a[4], a[5], chr(int(a[7])) if a[7] else " ", int(a[6]))
+    same_status = 0
+    for i in range(8):
+        po = oracle_problem(oracle, so, p[i], flat if i == 0 else grid, 0.1 if i == 0 else res)
+        f0 = po.cost(po.x0())
+        xo, ro = po.solve_ipopt()
+        for k in range(min(6, ro.n_trace)):
+            o_row = (ro.tr_inf_pr[k], ro.tr_inf_du[k], ro.tr_mu[k], ro.tr_dnorm[k], ro.tr_alpha_du[k], ro.tr_alpha_pr[k], ro.tr_ls[k], ord(ro.tr_tag[k:k + 1].decode()) if ro.tr_tag[k:k + 1] != b" " else 0)
+            assert fmt(tr[i, k]) == fmt(o_row), (i, k, fmt(tr[i, k]), fmt(o_row))
+        assert abs(tr[i, 0, 1] - 2 * 1.5 * 9.80665 / 4) < 1e-12             # iteration 0: inf_du = ||grad f(x0)||_inf
+        same_status += int(r["status"][i] == ro.status)
+        if r["status"][i] == 0:
+            assert r["constr_viol"][i] <= 1e-4
+            if ro.status == 0:
+                assert abs(po.cost(x[i]) - ro.objective) <= 1e-3 * f0, (i, po.cost(x[i]), ro.objective, f0)
+    print("cost terms: statuses", r["status"], "iters", r["iters"], "same status as the oracle:", same_status, "of 8")
+    assert same_status >= 4 and (r["status"] == 0).sum() >= 4
+    with pytest.raises(Exception):
+        S.solve(p, Q.default_options(algorithm=Q.ALG_FAST))      # the FAST algorithm assumes f == 0
+    S.close()
