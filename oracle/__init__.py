@@ -31,7 +31,8 @@ class Shape(C.Structure):
                 ("ee_polys_per_swing", C.c_int), ("dt_dynamic", C.c_double),
                 ("dt_rom", C.c_double), ("combo", C.c_int), ("duration", C.c_double),
                 ("base_rom", C.c_int), ("dt_base_rom", C.c_double), ("terrain_gradients", C.c_int),
-                ("cost_force_z", C.c_double), ("cost_ee_vel_xy", C.c_double)]
+                ("cost_force_z", C.c_double), ("cost_ee_vel_xy", C.c_double),
+                ("optimize_timings", C.c_int), ("phase_dur_min", C.c_double), ("phase_dur_max", C.c_double)]
 
 
 class Instance(C.Structure):
@@ -100,6 +101,7 @@ def lib():
         L.orc_get_bounds.argtypes = [C.c_void_p, dp, dp, dp, dp]
         L.orc_get_phase_durations.argtypes = [C.c_void_p, C.c_int, dp]
         L.orc_get_layout.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_get_schedule_layout.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_height.restype = C.c_double
         L.orc_height.argtypes = [C.POINTER(Heightfield), C.c_double, C.c_double]
         L.orc_height_cell.argtypes = [C.POINTER(Heightfield), C.c_double, C.c_double, C.POINTER(C.c_longlong)]
@@ -204,6 +206,12 @@ class Problem:
         ro = (C.c_int * 20)()
         lib().orc_get_layout(self.h, vo, ro)
         return list(vo), list(ro)
+
+    def schedule_layout(self):
+        """(variable offset of every foot's phase durations, TotalDuration row of every foot); -1 when timings are fixed"""
+        so, rt = (C.c_int * 4)(), (C.c_int * 4)()
+        lib().orc_get_schedule_layout(self.h, so, rt)
+        return list(so), list(rt)
 
     def g(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)

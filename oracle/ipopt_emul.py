@@ -122,7 +122,13 @@ class IpoptEmulator:
         self.dL = np.where(self.hasL, dl * sc[self.iq], -np.inf)
         self.dU = np.where(self.hasU, du * sc[self.iq], np.inf)
         self.gl_raw, self.gu_raw = gl, gu
-        self.n_bounds = int(self.hasL.sum() + self.hasU.sum())
+        # bounds on the variables themselves (none on the reference's path, where every bounded variable is fixed; the gait-timing
+        # option bounds the phase durations): multipliers z_L, z_U, relaxed like the slack bounds
+        fl, fu = xl[self.free], xu[self.free]
+        self.xhasL, self.xhasU = fl > -INF, fu < INF
+        self.xL = np.where(self.xhasL, fl - o.bound_relax_factor * np.maximum(1.0, np.abs(fl)), -np.inf)
+        self.xU = np.where(self.xhasU, fu + o.bound_relax_factor * np.maximum(1.0, np.abs(fu)), np.inf)
+        self.n_bounds = int(self.hasL.sum() + self.hasU.sum() + self.xhasL.sum() + self.xhasU.sum())
         # optional cost terms (f == 0 on the reference's path): gradient-based objective scaling at the starting point
         self.has_cost = hasattr(problem, "cost") and (problem.shape.cost_force_z != 0.0 or problem.shape.cost_ee_vel_xy != 0.0)
         self.df = 1.0
@@ -168,14 +174,20 @@ class IpoptEmulator:
         lu = sla.lu_factor(K)
         return (lu, K)
 
-    def kkt_solve(self, fac, Sig, Jd, rx, rs, rc, rd, rvL, rvU, sL, sU, vL, vU):
-        """solves the 8-block primal-dual system  K * sol = rhs  (PDFullSpaceSolver::SolveOnce)."""
+    def kkt_solve(self, fac, Sig, Jd, rx, rs, rc, rd, rvL, rvU, sL, sU, vL, vU, xb=None):
+        """solves the 8-block primal-dual system  K * sol = rhs  (PDFullSpaceSolver::SolveOnce).
+        xb = (rzL, rzU, xsL, xsU, zL, zU): the blocks of the variable bounds (their Sigma is part of the factored W)."""
         import scipy.linalg as sla
         lu, K = fac
         n = self.n
         aug_s = rs.copy()
         aug_s[self.hasL] += rvL / sL
         aug_s[self.hasU] -= rvU / sU
+        rx = rx.copy()
+        if xb is not None:
+            rzL, rzU, xsL, xsU, zL, zU = xb
+            rx[self.xhasL] += rzL / xsL
+            rx[self.xhasU] -= rzU / xsU
         b = np.concatenate([rx + Jd.T @ (Sig * rd + aug_s), rc])
         sol = sla.lu_solve(lu, b)
         r = b - K @ sol                                   # one refinement step on the condensed system
@@ -185,7 +197,9 @@ class IpoptEmulator:
         dyd = Sig * ds - aug_s
         dvL = (rvL - vL * ds[self.hasL]) / sL
         dvU = (rvU + vU * ds[self.hasU]) / sU
-        return dx, ds, dyc, dyd, dvL, dvU
+        if xb is not None:
+            return dx, ds, dyc, dyd, dvL, dvU, (rzL - zL * dx[self.xhasL]) / xsL, (rzU + zU * dx[self.xhasU]) / xsU
+        return dx, ds, dyc, dyd, dvL, dvU, np.zeros(0), np.zeros(0)
 
     # ---- the algorithm
     def solve(self):
@@ -193,6 +207,14 @@ class IpoptEmulator:
         n, mc, md = self.n, self.mc, self.md
         hasL, hasU, dL, dU = self.hasL, self.hasU, self.dL, self.dU
         x = self.x_full[self.free].copy()
+        xhasL, xhasU, xL, xU = self.xhasL, self.xhasU, self.xL, self.xU
+        if xhasL.any() or xhasU.any():                     # DefaultIterateInitializer::push_variables on x
+            xw = np.where(xhasL & xhasU, xU - xL, np.inf)
+            qL = np.minimum(o.bound_push * np.maximum(1.0, np.abs(np.where(xhasL, xL, 0.0))), o.bound_frac * xw)
+            qU = np.minimum(o.bound_push * np.maximum(1.0, np.abs(np.where(xhasU, xU, 0.0))), o.bound_frac * xw)
+            x = np.where(xhasL, np.maximum(x, xL + qL), x)
+            x = np.where(xhasU, np.minimum(x, xU - qU), x)
+        zL, zU = np.ones(int(xhasL.sum())), np.ones(int(xhasU.sum()))
         c, d, graw = self.cd(x)
         Jc, Jd = self.jac(x)
         fval, gf = self.f(x, with_grad=True)
@@ -232,8 +254,12 @@ class IpoptEmulator:
         def slacks(s):
             return s[hasL] - dL[hasL], dU[hasU] - s[hasU]
 
+        def xslacks(x_):
+            return x_[xhasL] - xL[xhasL], xU[xhasU] - x_[xhasU]
+
         while True:
             sL, sU = slacks(s)
+            xsL, xsU = xslacks(x)
             # ---- L-BFGS update (LimMemQuasiNewtonUpdater::UpdateHessian)
             if last is not None:
                 lx, lJc, lJd, lgf = last
@@ -267,15 +293,18 @@ class IpoptEmulator:
 
             # ---- error measures (IpoptCalculatedQuantities)
             glx = gf + Jc.T @ yc + Jd.T @ yd
+            glx[xhasL] -= zL
+            glx[xhasU] += zU
             gls = -yd.copy()
             gls[hasL] -= vL
             gls[hasU] += vU
             dms = d - s
             dual_inf = max(np.abs(glx).max(), np.abs(gls).max())
             primal_inf = max(np.abs(c).max() if mc else 0.0, np.abs(dms).max())
-            compl = max((sL * vL).max() if len(sL) else 0.0, (sU * vU).max() if len(sU) else 0.0)
+            compl = max((sL * vL).max() if len(sL) else 0.0, (sU * vU).max() if len(sU) else 0.0,
+                        (xsL * zL).max() if len(xsL) else 0.0, (xsU * zU).max() if len(xsU) else 0.0)
             sum_y = np.abs(yc).sum() + np.abs(yd).sum()
-            sum_z = vL.sum() + vU.sum()
+            sum_z = vL.sum() + vU.sum() + zL.sum() + zU.sum()
             s_d = max(o.s_max, (sum_y + sum_z) / (mc + md + self.n_bounds)) / o.s_max
             s_c = max(o.s_max, sum_z / max(self.n_bounds, 1)) / o.s_max
             nlp_error = max(dual_inf / s_d, primal_inf, compl / s_c)
@@ -296,12 +325,15 @@ class IpoptEmulator:
                 status = -1
                 break
 
-            avrg_compl = (float(sL @ vL) + float(sU @ vU)) / self.n_bounds
+            avrg_compl = (float(sL @ vL) + float(sU @ vU) + float(xsL @ zL) + float(xsU @ zU)) / self.n_bounds
             Sig = np.zeros(md)
             Sig[hasL] += vL / sL
             Sig[hasU] += vU / sU
+            Sig_x = np.zeros(n)
+            Sig_x[xhasL] += zL / xsL
+            Sig_x[xhasU] += zU / xsU
             delta_c = o.delta_cd_val * mu ** o.delta_cd_exp
-            fac = self.factor(W, Sig, Jc, Jd, delta_c)
+            fac = self.factor(W + np.diag(Sig_x), Sig, Jc, Jd, delta_c)
 
             # ---- barrier parameter (AdaptiveMuUpdate::UpdateBarrierParameter)
             if mu_max < 0:
@@ -319,7 +351,8 @@ class IpoptEmulator:
                 amu_filter.append((fval - m_, theta - m_))
 
             def barrier_error():
-                cm = max(np.abs(sL * vL - mu).max() if len(sL) else 0.0, np.abs(sU * vU - mu).max() if len(sU) else 0.0)
+                cm = max(np.abs(sL * vL - mu).max() if len(sL) else 0.0, np.abs(sU * vU - mu).max() if len(sU) else 0.0,
+                         np.abs(xsL * zL - mu).max() if len(xsL) else 0.0, np.abs(xsU * zU - mu).max() if len(xsU) else 0.0)
                 return max(dual_inf / s_d, primal_inf, cm / s_c)
 
             if not free_mode:
@@ -343,14 +376,16 @@ class IpoptEmulator:
                     ls_filter = []
 
             rvL0, rvU0 = sL * vL, sU * vU                  # curr_compl_s_L/U
+            rzL0, rzU0 = xsL * zL, xsU * zU                # curr_compl_x_L/U
             zero_n, zero_d = np.zeros(n), np.zeros(md)
             if free_mode:
                 tau = max(o.tau_min, 1.0 - nlp_error)
                 # QualityFunctionMuOracle::CalculateMu
-                aff = self.kkt_solve(fac, Sig, Jd, glx, gls, c, dms, rvL0, rvU0, sL, sU, vL, vU)
+                aff = self.kkt_solve(fac, Sig, Jd, glx, gls, c, dms, rvL0, rvU0, sL, sU, vL, vU, (rzL0, rzU0, xsL, xsU, zL, zU))
                 aff = [-a for a in aff]
                 cen = self.kkt_solve(fac, Sig, Jd, zero_n, zero_d, np.zeros(mc), zero_d,
-                                     np.full(len(sL), avrg_compl), np.full(len(sU), avrg_compl), sL, sU, vL, vU)
+                                     np.full(len(sL), avrg_compl), np.full(len(sU), avrg_compl), sL, sU, vL, vU,
+                                     (np.full(len(xsL), avrg_compl), np.full(len(xsU), avrg_compl), xsL, xsU, zL, zU))
                 n_dual, n_pri, n_comp = n + md, mc + md, self.n_bounds
                 gl2 = float(glx @ glx + gls @ gls)
                 pr2 = float(c @ c + dms @ dms)
@@ -359,12 +394,19 @@ class IpoptEmulator:
                     ds_ = aff[1] + sig * cen[1]
                     dsl, dsu = ds_[hasL], -ds_[hasU]
                     dvl, dvu = aff[4] + sig * cen[4], aff[5] + sig * cen[5]
-                    a_p = min(_frac_to_bound(sL, dsl, tau), _frac_to_bound(sU, dsu, tau))
-                    a_d = min(_frac_to_bound(vL, dvl, tau), _frac_to_bound(vU, dvu, tau))
+                    dx_ = aff[0] + sig * cen[0]
+                    dxl, dxu = dx_[xhasL], -dx_[xhasU]
+                    dzl, dzu = aff[6] + sig * cen[6], aff[7] + sig * cen[7]
+                    a_p = min(_frac_to_bound(sL, dsl, tau), _frac_to_bound(sU, dsu, tau),
+                              _frac_to_bound(xsL, dxl, tau), _frac_to_bound(xsU, dxu, tau))
+                    a_d = min(_frac_to_bound(vL, dvl, tau), _frac_to_bound(vU, dvu, tau),
+                              _frac_to_bound(zL, dzl, tau), _frac_to_bound(zU, dzu, tau))
                     cl = (sL + a_p * dsl) * (vL + a_d * dvl)
                     cu = (sU + a_p * dsu) * (vU + a_d * dvu)
+                    xl_ = (xsL + a_p * dxl) * (zL + a_d * dzl)
+                    xu_ = (xsU + a_p * dxu) * (zU + a_d * dzu)
                     return ((1 - a_d) ** 2 * gl2 / n_dual + (1 - a_p) ** 2 * pr2 / n_pri
-                            + (float(cl @ cl) + float(cu @ cu)) / n_comp)
+                            + (float(cl @ cl) + float(cu @ cu) + float(xl_ @ xl_) + float(xu_ @ xu_)) / n_comp)
 
                 def golden(s_up_in, q_up, s_lo_in, q_lo):
                     s_up, s_lo = s_up_in, s_lo_in            # ScaleSigma is the identity (linear search)
@@ -426,20 +468,25 @@ class IpoptEmulator:
                 res.trace[-1]["avrg_compl"] = avrg_compl
 
             # ---- search direction (PDSearchDirCalc)
-            step = self.kkt_solve(fac, Sig, Jd, glx, gls, c, dms, rvL0 - mu, rvU0 - mu, sL, sU, vL, vU)
-            dx, ds, dyc, dyd, dvL, dvU = [-a for a in step]
+            step = self.kkt_solve(fac, Sig, Jd, glx, gls, c, dms, rvL0 - mu, rvU0 - mu, sL, sU, vL, vU,
+                                  (rzL0 - mu, rzU0 - mu, xsL, xsU, zL, zU))
+            dx, ds, dyc, dyd, dvL, dvU, dzL, dzU = [-a for a in step]
             dnorm = max(np.abs(dx).max(), np.abs(ds).max())
 
             # ---- filter line search (BacktrackingLineSearch + FilterLSAcceptor)
-            alpha_max = min(_frac_to_bound(sL, ds[hasL], tau), _frac_to_bound(sU, -ds[hasU], tau))
-            alpha_du = min(_frac_to_bound(vL, dvL, tau), _frac_to_bound(vU, dvU, tau))
+            alpha_max = min(_frac_to_bound(sL, ds[hasL], tau), _frac_to_bound(sU, -ds[hasU], tau),
+                            _frac_to_bound(xsL, dx[xhasL], tau), _frac_to_bound(xsU, -dx[xhasU], tau))
+            alpha_du = min(_frac_to_bound(vL, dvL, tau), _frac_to_bound(vU, dvU, tau),
+                           _frac_to_bound(zL, dzL, tau), _frac_to_bound(zU, dzU, tau))
 
-            def barrier(s_):
+            def barrier(s_, x_):
                 a, b = slacks(s_)
-                return -mu * (np.log(a).sum() + np.log(b).sum())
+                xa, xb_ = xslacks(x_)
+                return -mu * (np.log(a).sum() + np.log(b).sum() + np.log(xa).sum() + np.log(xb_).sum())
 
-            phi0 = barrier(s) + fval
-            gBD = -mu * (float((ds[hasL] / sL).sum()) - float((ds[hasU] / sU).sum())) + float(gf @ dx)
+            phi0 = barrier(s, x) + fval
+            gBD = (-mu * (float((ds[hasL] / sL).sum()) - float((ds[hasU] / sU).sum()))
+                   - mu * (float((dx[xhasL] / xsL).sum()) - float((dx[xhasU] / xsU).sum())) + float(gf @ dx))
             if theta_max < 0:
                 theta_max = o.theta_max_fact * max(1.0, theta)
                 theta_min = o.theta_min_fact * max(1.0, theta)
@@ -466,7 +513,7 @@ class IpoptEmulator:
                 xt, st = x + alpha * dx, s + alpha * ds
                 ct, dt_, gt = self.cd(xt)
                 th_t = np.abs(ct).sum() + np.abs(dt_ - st).sum()
-                ph_t = barrier(st) + self.f(xt)
+                ph_t = barrier(st, xt) + self.f(xt)
                 ok = False
                 if th_t <= theta_max and np.isfinite(ph_t):
                     switching = gBD < 0 and alpha * (-gBD) ** o.s_phi > o.delta * theta ** o.s_theta
@@ -505,11 +552,16 @@ class IpoptEmulator:
             yd = yd + alpha * dyd
             vL = vL + alpha_du * dvL
             vU = vU + alpha_du * dvU
+            zL = zL + alpha_du * dzL
+            zU = zU + alpha_du * dzU
             sL, sU = slacks(s)
+            xsL, xsU = xslacks(x)
             # IpoptAlgorithm::correct_bound_multiplier: free mode uses the trial average complementarity
-            mu_c = min((float(sL @ vL) + float(sU @ vU)) / self.n_bounds, 1e3) if free_mode else mu
+            mu_c = min((float(sL @ vL) + float(sU @ vU) + float(xsL @ zL) + float(xsU @ zU)) / self.n_bounds, 1e3) if free_mode else mu
             vL = np.minimum(np.maximum(vL, mu_c / (o.kappa_sigma * sL)), o.kappa_sigma * mu_c / sL)
             vU = np.minimum(np.maximum(vU, mu_c / (o.kappa_sigma * sU)), o.kappa_sigma * mu_c / sU)
+            zL = np.minimum(np.maximum(zL, mu_c / (o.kappa_sigma * xsL)), o.kappa_sigma * mu_c / xsL)
+            zU = np.minimum(np.maximum(zU, mu_c / (o.kappa_sigma * xsU)), o.kappa_sigma * mu_c / xsU)
             Jc, Jd = self.jac(x)
             fval, gf = self.f(x, with_grad=True)
             it += 1

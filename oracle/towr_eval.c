@@ -34,10 +34,36 @@ static void spline_set(orc_spline *s, const double *x)
 		if (s->opt[i] >= 0) s->val[i] = x[s->offset + s->opt[i]];
 }
 
+/* polynomials of a phase share its duration equally, ref: src/nodes_variables_phase_based.cc:74-84 */
+static int polys_in_phase(const orc_spline *s, int phase)
+{
+	int n = 0;
+	for (int i = 0; i < s->n_polys; ++i) n += s->poly_phase[i] == phase;
+	return n;
+}
+
+/* ref: src/phase_durations.cc:57-66 (SetVariables: the last phase fills up the total time) and
+ * src/phase_spline.cc:55-65 (UpdatePolynomialDurations of every observing spline) */
+static void schedule_set(orc_problem *p, const double *x)
+{
+	for (int ee = 0; ee < ORC_NEE; ++ee) {
+		if (p->sched_off[ee] < 0) continue;
+		const int np = p->n_phases[ee];
+		double sum = 0.0;
+		for (int k = 0; k < np - 1; ++k) { p->phase_dur[ee][k] = x[p->sched_off[ee] + k]; sum += x[p->sched_off[ee] + k]; }
+		p->phase_dur[ee][np - 1] = p->T - sum;
+		for (int w = 0; w < 2; ++w) {
+			orc_spline *s = w ? &p->ee_force[ee] : &p->ee_motion[ee];
+			for (int i = 0; i < s->n_polys; ++i) s->dur[i] = p->phase_dur[ee][s->poly_phase[i]] / polys_in_phase(s, s->poly_phase[i]);
+		}
+	}
+}
+
 void orc_set_x(orc_problem *p, const double *x)
 {
 	spline_set(&p->base_lin, x); spline_set(&p->base_ang, x);
 	for (int ee = 0; ee < ORC_NEE; ++ee) { spline_set(&p->ee_motion[ee], x); spline_set(&p->ee_force[ee], x); }
+	schedule_set(p, x);
 }
 
 /* ------------------------------------------------------------ spline eval */
@@ -119,6 +145,43 @@ static void base_jac_local(const orc_spline *s, int id, double tl, int dx, int d
 	for (int side = 0; side < 2; ++side)
 		for (int nd = 0; nd < 2; ++nd)
 			out[side * 6 + nd * 3 + dim] = dnode(s->dur[id], tl, dx, side, nd);
+}
+
+/* ref: src/polynomial.cc:236-257 (CubicHermitePolynomial::GetDerivativeOfPosWrtDuration) */
+static double dpos_dT(const orc_spline *s, int id, double t, int k)
+{
+	const double x0 = VAL(s, id, 0, k), v0 = VAL(s, id, 1, k), x1 = VAL(s, id + 1, 0, k), v1 = VAL(s, id + 1, 1, k);
+	const double t2 = pow(t, 2), t3 = pow(t, 3), T = s->dur[id], T2 = pow(T, 2), T3 = pow(T, 3), T4 = pow(T, 4);
+	return (t3 * (v0 + v1)) / T3 - (t2 * (2 * v0 + v1)) / T2 - (3 * t3 * (2 * x0 - 2 * x1 + T * v0 + T * v1)) / T4
+	       + (2 * t2 * (3 * x0 - 3 * x1 + 2 * T * v0 + T * v1)) / T3;
+}
+
+/* Jacobian of a foot spline's position at global time t with respect to the foot's phase durations: out[dim][col],
+ * col < n_phases - 1.  ref: src/phase_spline.cc:67-93 (GetJacobianOfPosWrtDurations, GetDerivativeOfPosWrtPhaseDuration)
+ * and src/phase_durations.cc:126-154 (GetJacobianOfPos): the current phase's duration stretches its polynomials, every
+ * earlier duration shifts the spline along the time axis, and in the LAST phase (whose duration is what the others leave)
+ * the earlier ones also compress it. */
+static void dur_jac(const orc_problem *p, int ee, const orc_spline *s, double t, double out[3][ORC_MAX_PHASES])
+{
+	const int np = p->n_phases[ee];
+	int id; double tl;
+	locate(s, t, &id, &tl);
+	double vel[3];
+	poly_point(s, id, tl, NULL, vel, NULL);
+	/* current phase by the PHASE durations (Spline::GetSegmentID on them, ref: src/spline.cc:48-63) */
+	int phase = np - 1; { double acc = 0.0; for (int i = 0; i < np; ++i) { acc += p->phase_dur[ee][i]; if (acc >= t - 1e-10) { phase = i; break; } } }
+	const double inner = 1.0 / polys_in_phase(s, s->poly_phase[id]);
+	int prev = 0; for (int i = 0; i < id; ++i) prev += s->poly_phase[i] == s->poly_phase[id];
+	const int in_last = phase == np - 1;
+	for (int k = 0; k < 3; ++k) {
+		const double dx_dT = inner * (dpos_dT(s, id, tl, k) - prev * vel[k]);
+		for (int c = 0; c < np - 1; ++c) {
+			double j = 0.0;
+			if (!in_last && c == phase) j = dx_dT;
+			if (c < phase) { j = -1 * vel[k]; if (in_last) j -= dx_dT; }
+			out[k][c] = j;
+		}
+	}
 }
 
 /* ------------------------------------------------------------ Euler ZYX */
@@ -424,6 +487,13 @@ void orc_eval_g(orc_problem *p, const double *x, double *g)
 			for (int d = 0; d < 3; ++d) g[row0 + 3 * j + d] = a0[d] - a1[d];
 		}
 	}
+	/* total duration (optional), ref: src/total_duration_constraint.cc:48-54: the sum EXCLUDES the last phase */
+	for (int ee = 0; ee < ORC_NEE; ++ee) {
+		if (p->row_total[ee] < 0) continue;
+		double sum = 0.0;
+		for (int k = 0; k < p->n_phases[ee] - 1; ++k) sum += x[p->sched_off[ee] + k];
+		g[p->row_total[ee]] = sum;
+	}
 	/* base motion (optional), ref: src/base_motion_constraint.cc:60-66: rows AX AY AZ = Euler angles, LX LY LZ = position */
 	for (int k = 0; k < p->n_brom; ++k) {
 		double b[3], e[3];
@@ -585,6 +655,21 @@ void orc_eval_jac(orc_problem *p, const double *x, double *J, unsigned char *mas
 			for (int dim = 0; dim < 3; ++dim) spline_jac_row(&p->ee_motion[ee], id, tl, kPos, dim, &je[dim]);
 			crossmat(d.f[ee], C);
 			add_cross_times_jac(&o, rowA, C, je, 1.0);      /* -(Cross(f)*(-jac_ee_pos)) */
+			/* contact schedule, ref: src/dynamic_constraint.cc:108-114: both of the above with the durations' Jacobians */
+			if (p->sched_off[ee] >= 0) {
+				double jfT[3][ORC_MAX_PHASES], jxT[3][ORC_MAX_PHASES], Cr[3][3];
+				dur_jac(p, ee, &p->ee_force[ee], t, jfT); dur_jac(p, ee, &p->ee_motion[ee], t, jxT);
+				crossmat(r, Cr);
+				for (int c = 0; c < p->n_phases[ee] - 1; ++c) {
+					const int col = p->sched_off[ee] + c;
+					for (int i = 0; i < 3; ++i) {
+						double a = 0.0;
+						for (int q = 0; q < 3; ++q) a += Cr[i][q] * jfT[q][c] + C[i][q] * jxT[q][c];
+						jadd(&o, rowA + i, col, a);
+						jadd(&o, rowL + i, col, -jfT[i][c]);
+					}
+				}
+			}
 		}
 	}
 	/* spline acc, ref: src/spline_acc_constraint.cc:65-80 */
@@ -632,6 +717,13 @@ void orc_eval_jac(orc_problem *p, const double *x, double *J, unsigned char *mas
 					for (int q = 0; q < jb[c].n; ++q) jadd(&o, row0 + r, jb[c].col[q], -1 * a.R[c][r] * jb[c].v[q]);
 					for (int q = 0; q < je[c].n; ++q) jadd(&o, row0 + r, je[c].col[q], a.R[c][r] * je[c].v[q]);
 				}
+			if (p->sched_off[ee] >= 0) {                         /* ref: src/range_of_motion_constraint.cc:107-109 */
+				double jxT[3][ORC_MAX_PHASES];
+				dur_jac(p, ee, &p->ee_motion[ee], t, jxT);
+				for (int c = 0; c < p->n_phases[ee] - 1; ++c)
+					for (int r = 0; r < 3; ++r)
+						jadd(&o, row0 + r, p->sched_off[ee] + c, a.R[0][r] * jxT[0][c] + a.R[1][r] * jxT[1][c] + a.R[2][r] * jxT[2][c]);
+			}
 			double rW[3] = {pe[0] - b[0], pe[1] - b[1], pe[2] - b[2]}, dr[3][12];
 			drotvec_du(&a, rW, 1, dr);
 			for (int r = 0; r < 3; ++r)
@@ -685,5 +777,8 @@ void orc_eval_jac(orc_problem *p, const double *x, double *J, unsigned char *mas
 				row++;
 			}
 		}
-	}
+	}	/* total duration (optional), ref: src/total_duration_constraint.cc:64-70 */
+	for (int ee = 0; ee < ORC_NEE; ++ee)
+		if (p->row_total[ee] >= 0)
+			for (int c = 0; c < p->n_phases[ee] - 1; ++c) jset(&o, p->row_total[ee], p->sched_off[ee] + c, 1.0);
 }

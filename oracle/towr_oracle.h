@@ -69,6 +69,12 @@ typedef struct {
 	 * src/node_cost.cc:53-83): weight of ForcesCostID (force z of every force node, squared) and of EEMotionCostID (foot velocity
 	 * x and y of every motion node, squared); 0 = the term is absent */
 	double cost_force_z, cost_ee_vel_xy;
+	/* optional gait-timing optimisation (Parameters::OptimizePhaseDurations, off on the reference's path; ref: src/parameters.cc:52,77-80,
+	 * src/phase_durations.cc, src/phase_spline.cc:67-93, src/total_duration_constraint.cc): every foot's phase durations but the last
+	 * become variables (sets appended after the force sets, bounds [phase_dur_min, phase_dur_max]), the foot splines follow them, the
+	 * dynamic and range-of-motion rows gain columns for them and one TotalDuration row per foot is appended.  ORACLE ONLY. */
+	int    optimize_timings;
+	double phase_dur_min, phase_dur_max;     /* bound_phase_duration_ = (0.2, 1.0) */
 } orc_shape;
 
 typedef struct {
@@ -107,6 +113,8 @@ typedef struct orc_problem {
 	double *t_dyn, *t_rom;
 	int row_base_rom, n_brom; /* BaseMotionConstraint rows (6 per sample: AX AY AZ LX LY LZ), -1 / 0 when off */
 	double *t_brom;
+	int sched_off[ORC_NEE];   /* variable offset of foot ee's phase durations (n_phases - 1 of them), -1 when timings are fixed */
+	int row_total[ORC_NEE];   /* TotalDuration row of foot ee, -1 when off */
 } orc_problem;
 
 /* ---- problem construction (towr_problem.c) ---- */
@@ -120,6 +128,7 @@ void orc_get_x0(const orc_problem *p, double *x0);
 void orc_get_bounds(const orc_problem *p, double *xl, double *xu, double *gl, double *gu);
 int  orc_get_phase_durations(const orc_problem *p, int ee, double *out);
 void orc_get_layout(const orc_problem *p, int *var_offsets /*10+1*/, int *row_offsets /*19+1*/);
+void orc_get_schedule_layout(const orc_problem *p, int *sched_off /*4*/, int *row_total /*4*/);
 
 /* ---- terrain (towr_terrain.c) ---- */
 double orc_height(const orc_heightfield *hf, double x, double y);

@@ -261,6 +261,7 @@ void orc_default_shape(orc_shape *s)
 	s->dt_rom = 0.08;
 	s->base_rom = 0; s->dt_base_rom = 0.1 / 4.0; s->terrain_gradients = 0;
 	s->cost_force_z = 0.0; s->cost_ee_vel_xy = 0.0;
+	s->optimize_timings = 0; s->phase_dur_min = 0.2; s->phase_dur_max = 1.0;     /* ref: src/parameters.cc:52 */
 	s->combo = ORC_CUSTOM;
 	s->duration = 5.0;
 }
@@ -312,6 +313,11 @@ orc_problem *orc_problem_create(const orc_shape *shape, const orc_instance *inst
 	p->base_ang.offset = off; off += p->base_ang.n_vars;
 	for (int ee = 0; ee < ORC_NEE; ++ee) { p->ee_motion[ee].offset = off; off += p->ee_motion[ee].n_vars; }
 	for (int ee = 0; ee < ORC_NEE; ++ee) { p->ee_force[ee].offset = off; off += p->ee_force[ee].n_vars; }
+	/* contact schedule sets come last, ref: src/nlp_formulation.cc:80-83; all phases but the last, ref: src/phase_durations.cc:44-46 */
+	for (int ee = 0; ee < ORC_NEE; ++ee) {
+		p->sched_off[ee] = -1; p->row_total[ee] = -1;
+		if (shape->optimize_timings) { p->sched_off[ee] = off; off += p->n_phases[ee] - 1; }
+	}
 	p->n = off;
 
 	p->x0 = (double *)calloc(p->n, sizeof(double));
@@ -358,6 +364,12 @@ orc_problem *orc_problem_create(const orc_shape *shape, const orc_instance *inst
 	spline_get_values(&p->base_ang, p->x0);
 	for (int ee = 0; ee < ORC_NEE; ++ee) spline_get_values(&p->ee_motion[ee], p->x0);
 	for (int ee = 0; ee < ORC_NEE; ++ee) spline_get_values(&p->ee_force[ee], p->x0);
+	if (shape->optimize_timings)                             /* ref: src/phase_durations.cc:68-76,100-109 */
+		for (int ee = 0; ee < ORC_NEE; ++ee)
+			for (int k = 0; k < p->n_phases[ee] - 1; ++k) {
+				p->x0[p->sched_off[ee] + k] = p->phase_dur[ee][k];
+				p->xl[p->sched_off[ee] + k] = shape->phase_dur_min; p->xu[p->sched_off[ee] + k] = shape->phase_dur_max;
+			}
 
 	/* ---- constraint layout, ref: src/parameters.cc:55-60 order ---- */
 	p->t_dyn = make_times(p->T, shape->dt_dynamic, &p->n_dyn);
@@ -383,6 +395,8 @@ orc_problem *orc_problem_create(const orc_shape *shape, const orc_instance *inst
 		p->t_brom = make_times(p->T, shape->dt_base_rom, &p->n_brom);
 		p->row_base_rom = row; row += 6 * p->n_brom;
 	}
+	if (shape->optimize_timings)                             /* constraints_.push_back(TotalTime), ref: src/parameters.cc:77-80 */
+		for (int ee = 0; ee < ORC_NEE; ++ee) p->row_total[ee] = row++;
 	p->m = row;
 	p->gl = (double *)calloc(p->m, sizeof(double));
 	p->gu = (double *)calloc(p->m, sizeof(double));
@@ -410,6 +424,9 @@ orc_problem *orc_problem_create(const orc_shape *shape, const orc_instance *inst
 			p->gl[r] = 0.0;       p->gu[r] = ORC_INF; r++;
 		}
 	}
+	/* ref: src/total_duration_constraint.cc:56-62 (the hard-coded 0.1 and min_duration_last_phase = 0.2) */
+	if (shape->optimize_timings)
+		for (int ee = 0; ee < ORC_NEE; ++ee) { p->gl[p->row_total[ee]] = 0.1; p->gu[p->row_total[ee]] = p->T - 0.2; }
 	/* BaseMotionConstraint bounds, ref: src/base_motion_constraint.cc:47-57: roll, pitch within +-0.01 rad, yaw and x, y free,
 	 * z within [z_init - 0.02, z_init + 0.1], z_init = the base spline's initial height */
 	for (int k = 0; k < p->n_brom; ++k) {
@@ -443,11 +460,15 @@ int orc_get_phase_durations(const orc_problem *p, int ee, double *out)
 	memcpy(out, p->phase_dur[ee], sizeof(double) * p->n_phases[ee]);
 	return p->n_phases[ee];
 }
+void orc_get_schedule_layout(const orc_problem *p, int *so, int *rt)
+{
+	for (int ee = 0; ee < 4; ++ee) { so[ee] = p->sched_off[ee]; rt[ee] = p->row_total[ee]; }
+}
 void orc_get_layout(const orc_problem *p, int *vo, int *ro)
 {
 	vo[0] = p->base_lin.offset; vo[1] = p->base_ang.offset;
 	for (int ee = 0; ee < 4; ++ee) { vo[2 + ee] = p->ee_motion[ee].offset; vo[6 + ee] = p->ee_force[ee].offset; }
-	vo[10] = p->n;
+	vo[10] = p->ee_force[3].offset + p->ee_force[3].n_vars;      /* schedule sets (if any) follow: orc_get_schedule_layout */
 	for (int ee = 0; ee < 4; ++ee) ro[ee] = p->row_terrain[ee];
 	ro[4] = p->row_dynamic; ro[5] = p->row_acc_lin; ro[6] = p->row_acc_ang;
 	for (int ee = 0; ee < 4; ++ee) { ro[7 + ee] = p->row_rom[ee]; ro[11 + ee] = p->row_force[ee]; ro[15 + ee] = p->row_swing[ee]; }
