@@ -198,6 +198,10 @@ typedef struct {
 } qtos_stream_info;
 int  qtos_stream_begin(qtos_ctx *ctx, const qtos_options *o);
 int  qtos_stream_submit(qtos_ctx *ctx, const qtos_problem *p, int n, qtos_result *res, double *x_out, int *ticket);
+/* like qtos_stream_submit, and the job also delivers the reference's actual output -- the 1 kHz rows of every plan, rows_out =
+ * [n][csv_rows][37] doubles on the host (ref: main.cpp:92-131, what getTrajectory writes to traj.csv) -- sampled on the device and
+ * copied on the session's copy stream while the pool keeps iterating; page-locked rows_out lets the copies run at PCIe speed */
+int  qtos_stream_submit_csv(qtos_ctx *ctx, const qtos_problem *p, int n, qtos_result *res, double *x_out, double *rows_out, int *ticket);
 int  qtos_stream_submit_device(qtos_ctx *ctx, const qtos_problem *d_p, int n, qtos_result *d_res, double *d_x_out, int *ticket);
 int  qtos_stream_wait(qtos_ctx *ctx, int ticket);
 int  qtos_stream_stats(const qtos_ctx *ctx, qtos_stream_info *out);

@@ -112,7 +112,7 @@ assert PROBLEM_DTYPE.itemsize == 8 * 28 + 8 and RESULT_DTYPE.itemsize == 56
 EXPORTS = ["qtos_default_shape", "qtos_default_options", "qtos_create", "qtos_destroy", "qtos_last_error",
            "qtos_get_dims", "qtos_upload_heightfield", "qtos_free_heightfield", "qtos_heightfield_query", "qtos_heightfield_cells",
            "qtos_get_initial", "qtos_eval", "qtos_solve_batch", "qtos_solve_batch_device", "qtos_solve_batch_async",
-           "qtos_solve_batch_device_async", "qtos_wait", "qtos_stream_begin", "qtos_stream_submit", "qtos_stream_submit_device",
+           "qtos_solve_batch_device_async", "qtos_wait", "qtos_stream_begin", "qtos_stream_submit", "qtos_stream_submit_csv", "qtos_stream_submit_device",
            "qtos_stream_wait", "qtos_stream_stats", "qtos_stream_end", "qtos_make_records", "qtos_select_best", "qtos_get_trace", "qtos_sample_csv", "qtos_sample_csv_rows",
            "qtos_write_csv", "qtos_launch_count", "qtos_set_profiling", "qtos_last_stats", "qtos_stream",
            "qtos_measure_fp64_peak", "qtos_measure_heightfield_staging"]
@@ -147,6 +147,7 @@ def lib():
         L.qtos_wait.argtypes = [vp]
         L.qtos_stream_begin.argtypes = [vp, C.POINTER(Options)]
         L.qtos_stream_submit.argtypes = [vp, vp, C.c_int, vp, dp, C.POINTER(C.c_int)]
+        L.qtos_stream_submit_csv.argtypes = [vp, vp, C.c_int, vp, dp, dp, C.POINTER(C.c_int)]
         L.qtos_stream_submit_device.argtypes = [vp, vp, C.c_int, vp, vp, C.POINTER(C.c_int)]
         L.qtos_stream_wait.argtypes = [vp, C.c_int]
         L.qtos_stream_stats.argtypes = [vp, C.POINTER(StreamInfo)]
@@ -340,9 +341,10 @@ class Solver:
         self._stream_keep = {}
         self._ck(self._L.qtos_stream_begin(self._h, C.byref(o)))
 
-    def stream_submit(self, problems, out=None):
+    def stream_submit(self, problems, out=None, csv_out=None):
         """queue a job of <= max_batch windows (host buffers); returns a ticket for stream_wait.  `out` = (results, x) as
-        in solve(); fresh arrays otherwise."""
+        in solve(); fresh arrays otherwise.  `csv_out` = float64[n, csv_rows, 37] (C-contiguous, ideally page-locked): the job also
+        delivers the 1 kHz rows of every plan -- what the reference writes to traj.csv -- copied while the pool keeps iterating."""
         p, pp = self._probs(problems)
         n = len(p)
         res, x = out if out is not None else (np.zeros(n, dtype=RESULT_DTYPE), np.zeros((n, self.n_vars)))
@@ -350,21 +352,26 @@ class Solver:
                 or not res.flags.c_contiguous or not x.flags.c_contiguous:
             raise ValueError("out must be (RESULT_DTYPE[n], float64[n, n_vars]), C-contiguous")
         t = C.c_int(-1)
-        self._ck(self._L.qtos_stream_submit(self._h, pp, n, res.ctypes.data_as(C.c_void_p), _dp(x), C.byref(t)))
-        self._stream_keep[t.value] = (p, res, x)
+        if csv_out is not None:
+            if csv_out.dtype != np.float64 or csv_out.shape != (n, self.csv_rows, CSV_COLS) or not csv_out.flags.c_contiguous:
+                raise ValueError("csv_out must be float64[n, csv_rows, %d], C-contiguous" % CSV_COLS)
+            self._ck(self._L.qtos_stream_submit_csv(self._h, pp, n, res.ctypes.data_as(C.c_void_p), _dp(x), _dp(csv_out), C.byref(t)))
+        else:
+            self._ck(self._L.qtos_stream_submit(self._h, pp, n, res.ctypes.data_as(C.c_void_p), _dp(x), C.byref(t)))
+        self._stream_keep[t.value] = (p, res, x, csv_out)
         return t.value
 
     def stream_submit_device(self, d_problems_ptr, n, d_results_ptr, d_x_ptr):
         t = C.c_int(-1)
         self._ck(self._L.qtos_stream_submit_device(self._h, C.c_void_p(d_problems_ptr), int(n), C.c_void_p(d_results_ptr),
                                                    C.c_void_p(d_x_ptr), C.byref(t)))
-        self._stream_keep[t.value] = (None, None, None)
+        self._stream_keep[t.value] = (None, None, None, None)
         return t.value
 
     def stream_wait(self, ticket):
         """block until every window of the job has ended; returns its (results, x) (None, None for device jobs)"""
         self._ck(self._L.qtos_stream_wait(self._h, int(ticket)))
-        _, res, x = self._stream_keep.pop(ticket, (None, None, None))
+        _, res, x, _rows = self._stream_keep.pop(ticket, (None, None, None, None))
         return res, x
 
     def stream_info(self):

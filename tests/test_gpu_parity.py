@@ -508,10 +508,36 @@ def test_continuous_batching_returns_the_batch_call_results():
     t2 = S.stream_submit(p[:8])                                     # the session outlives an idle period
     r, x = S.stream_wait(t2)
     assert np.array_equal(x, x0[:8])
+    # a job can also deliver the reference's actual output, the 1 kHz rows of every plan (qtos_stream_submit_csv): identical to the
+    # rows the sampler entry point returns for the same plans; pinned or pageable destination
+    rows_ref = S.sample_csv(p[:40], x0[:40])
+    h_rows = torch.empty((40, S.csv_rows, Q.CSV_COLS), dtype=torch.float64).pin_memory()
+    t3 = S.stream_submit(p[:40], csv_out=h_rows.numpy())
+    pageable = np.zeros((12, S.csv_rows, Q.CSV_COLS))
+    t4 = S.stream_submit(p[40:52], csv_out=pageable)
+    r, x = S.stream_wait(t3); S.stream_wait(t4)
+    assert np.array_equal(x, x0[:40])
+    S.stream_end()
+    _r, _x, rows_sync = S.solve(p[:52], csv=True)
+    assert np.array_equal(h_rows.numpy(), rows_sync[:40]) and np.array_equal(pageable, rows_sync[40:52])
+    assert np.array_equal(rows_ref, rows_sync[:40])
+    with pytest.raises(ValueError):
+        S.stream_begin(); S.stream_submit(p[:4], csv_out=np.zeros((4, 7, Q.CSV_COLS)))
     S.stream_end()
     r1, x1, _ = S.solve(p[:16])                                     # and the context is a batch solver again
     assert np.array_equal(x1, x0[:16])
     S.close()
+    # a job larger than one copy chunk (256 windows): the rows of the windows either side of the chunk boundary
+    Sb = Q.Solver(Q.default_shape(*SHAPES["S2"]), max_batch=300)
+    hid = Sb.upload_heightfield(grid, res)
+    pb = workloads.multistart_problems(300, grid, res, hf_id=hid)
+    big = np.zeros((300, Sb.csv_rows, Q.CSV_COLS))
+    Sb.stream_begin()
+    rb, xb = Sb.stream_wait(Sb.stream_submit(pb, csv_out=big))
+    Sb.stream_end()
+    pick = [0, 255, 256, 299]
+    assert np.array_equal(big[pick], Sb.sample_csv(pb[pick], xb[pick])) and np.isfinite(big).all()
+    Sb.close()
 
 
 def test_second_attempt_rescues_failed_line_searches(solvers, oracle):
