@@ -466,7 +466,17 @@ __device__ __forceinline__ void row_dot2(const DevTables &T, const double *Jv, c
 		const Element &E = T.elems[T.row_elem[row]];
 		const double *jr = Jv + E.valoff + (row - E.row0);
 		const int16_t *cols = T.elem_cols + E.coloff;
-		for (int a = threadIdx.x & 7; a < E.ncols; a += 8) { const double jv = jr[a * E.ld]; const int c = cols[a]; a0 += jv * z0[c]; a1 += jv * z1[c]; }
+		/* two columns per lane in flight (the loop is bound by its dependent loads: value, column index, then z); the sums keep
+		 * their order */
+		const int ncols = E.ncols, ld = E.ld;
+		int a = threadIdx.x & 7;
+		for (; a + 8 < ncols; a += 16) {
+			const double jv = jr[a * ld], jw = jr[(a + 8) * ld];
+			const int c = cols[a], d = cols[a + 8];
+			a0 += jv * z0[c]; a1 += jv * z1[c];
+			a0 += jw * z0[d]; a1 += jw * z1[d];
+		}
+		if (a < ncols) { const double jv = jr[a * ld]; const int c = cols[a]; a0 += jv * z0[c]; a1 += jv * z1[c]; }
 	}
 #pragma unroll
 	for (int o = 1; o < 8; o <<= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
@@ -533,12 +543,14 @@ kip_solve(DevTables T, DevWork W, qtos_options opt, int rc)
 			}
 			__syncthreads();
 			if (pass == 0) {
+				/* C = Mid - Q'Q on the slots in use, identity on the others */
+				for (int q = tid; q < q12 * q12; q += KS_T) {
+					const int a = q / q12, b = q - a * q12;
+					const bool used = (a % IP_LM) < n_pairs && (b % IP_LM) < n_pairs;
+					Clu[q] = used ? ip[IP_MID + q] - G[a * 14 + b] : (a == b ? 1.0 : 0.0);
+				}
+				__syncthreads();
 				if (tid == 0) {
-					/* C = Mid - Q'Q on the slots in use, identity on the others */
-					for (int a = 0; a < q12; ++a) for (int b = 0; b < q12; ++b) {
-						const bool used = (a % IP_LM) < n_pairs && (b % IP_LM) < n_pairs;
-						Clu[a * q12 + b] = used ? ip[IP_MID + a * q12 + b] - G[a * 14 + b] : (a == b ? 1.0 : 0.0);
-					}
 					piv[q12] = lu12_factor(Clu, piv);
 					if (!piv[q12]) { ip[IP_NPAIRS] = 0.0; ip[IP_HEAD] = 0.0; ip[IP_SIGMA_W] = 1.0; }     /* singular: drop the pairs */
 				}

@@ -650,8 +650,16 @@ k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld, int max_w)
 					/* L[I,J] = S * inv(L[J,J])' : second DMMA product, B = inv(L[J,J]) in fragment order from global */
 					if (J == I - 1) {                  /* inv(L[I-1,I-1]) and z_{I-1} are needed from here on, not earlier */
 						diag_done_wait();
+#ifdef FACTOR_INV_FROM_GLOBAL
 						const double2 *bi = reinterpret_cast<const double2 *>(Dinv + (size_t)J * 256 + tn * 128) + lane;
 						i01 = bi[0]; i23 = bi[32];
+#else
+						/* the diagonal warp left inv(L[I-1,I-1]) in the hand-off tile as well: this lane's operand fragment (row
+						 * tn * 8 + fr, columns 4 fc .. 4 fc + 3) comes from shared memory instead of through L2 -- the load sits on
+						 * the critical path of every block row (the tile is rewritten only after the next tile_sync) */
+						const double2 *bi = reinterpret_cast<const double2 *>(dS + (tn * 8 + fr) * TLD + 4 * fc);
+						i01 = bi[0]; i23 = bi[1];
+#endif
 					}
 					tile_sync();
 					const double2 *ta = reinterpret_cast<const double2 *>(tmp + (tm * 8 + fr) * TLT + 4 * fc);
