@@ -157,6 +157,10 @@ int  qtos_free_heightfield(qtos_ctx *ctx, int hf_id);
 /* batched CustomTerrain::GetHeight (ref: custom_terrain.cpp:51-94), bit-exact; xy = n pairs */
 int  qtos_heightfield_query(qtos_ctx *ctx, int hf_id, const double *xy, int n, double *h_out);
 int  qtos_heightfield_cells(qtos_ctx *ctx, int hf_id, const double *xy, int n, long long *idx4_out);
+/* dh/dx and dh/dy of the bilinear surface at n points: the derivative CustomTerrain::GetHeightDerivWrtX / WrtY carry commented out
+ * (ref: custom_terrain.cpp:96-156), same cells and operation order as the height, bit-exact against the oracle's restatement.
+ * The solver's terrain rows keep the reference's zero derivatives; this is the query alone */
+int  qtos_heightfield_gradients(qtos_ctx *ctx, int hf_id, const double *xy, int n, double *hx_out, double *hy_out);
 
 /* problem structure for one instance: x0, bounds (host arrays, n_vars / n_cons long, nullable) */
 int  qtos_get_initial(qtos_ctx *ctx, const qtos_problem *p, int n, double *x0, double *xl, double *xu,

@@ -148,6 +148,11 @@ class Terrain:
     def height(self, x, y):
         return lib().orc_height(C.byref(self.c), float(x), float(y))
 
+    def height_deriv(self, x, y):
+        hx, hy = C.c_double(), C.c_double()
+        lib().orc_height_deriv(C.byref(self.c), float(x), float(y), C.byref(hx), C.byref(hy))
+        return hx.value, hy.value
+
     def cell(self, x, y):
         idx = (C.c_longlong * 4)()
         lib().orc_height_cell(C.byref(self.c), float(x), float(y), idx)

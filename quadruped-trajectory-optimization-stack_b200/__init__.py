@@ -110,7 +110,7 @@ RESULT_DTYPE = np.dtype([("status", "i4"), ("iters", "i4"), ("constr_viol", "f8"
 assert PROBLEM_DTYPE.itemsize == 8 * 28 + 8 and RESULT_DTYPE.itemsize == 56
 
 EXPORTS = ["qtos_default_shape", "qtos_default_options", "qtos_create", "qtos_destroy", "qtos_last_error",
-           "qtos_get_dims", "qtos_upload_heightfield", "qtos_free_heightfield", "qtos_heightfield_query", "qtos_heightfield_cells",
+           "qtos_get_dims", "qtos_upload_heightfield", "qtos_free_heightfield", "qtos_heightfield_query", "qtos_heightfield_cells", "qtos_heightfield_gradients",
            "qtos_get_initial", "qtos_eval", "qtos_solve_batch", "qtos_solve_batch_device", "qtos_solve_batch_async",
            "qtos_solve_batch_device_async", "qtos_wait", "qtos_stream_begin", "qtos_stream_submit", "qtos_stream_submit_csv", "qtos_stream_submit_device",
            "qtos_stream_wait", "qtos_stream_stats", "qtos_stream_end", "qtos_make_records", "qtos_select_best", "qtos_get_trace", "qtos_sample_csv", "qtos_sample_csv_rows",
@@ -138,6 +138,7 @@ def lib():
         L.qtos_free_heightfield.argtypes = [vp, C.c_int]
         L.qtos_heightfield_query.argtypes = [vp, C.c_int, dp, C.c_int, dp]
         L.qtos_heightfield_cells.argtypes = [vp, C.c_int, dp, C.c_int, C.POINTER(C.c_longlong)]
+        L.qtos_heightfield_gradients.argtypes = [vp, C.c_int, dp, C.c_int, dp, dp]
         L.qtos_get_initial.argtypes = [vp, vp, C.c_int, dp, dp, dp, dp, dp]
         L.qtos_eval.argtypes = [vp, vp, C.c_int, dp, dp, dp]
         L.qtos_solve_batch.argtypes = [vp, vp, C.c_int, C.POINTER(Options), vp, dp, dp]
@@ -269,6 +270,13 @@ class Solver:
         out = np.zeros((len(xy), 4), dtype=np.int64)
         self._ck(self._L.qtos_heightfield_cells(self._h, int(hf_id), _dp(xy), len(xy), out.ctypes.data_as(C.POINTER(C.c_longlong))))
         return out
+
+    def heightfield_gradients(self, hf_id, xy):
+        """(dh/dx, dh/dy) of the bilinear surface at the points xy[n, 2] (the derivative the reference carries commented out)"""
+        xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+        hx, hy = np.zeros(len(xy)), np.zeros(len(xy))
+        self._ck(self._L.qtos_heightfield_gradients(self._h, int(hf_id), _dp(xy), len(xy), _dp(hx), _dp(hy)))
+        return hx, hy
 
     def initial(self, problems):
         p, pp = self._probs(problems)

@@ -104,6 +104,25 @@ __device__ __forceinline__ void qtos_height_cell(const DevHeightfield &hf, doubl
 	c[3] = c[1] + 1 < hf.ny - 1 ? c[1] + 1 : hf.ny - 1;
 }
 
+/* First derivatives of the bilinear surface: the code CustomTerrain::GetHeightDerivWrtX / WrtY carry commented out (they return 0
+ * on the reference's path), same cell selection as the height and the reference's operation order, no FMA contraction.
+ * ref: solver/towr/src/custom_terrain.cpp:96-156.  Served by qtos_heightfield_gradients; the solver's terrain rows keep the
+ * reference's zero derivatives. */
+__device__ __forceinline__ void qtos_height_grad(const DevHeightfield &hf, double x, double y, double &hx, double &hy)
+{
+	long long c[4];
+	qtos_height_cell(hf, x, y, c);
+	const double res = hf.res;
+	const double x0 = __dadd_rn(__dmul_rn((double)c[0], res), -1.0), x1 = __dadd_rn(__dmul_rn((double)c[2], res), -1.0);
+	const double y0 = __dadd_rn(__dmul_rn((double)c[1], res), -1.0), y1 = __dadd_rn(__dmul_rn((double)c[3], res), -1.0);
+	const double z00 = __ldg(hf.h + c[0] * hf.ny + c[1]), z01 = __ldg(hf.h + c[0] * hf.ny + c[3]);
+	const double z10 = __ldg(hf.h + c[2] * hf.ny + c[1]), z11 = __ldg(hf.h + c[2] * hf.ny + c[3]);
+	const double s = __ddiv_rn(1.0, __dmul_rn(res, res));
+	hx = __dmul_rn(s, __dadd_rn(__dmul_rn(__dadd_rn(-z00, z10), __dsub_rn(y1, y)), __dmul_rn(__dadd_rn(-z01, z11), __dsub_rn(y, y0))));
+	hy = __dmul_rn(s, __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(z00, __dsub_rn(x, x1)), __dmul_rn(z10, __dsub_rn(x0, x))),
+	                                      __dmul_rn(z01, __dsub_rn(x1, x))), __dmul_rn(z11, __dsub_rn(x, x0))));
+}
+
 __device__ __forceinline__ double qtos_height(const DevHeightfield &hf, double x, double y)
 {
 	long long c[4];

@@ -986,6 +986,15 @@ __global__ void k_height(DevHeightfield hf, const double *xy, int n, double *h_o
 	if (idx_out) { long long c[4]; qtos_height_cell(hf, xy[2 * i], xy[2 * i + 1], c); for (int q = 0; q < 4; ++q) idx_out[4 * i + q] = c[q]; }
 }
 
+__global__ void k_height_grad(DevHeightfield hf, const double *xy, int n, double *hx_out, double *hy_out)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double hx, hy;
+	qtos_height_grad(hf, xy[2 * i], xy[2 * i + 1], hx, hy);
+	hx_out[i] = hx; hy_out[i] = hy;
+}
+
 /* ------------------------------------------------------------------ best-plan selection (the one exchange step of the path)
  *
  * A record = 5 doubles (group, not converged, cost, violation, global id).  The winner of a group is the lexicographic minimum of

@@ -106,7 +106,19 @@ def test_heightfield_queries_bit_exact(solvers, oracle, golden_hf):
         assert np.array_equal(h, want)                      # bit-exact, no tolerance
         assert np.array_equal(cells, wantc)
         assert np.array_equal(h, HF.get_height(grid, res, pts[:, 0], pts[:, 1]))
+        # the gradient query (the derivative the reference carries commented out, custom_terrain.cpp:96-156): bit-exact against the
+        # oracle's restatement, and the slope of the height along each axis inside a cell
+        hx, hy = S.heightfield_gradients(hid, pts)
+        wg = np.array([ter.height_deriv(x, y) for x, y in pts])
+        assert np.array_equal(hx, wg[:, 0]) and np.array_equal(hy, wg[:, 1])
+        inner = pts[:2000]
+        d = 1e-7
+        same = np.all(S.height_cells(hid, inner) == S.height_cells(hid, inner + d), axis=1)
+        fdx = (S.height(hid, inner + [d, 0]) - S.height(hid, inner)) / d
+        fdy = (S.height(hid, inner + [0, d]) - S.height(hid, inner)) / d
+        assert np.abs(fdx - hx[:2000])[same].max() < 1e-5 and np.abs(fdy - hy[:2000])[same].max() < 1e-5
     assert len(S.height(hid, np.zeros((0, 2)))) == 0        # empty query
+    assert len(S.heightfield_gradients(hid, np.zeros((0, 2)))[0]) == 0
 
 
 @pytest.mark.parametrize("alg", ["ipopt", "fast"])
