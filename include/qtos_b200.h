@@ -65,6 +65,12 @@ typedef struct {
 	                                     node_cost.cc:53-83).  0 = the term is absent.  With a weight set the objective is minimised by
 	                                     QTOS_ALG_IPOPT exactly as Ipopt would (gradient in the dual infeasibility, the limited-memory pairs,
 	                                     the barrier function of the filter line search); QTOS_ALG_FAST refuses such a shape */
+	int    terrain_gradients;         /* 1: the terrain's first derivatives are what the bilinear surface gives (the code the reference
+	                                     carries commented out, custom_terrain.cpp:96-156) instead of the reference's zeros: the terrain
+	                                     rows' Jacobian gets -dh/dx, -dh/dy (terrain_constraint.cc:90-108) and the force rows are stated
+	                                     in the contact basis of the foothold (height_map.cc:95-141, force_constraint.cc:67-135; second
+	                                     derivatives stay zero like the reference's).  0 (default) = the reference's path.  On plateau
+	                                     terrain this is a regression */
 } qtos_shape;
 
 /* one local-plan window = the flags of ./main (ref: main.cpp:163-306) */

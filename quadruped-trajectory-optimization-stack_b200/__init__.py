@@ -68,7 +68,7 @@ class Shape(C.Structure):
                 ("ee_polys_per_swing", C.c_int), ("dt_dynamic", C.c_double),
                 ("dt_rom", C.c_double), ("combo", C.c_int), ("duration", C.c_double),
                 ("base_rom", C.c_int), ("dt_base_rom", C.c_double),
-                ("cost_force_z", C.c_double), ("cost_ee_vel_xy", C.c_double)]
+                ("cost_force_z", C.c_double), ("cost_ee_vel_xy", C.c_double), ("terrain_gradients", C.c_int)]
 
 
 class Options(C.Structure):

@@ -388,6 +388,16 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 			int vx = nv(2 + ee, nd, 0), vy = nv(2 + ee, nd, 1), vz = nv(2 + ee, nd, 2);
 			H->ter_row.push_back(r);
 			H->ter_var.push_back((int16_t)vx); H->ter_var.push_back((int16_t)vy); H->ter_var.push_back((int16_t)vz);
+			if (sh.terrain_gradients) {
+				/* dg/d(x, y) = -dh/d(x, y) at the node (ref: terrain_constraint.cc:90-108 with the derivatives of custom_terrain.cpp:96-156) */
+				std::vector<int> cols; int slot[3];
+				const int vv[3] = {vx, vy, vz};
+				for (int d = 0; d < 3; ++d) { const int f = vv[d] >= 0 ? free_of[vv[d]] : -1; slot[d] = -1; if (f >= 0) { slot[d] = (int)cols.size(); cols.push_back(f); } }
+				const int e = new_elem(EL_TG, r, 1, cols);
+				const int rec[8] = {r, vx, vy, vz, slot[0], slot[1], slot[2], e};
+				H->tg_ter.insert(H->tg_ter.end(), rec, rec + 8);
+				continue;
+			}
 			LinRow lr; lr.row = r; lin_add(lr, vz, 1.0);
 			const_elem({lr});              /* J only; g comes from the terrain table */
 		}
@@ -498,6 +508,28 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 		for (int nd = 0; nd < spl[6 + ee].n_nodes(); ++nd) {
 			if (spl[6 + ee].const_node(nd)) continue;
 			const int fx = nv(6 + ee, nd, 0), fy = nv(6 + ee, nd, 1), fz = nv(6 + ee, nd, 2);
+			if (sh.terrain_gradients) {
+				/* the five rows in the contact basis of the foothold = the motion node at the start of the force node's phase
+				 * (ref: force_constraint.cc:67-135, nodes_variables_phase_based.cc:113-141); f . d(basis)/d(foothold) is zero
+				 * because the reference's second derivatives are, so the columns stay the three force components */
+				const int phase = spl[6 + ee].phase[nd == 0 ? 0 : nd - 1];
+				int en = 0;
+				for (int i = 0; i < spl[2 + ee].n_polys(); ++i) if (spl[2 + ee].phase[i] == phase) { en = i; break; }
+				const int ex = nv(2 + ee, en, 0), ey = nv(2 + ee, en, 1);
+				std::vector<int> cols; int slot[3];
+				const int vv[3] = {fx, fy, fz};
+				for (int d = 0; d < 3; ++d) { const int f = vv[d] >= 0 ? free_of[vv[d]] : -1; slot[d] = -1; if (f >= 0) { slot[d] = (int)cols.size(); cols.push_back(f); } }
+				const int e = new_elem(EL_TG, r, 5, cols);
+				const int rec[10] = {r, fx, fy, fz, ex, ey, slot[0], slot[1], slot[2], e};
+				H->tg_frc.insert(H->tg_frc.end(), rec, rec + 10);
+				H->gl[r] = 0.0;      H->gu[r] = sh.force_limit;
+				H->gl[r + 1] = -INF; H->gu[r + 1] = 0.0;
+				H->gl[r + 2] = 0.0;  H->gu[r + 2] = INF;
+				H->gl[r + 3] = -INF; H->gu[r + 3] = 0.0;
+				H->gl[r + 4] = 0.0;  H->gu[r + 4] = INF;
+				r += 5;
+				continue;
+			}
 			std::vector<LinRow> rows(5);
 			for (int q = 0; q < 5; ++q) rows[q].row = r + q;
 			lin_add(rows[0], fz, 1.0);
@@ -748,6 +780,10 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 			}
 			if (H->elems[e].type == EL_DYN) { for (auto &D : H->dyn) if (D.elem == (int)e) for (auto &sl : D.slot) if (sl >= 0) sl = (int8_t)inv[sl]; }
 			if (H->elems[e].type == EL_ROM) { for (auto &R : H->rom) if (R.elem == (int)e) for (auto &sl : R.slot) if (sl >= 0) sl = (int8_t)inv[sl]; }
+			if (H->elems[e].type == EL_TG) {
+				for (size_t k = 0; k + 8 <= H->tg_ter.size(); k += 8) if (H->tg_ter[k + 7] == (int)e) for (int d = 4; d < 7; ++d) if (H->tg_ter[k + d] >= 0) H->tg_ter[k + d] = inv[H->tg_ter[k + d]];
+				for (size_t k = 0; k + 10 <= H->tg_frc.size(); k += 10) if (H->tg_frc[k + 9] == (int)e) for (int d = 6; d < 9; ++d) if (H->tg_frc[k + d] >= 0) H->tg_frc[k + d] = inv[H->tg_frc[k + d]];
+			}
 		}
 	}
 

@@ -44,6 +44,9 @@ struct DevTables {
 	const double *csv_t, *csv_tl; const uint8_t *csv_id;
 	const double *dur; int dur_ld;          /* [10][dur_ld] */
 	const double *cost_c;                   /* [n_all] objective coefficients (f = sum cost_c[v] x_v^2), nullptr without cost terms */
+	const int *tg_ter, *tg_frc;             /* qtos_shape.terrain_gradients: Jacobian tasks of terrain rows [n_ter][8] and force nodes [n_frc][10] */
+	int n_frc, mu_pad_;                     /* n_frc = 0 without the option */
+	double mu;                              /* friction coefficient (force rows in the contact basis) */
 	double nominal[QTOS_NEE][3];
 };
 
@@ -412,10 +415,52 @@ __device__ __forceinline__ void rom_jac(const DevTables &T, const RomSample &R, 
 	}
 }
 
+/* contact basis at a foothold from the terrain's first derivatives (ref: height_map.cc:95-141, GetNormalizedBasis of Normal,
+ * Tangent1, Tangent2); with zero derivatives it is (ez, ex, ey) */
+__device__ __forceinline__ void contact_basis(const DevHeightfield &hf, double x, double y, double n[3], double t1[3], double t2[3])
+{
+	double hx, hy;
+	qtos_height_grad(hf, x, y, hx, hy);
+	const double nn = sqrt(hx * hx + hy * hy + 1.0), n1 = sqrt(1.0 + hx * hx), n2 = sqrt(1.0 + hy * hy);
+	n[0] = -hx / nn; n[1] = -hy / nn; n[2] = 1.0 / nn;
+	t1[0] = 1.0 / n1; t1[1] = 0.0; t1[2] = hx / n1;
+	t2[0] = 0.0; t2[1] = 1.0 / n2; t2[2] = hy / n2;
+}
+
+/* Jacobian values of one terrain row (k < n_ter) or one force node (k - n_ter) with terrain gradients, scaled by sc
+ * (ref: terrain_constraint.cc:90-108, force_constraint.cc:110-171) */
+__device__ __forceinline__ void tg_jac_task(const DevTables &T, const DevHeightfield &hf, const double *x, const double *sc, double *Jv, int k)
+{
+	if (k < T.n_ter) {
+		const int *t = T.tg_ter + 8 * k;
+		const Element &E = T.elems[t[7]];
+		double hx, hy;
+		qtos_height_grad(hf, x[t[1]], x[t[2]], hx, hy);
+		const double s = sc[t[0]];
+		double *v = Jv + E.valoff;
+		if (t[4] >= 0) v[t[4] * E.ld] = s * -hx;
+		if (t[5] >= 0) v[t[5] * E.ld] = s * -hy;
+		if (t[6] >= 0) v[t[6] * E.ld] = s;
+		return;
+	}
+	const int *t = T.tg_frc + 10 * (k - T.n_ter);
+	const Element &E = T.elems[t[9]];
+	double n[3], t1[3], t2[3];
+	contact_basis(hf, x[t[4]], x[t[5]], n, t1, t2);
+	const double *s = sc + t[0];
+	for (int d = 0; d < 3; ++d) {
+		if (t[6 + d] < 0) continue;
+		double *v = Jv + E.valoff + t[6 + d] * E.ld;
+		v[0] = s[0] * n[d];
+		v[1] = s[1] * (t1[d] - T.mu * n[d]); v[2] = s[2] * (t1[d] + T.mu * n[d]);
+		v[3] = s[3] * (t2[d] - T.mu * n[d]); v[4] = s[4] * (t2[d] + T.mu * n[d]);
+	}
+}
+
 /* all constraint values g(x) (unscaled), block-cooperative; no sync inside */
 __device__ __forceinline__ void eval_g_block(const DevTables &T, const DevHeightfield &hf, const double *x, double *g)
 {
-	const int n_tasks = T.n_dyn + T.n_rom4 + T.n_lin + T.n_ter;
+	const int n_tasks = T.n_dyn + T.n_rom4 + T.n_lin + T.n_ter + T.n_frc;
 	for (int t = threadIdx.x; t < n_tasks; t += blockDim.x) {
 		int k = t;
 		if (k < T.n_dyn) {
@@ -443,18 +488,37 @@ __device__ __forceinline__ void eval_g_block(const DevTables &T, const DevHeight
 			continue;
 		}
 		k -= T.n_lin;
-		{
+		if (k < T.n_ter) {
 			const int16_t *v = T.ter_var + 3 * k;
 			g[T.ter_row[k]] = x[v[2]] - qtos_height(hf, x[v[0]], x[v[1]]);
+			continue;
+		}
+		k -= T.n_ter;
+		{
+			/* force rows in the contact basis of the foothold (qtos_shape.terrain_gradients; ref: force_constraint.cc:67-93) */
+			const int *q = T.tg_frc + 10 * k;
+			double n[3], t1[3], t2[3];
+			contact_basis(hf, x[q[4]], x[q[5]], n, t1, t2);
+			double fn = 0, a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+			for (int i = 0; i < 3; ++i) {
+				const double f = x[q[1 + i]];
+				fn += f * n[i];
+				a1 += f * (t1[i] - T.mu * n[i]); a2 += f * (t1[i] + T.mu * n[i]);
+				b1 += f * (t2[i] - T.mu * n[i]); b2 += f * (t2[i] + T.mu * n[i]);
+			}
+			double *o = g + q[0];
+			o[0] = fn; o[1] = a1; o[2] = a2; o[3] = b1; o[4] = b2;
 		}
 	}
 }
 
 /* dynamics + range-of-motion element blocks at x, scaled by sc; block-cooperative */
-__device__ __forceinline__ void eval_jac_block(const DevTables &T, const double *x, const double *sc, double *Jv)
+__device__ __forceinline__ void eval_jac_block(const DevTables &T, const DevHeightfield &hf, const double *x, const double *sc, double *Jv)
 {
-	const int n_tasks = T.n_dyn + T.n_rom4;
+	const int n_tg = T.tg_ter ? T.n_ter + T.n_frc : 0;
+	const int n_tasks = T.n_dyn + T.n_rom4 + n_tg;
 	for (int t = threadIdx.x; t < n_tasks; t += blockDim.x) {
+		if (t >= T.n_dyn + T.n_rom4) { tg_jac_task(T, hf, x, sc, Jv, t - T.n_dyn - T.n_rom4); continue; }
 		if (t < T.n_dyn) {
 			const DynSample &D = T.dyn[t];
 			const Element &E = T.elems[D.elem];

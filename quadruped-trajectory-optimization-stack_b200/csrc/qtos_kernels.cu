@@ -218,6 +218,19 @@ k_jac_rom(DevTables T, DevWork W, int n)
 	rom_jac(T, R, S, WS(sc, T.m) + E.row0, WS(Jv, T.nJ) + E.valoff, E.ncols);
 }
 
+/* qtos_shape.terrain_gradients: the x-dependent Jacobian values of the terrain rows and the force nodes, one thread per task */
+__global__ void __launch_bounds__(128)
+k_jac_tg(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightfield *hfs, int n_hf, int n)
+{
+	const int nt = T.n_ter + T.n_frc;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n * nt) return;
+	const int pid = t / nt, k = t - pid * nt;
+	if (W.status[pid] != QTOS_RUNNING) return;
+	const int hid = probs[pid].hf_id >= 0 && probs[pid].hf_id < n_hf ? probs[pid].hf_id : 0;
+	tg_jac_task(T, hfs[hid], WS(x, T.n_all), WS(sc, T.m), WS(Jv, T.nJ), k);
+}
+
 /* ------------------------------------------------------------------ k_prepare */
 
 /* iterations the reference completes within max_cpu_time (`-r`), see qtos_options */
@@ -1060,7 +1073,7 @@ k_eval_dense(DevTables T, DevWork W, const qtos_problem *probs, const DevHeightf
 	if (!jac_out) return;
 	for (int i = threadIdx.x; i < T.nJ; i += blockDim.x) Jv[i] = T.Jconst[i];
 	__syncthreads();
-	eval_jac_block(T, x, sc, Jv);
+	eval_jac_block(T, hf, x, sc, Jv);
 	__syncthreads();
 	double *J = jac_out + (size_t)pid * T.m * T.n_all;
 	for (int i = threadIdx.x; i < T.m * T.n_all; i += blockDim.x) J[i] = 0.0;

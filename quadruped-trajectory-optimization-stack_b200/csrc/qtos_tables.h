@@ -25,7 +25,7 @@ enum { QP_START_POS = 0, QP_START_ANG = 3, QP_START_VEL = 6, QP_START_ANGVEL = 9
        QP_EE = 15, QP_ZERO = 27 };
 
 enum { ROW_EQ = 1, ROW_HASL = 2, ROW_HASU = 4 };
-enum { EL_DYN = 0, EL_ROM = 1, EL_CONST = 2 };
+enum { EL_DYN = 0, EL_ROM = 1, EL_CONST = 2, EL_TG = 3 };   /* EL_TG: terrain / force rows with terrain gradients (values depend on x) */
 
 struct DynSample {                 /* one dynamics sample time (6 rows) */
 	int    base_id;                /* base polynomial (nodes base_id, base_id+1) */
@@ -108,6 +108,10 @@ struct HostTables {
 	std::vector<double>  lin_val;
 	std::vector<int>     ter_row;                        /* terrain rows: g = x[vz] - h(x[vx], x[vy]) */
 	std::vector<int16_t> ter_var;                        /* [n_ter][3] */
+	/* qtos_shape.terrain_gradients: Jacobian tasks of the terrain rows (row, vx, vy, vz, slot x, slot y, slot z, element) and
+	 * the force nodes (row0, fx, fy, fz, foothold x, foothold y, slot fx, slot fy, slot fz, element); slot = column of the element
+	 * or -1 (fixed variable); empty without the option */
+	std::vector<int>     tg_ter, tg_frc;
 	/* condensed KKT structure */
 	std::vector<int>     fb, blkptr;                     /* [nb], [nb+1] (in blocks) */
 	std::vector<int>     diag_off;                       /* [npad] offset of (i,i) in M */

@@ -698,3 +698,54 @@ def test_cost_terms_option(oracle):
     with pytest.raises(Exception):
         S.solve(p, Q.default_options(algorithm=Q.ALG_FAST))      # the FAST algorithm assumes f == 0
     S.close()
+
+
+def test_terrain_gradients_option(oracle):
+    """qtos_shape.terrain_gradients: the terrain's first derivatives as the bilinear surface gives them -- the code
+    the reference carries commented out (custom_terrain.cpp:96-156) -- in the terrain rows' Jacobian (terrain_constraint.cc:90-108) and
+    in the contact basis of the force rows (height_map.cc:95-141, force_constraint.cc:67-135).  Values and Jacobian equal the oracle's
+    on the bench's plateau terrain; on a smooth hill the solves follow the oracle's Ipopt port like the default path does; on the
+    plateaus the option is the regression the oracle measured (the derivative is zero almost everywhere and huge on the 2 cm ramps), and
+    the GPU reports it the same way."""
+    sh = Q.default_shape("C1", 2.0); sh.terrain_gradients = 1
+    so = oracle.default_shape("C1", 2.0); so.terrain_gradients = 1
+    S = Q.Solver(sh, max_batch=16)
+    assert S.n_vars == 640 and S.n_cons == 892
+    rough, res = HF.rough_terrain(5)
+    gx, gy = np.meshgrid(np.arange(256) * 0.02 - 1.0, np.arange(256) * 0.02 - 1.0, indexing="ij")
+    hill = 0.04 + 0.03 * np.sin(1.7 * gx) * np.cos(1.3 * gy)
+    h_rough, h_hill = S.upload_heightfield(rough, res), S.upload_heightfield(hill, 0.02)
+    rng = np.random.default_rng(2)
+    for grid, hid in ((rough, h_rough), (hill, h_hill)):
+        p = workloads.multistart_problems(4, grid, 0.02, seed=5, hf_id=hid)
+        x0, xl, xu, gl, gu = S.initial(p)
+        for i in range(2):
+            po = oracle_problem(oracle, so, p[i], grid, 0.02)
+            oxl, oxu, ogl, ogu = po.bounds()
+            assert np.array_equal(np.clip(gl[i], -1e20, 1e20), ogl) and np.array_equal(np.clip(gu[i], -1e20, 1e20), ogu)
+            x = x0[i] + 0.03 * rng.standard_normal(S.n_vars); x[oxl == oxu] = oxl[oxl == oxu]
+            g, J = S.eval(p[i:i + 1], x[None])
+            og, oJ = po.g(x), po.jac(x); oJ[:, oxl == oxu] = 0
+            assert np.abs(g[0] - og).max() < G_TOL and np.abs(J[0] - oJ).max() < 1e-9, (np.abs(g[0] - og).max(), np.abs(J[0] - oJ).max())
+            _, ro_ = po.layout()
+            assert np.abs(oJ[ro_[0]:ro_[4]]).sum(axis=1).max() > 1.0 or grid is rough      # the hill's terrain rows do see dh/dx, dh/dy
+    # solves on the smooth hill: status, iteration count and plan follow the oracle
+    p = workloads.multistart_problems(12, hill, 0.02, seed=9, hf_id=h_hill)
+    r, x, rows = S.solve(p, csv=True)
+    close = 0
+    for i in range(12):
+        po = oracle_problem(oracle, so, p[i], hill, 0.02)
+        xo, ro = po.solve_ipopt()
+        assert r["status"][i] == ro.status, (i, r["status"][i], ro.status)
+        if ro.status == 0:
+            assert r["constr_viol"][i] <= 1e-4
+            close += int(r["iters"][i] == ro.iters and np.abs(rows[i][:, 1:19] - po.csv(xo)[:, 1:19]).max() < TRAJ_TOL_M)
+    print("terrain gradients, smooth hill: statuses", r["status"], "iters", r["iters"], "same iterations and within 1 mm:", close, "of 12")
+    assert (r["status"] == 0).sum() >= 10 and close >= 9
+    # plateaus: the regression, reported like the oracle reports it
+    p = workloads.multistart_problems(12, rough, 0.02, seed=5, hf_id=h_rough)
+    r, x, _ = S.solve(p)
+    same = sum(int(r["status"][i] == oracle_problem(oracle, so, p[i], rough, 0.02).solve_ipopt()[1].status) for i in range(12))
+    print("terrain gradients, plateaus: statuses", r["status"], "same status as the oracle:", same, "of 12")
+    assert same >= 8
+    S.close()

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_the_header():
-    assert ctypes.sizeof(Q.Shape) == 8 * (1 + 9 + 12 + 3 + 3 + 1) + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 16   # ints padded to 8; base_rom, dt_base_rom; two cost weights
+    assert ctypes.sizeof(Q.Shape) == 8 * (1 + 9 + 12 + 3 + 3 + 1) + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 16 + 8   # ints padded to 8; base_rom, dt_base_rom; two cost weights; terrain_gradients
     assert Q.PROBLEM_DTYPE.itemsize == 232 and Q.RESULT_DTYPE.itemsize == 56
     s = Q.default_shape()
     assert s.mass == 1.5 and s.combo == 5 and s.duration == 5.0 and s.force_polys_per_stance == 3
