@@ -25,6 +25,22 @@ S.stream_end()
 d_res = torch.from_numpy(r.view(np.uint8).reshape(len(r), -1)).cuda()
 d_group = torch.zeros(len(r), dtype=torch.int32, device="cuda")
 print("winners", parallel.select_best_device(S, d_res, d_group, 0, 1, 2).cpu())
+# this round's additions: trajectory rows delivered by the streaming session, the gradient query, a shape with cost terms and
+# terrain gradients (objective branches of kip_prepare / kip_step / k_init, k_jac_tg, force tasks of eval_g_block), base_rom
+rows_out = np.zeros((6, S.csv_rows, Q.CSV_COLS))
+S.stream_begin(Q.default_options(max_iter=10))
+S.stream_wait(S.stream_submit(p[:6], csv_out=rows_out))
+S.stream_end()
+print("stream csv finite", bool(np.isfinite(rows_out).all()))
+print("gradients", [float(np.abs(v).max()) for v in S.heightfield_gradients(hid, np.random.default_rng(1).uniform(-1.2, 4.5, (300, 2)))])
+sh2 = Q.default_shape(*shape); sh2.cost_force_z = 1.0; sh2.cost_ee_vel_xy = 0.1; sh2.terrain_gradients = 1; sh2.base_rom = 1
+S2 = Q.Solver(sh2, max_batch=4)
+hid2 = S2.upload_heightfield(grid, res)
+p2 = workloads.multistart_problems(6, grid, res, hf_id=hid2)
+r2, x2, _ = S2.solve(p2, Q.default_options(max_iter=10))
+g2, J2 = S2.eval(p2[:2], x2[:2])
+print("options", r2["status"], r2["iters"], bool(np.isfinite(g2).all()))
+S2.close()
 xy = np.random.default_rng(0).uniform(0.2, 1.0, (4 * 52, 2))
 print(S.measure_heightfield_staging(hid, xy, 52))
 S.close()
