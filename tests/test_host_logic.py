@@ -161,3 +161,28 @@ def test_n_flag_compares_the_joined_tokens():
     assert a["normalize"] and a["start"][:2] == [0.0, 0.0] and a["goal"][:2] == [0.5, 0.0]
     b = towr_cli.parse_main_argv(["-n", "t", "-s", "1.0", "2.0", "0.24", "-g", "1.5", "2.0", "0.24"])
     assert not b["normalize"] and b["start"][:2] == [1.0, 2.0]
+
+
+def test_python_structs_follow_the_header_field_by_field():
+    """the ctypes / numpy mirrors of the C ABI's structs name the header's fields in the header's order (sizes alone would not
+    notice two swapped doubles), and so does the stub INTEGRATION.md shows a maintainer"""
+    hdr = open(os.path.join(ROOT, "include", "qtos_b200.h")).read()
+
+    def fields(name):
+        body = re.search(r"typedef struct\s*\{([^{}]*)\}\s*%s;" % name, hdr).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            out.append(re.match(r"(?:const\s+)?\w+\s+\**(\w+)", decl).group(1))
+        return out
+
+    assert fields("qtos_shape") == [f[0] for f in Q.Shape._fields_]
+    assert fields("qtos_options") == [f[0] for f in Q.Options._fields_]
+    assert fields("qtos_problem") == list(Q.PROBLEM_DTYPE.names)
+    assert fields("qtos_result") == list(Q.RESULT_DTYPE.names)
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub = re.search(r"class Shape\(C\.Structure\):.*?_fields_ = \[(.*?)\][^\n]*\nclass Problem", doc, re.S).group(1)
+    assert re.findall(r'\("(\w+)"', stub) == fields("qtos_shape")
