@@ -29,7 +29,7 @@ import numpy as np
 from . import make_problems
 
 ORIGIN_SHIFT = 1.0          # ref: generateHeightField.py:205-206
-PROBE_RUNTIME = 5.0         # `-r 5.0`, accepted and ignored by the GPU solver
+PROBE_RUNTIME = 5.0         # worker_f's `-r 5.0` (ref: generateHeightField.py:373): Ipopt's max_cpu_time, an iteration budget here
 
 
 _SCAN = ((1, 0), (-1, 0), (0, 1), (0, -1), (1, 1), (1, -1), (-1, -1), (-1, 1))     # ref :282-301: the order decides
@@ -193,6 +193,9 @@ class PathMap:
         if n == 0:
             return
         hid = solver.upload_heightfield(np.asarray(towr_grid, dtype=np.float64), resolution)
+        if options is None:                          # what `./main ... -r 5.0` would run with
+            from . import default_options
+            options = default_options(max_cpu_time=PROBE_RUNTIME)
         res, _x, _ = solver.solve(probe_problems(self.probes, hid), options)
         self.results = res
         self.feasible = res["status"] == 0           # `p_status.returncode == 0`
