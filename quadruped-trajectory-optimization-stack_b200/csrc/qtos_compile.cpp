@@ -824,8 +824,43 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 		if (16 * H->rp_ld >= (1 << 13)) return fail("assembly: panel too wide for packed terms");
 		H->as_ptr.assign(1, 0); H->at_ptr.assign(1, 0); H->as_col.clear(); H->at.clear();
 		H->as_max = 0; H->asm_terms_total = 0;
+		long long asm_cost = 0, asm_cost_even = 0;
+		size_t asm_smem = 0;                                /* of the assembly kernel: panel + staged columns of the fullest block row */
+		{
+			std::vector<int> staged(nb, 0);
+			for (size_t e = 0; e < H->elems.size(); ++e) for (int a : ecols[e]) staged[pos[a] / NB]++;
+			const size_t as_max = (size_t)*std::max_element(staged.begin(), staged.end());
+			asm_smem = ((size_t)16 * H->rp_ld + 6 * as_max) * sizeof(double) + ((as_max + 3) & ~(size_t)3) * sizeof(int);
+		}
 		for (int I = 0; I < nb; ++I) {
 			const int s0 = (int)H->as_col.size();
+			/* the CTA of a block row ends with its slowest warp.  With panel rows dealt to the warps by their term counts (longest
+			 * first to the least loaded warp) the slowest warp's stream is 17 % (S2) / 22 % (S5) shorter than with rows
+			 * 4 w .. 4 w + 3, but the streams hold ~6 % more padding (lighter rows, more steps closed early).  Measured on the
+			 * B200: S5, four resident CTAs per SM, 32.5 -> 30.3 ms per 2048-window step; S2, six CTAs per SM (other CTAs fill the
+			 * wait, the kernel is bound by its L1 wavefronts), 20.05 -> 20.27.  So the deal is used where the panel leaves room
+			 * for fewer than six CTAs.  Which warp owns a row changes neither the terms of a target nor their order. */
+			const bool deal_rows = !getenv("QTOS_ASM_ROWS_EVEN") && (getenv("QTOS_ASM_ROWS_DEALT") || 6 * (asm_smem + 1024) > 228 * 1024);
+			int owner[NB];
+			{
+				long long cnt[NB] = {0}, load[4] = {0, 0, 0, 0}, even[4] = {0, 0, 0, 0};
+				for (size_t e = 0; e < H->elems.size(); ++e)
+					for (size_t a = 0; a < ecols[e].size(); ++a) {
+						const int pa = pos[ecols[e][a]];
+						if (pa / NB == I) cnt[pa % NB] += (long long)a + 1;
+					}
+				int order[NB];
+				for (int i = 0; i < NB; ++i) order[i] = i;
+				std::stable_sort(order, order + NB, [&](int x, int y) { return cnt[x] > cnt[y]; });
+				for (int q = 0; q < NB; ++q) {
+					int best = 0;
+					for (int w = 1; w < 4; ++w) if (load[w] < load[best]) best = w;
+					owner[order[q]] = best; load[best] += cnt[order[q]];
+					even[order[q] / 4] += cnt[order[q]];
+				}
+				if (!deal_rows) for (int i = 0; i < NB; ++i) owner[i] = i / 4;
+				asm_cost += *std::max_element(load, load + 4); asm_cost_even += *std::max_element(even, even + 4);
+			}
 			for (int w = 0; w < 4; ++w) {
 				std::set<int> in_step;
 				auto close_step = [&]() { while (H->at.size() % 32) H->at.push_back(0u); in_step.clear(); };
@@ -836,7 +871,7 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 					std::vector<int> own, own_k;
 					for (size_t a = 0; a < c.size(); ++a) {
 						const int pa = pos[c[a]];
-						if (pa / NB != I || (pa % NB) / 4 != w) continue;
+						if (pa / NB != I || owner[pa % NB] != w) continue;
 						const int k = (int)H->as_col.size() - s0;
 						if (k > 511) return fail("assembly: too many staged columns in a block row");
 						AsmCol A; A.voff = E.valoff + (int)a * E.ld; A.row0 = (int16_t)E.row0; A.nrows = (uint8_t)E.nrows; A.i = (uint8_t)(pa % NB);
@@ -866,6 +901,8 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 			H->as_ptr.push_back((int)H->as_col.size());
 			H->as_max = std::max(H->as_max, (int)H->as_col.size() - s0);
 		}
+		if (getenv("QTOS_COMPILE_STATS")) fprintf(stderr, "assembly: %lld terms, slowest-warp terms summed over block rows %lld (rows 4 w .. 4 w + 3: %lld), a quarter of the terms %lld\n",
+		                                          (long long)H->asm_terms_total, asm_cost, asm_cost_even, (long long)H->asm_terms_total / 4);
 		for (int pass = 0; pass < 2; ++pass) {             /* 0: all terms (J' v), 1: elements with equality rows only (Jc' v) */
 			std::vector<int> &ptr = pass ? H->jgc_ptr : H->jg_ptr;
 			std::vector<uint2_t> &tab = pass ? H->jgc : H->jg;

@@ -265,8 +265,11 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt)
 /* ------------------------------------------------------------------ kip_solve */
 
 #define KS_T 128
+/* resident CTAs per SM the kernel is compiled for: kip_solve<5> (95 registers, no spills) where the ring of L blocks that five CTAs leave
+ * room for still holds a block row + 1 (S2: 15 blocks; 42.0 -> 39.5 ms per bench step against four CTAs and a 20-block ring), kip_solve<4>
+ * (121 registers) otherwise -- wide shapes get three CTAs either way and lose 1.3 % with the tighter register budget (S5: 62.6 / 63.5 ms) */
 #ifndef KS_MINB
-#define KS_MINB 4
+#define KS_MINB 5
 #endif
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
@@ -483,7 +486,8 @@ __device__ __forceinline__ void row_dot2(const DevTables &T, const double *Jv, c
 	j0 = a0; j1 = a1;
 }
 
-__global__ void __launch_bounds__(KS_T, KS_MINB)
+template <int MINB>
+__global__ void __launch_bounds__(KS_T, MINB)
 kip_solve(DevTables T, DevWork W, qtos_options opt, int rc)
 {
 	const int pid = blockIdx.x;

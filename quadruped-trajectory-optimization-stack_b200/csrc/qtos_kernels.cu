@@ -520,7 +520,11 @@ __device__ __forceinline__ void diag_done_wait() { asm volatile("bar.sync 3, 160
  * IP_NRHS right-hand sides of W.RB (limited-memory columns, affine and centering directions) are forward-substituted as ONE
  * MORE BLOCK ROW of the factorization: with RB' (16 x n) appended below A, row nb of L is (L^-1 RB)' -- the same two DMMA
  * products per block as every other row, A operand from a shared-memory ring of the row's last max_w blocks. */
-template <int nbuf, int IPM>
+/* LAT = 1 is the same code under a second symbol: launches with at most one active problem per SM use it, and its preferred
+ * shared-memory carve-out leaves the rest of the SM's memory to L1, where the rows of L that come back as B operands then hit
+ * (one window: 1.86 -> 1.66 ms per solve for S2, 4.61 -> 3.99 for S5); a kernel attribute belongs to the function, so a separate
+ * instantiation keeps the full-size launches of other contexts at the maximum carve-out. */
+template <int nbuf, int IPM, int LAT = 0>
 __global__ void __launch_bounds__(FTT, FACTOR_MINB)
 k_factor(DevTables T, DevWork W, qtos_options opt, int rp_ld, int max_w)
 {
