@@ -265,12 +265,11 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt)
 /* ------------------------------------------------------------------ kip_solve */
 
 #define KS_T 128
-/* resident CTAs per SM the kernel is compiled for: kip_solve<5> (95 registers, no spills) where the ring of L blocks that five CTAs leave
- * room for still holds a block row + 1 (S2: 15 blocks; 42.0 -> 39.5 ms per bench step against four CTAs and a 20-block ring), kip_solve<4>
- * (121 registers) otherwise -- wide shapes get three CTAs either way and lose 1.3 % with the tighter register budget (S5: 62.6 / 63.5 ms) */
-#ifndef KS_MINB
-#define KS_MINB 5
-#endif
+/* resident CTAs per SM the kernel is compiled for: the most of 6 / 5 / 4 for which the ring of L blocks the CTAs leave room for still holds
+ * a block row + 1.  S2: kip_solve<6> (80 registers, no spills, 11-block ring) -- 42.0 ms per bench step with four CTAs and a 20-block ring,
+ * 39.5 with five and 15 blocks, 38.0 with six; wide shapes get three CTAs whatever the bound and keep kip_solve<4>'s 121 registers
+ * (S5: 62.6 ms, 63.5 under the five-CTA register budget) */
+#define KS_MINB_MAX 6
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
 {
