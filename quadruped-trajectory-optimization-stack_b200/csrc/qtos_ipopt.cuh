@@ -267,7 +267,7 @@ kip_prepare(DevTables T, DevWork W, qtos_options opt)
 #define KS_T 128
 /* resident CTAs per SM the kernel is compiled for: the most of 6 / 5 / 4 for which the ring of L blocks the CTAs leave room for still holds
  * a block row + 1.  S2: kip_solve<6> (80 registers, no spills, 11-block ring) -- 42.0 ms per bench step with four CTAs and a 20-block ring,
- * 39.5 with five and 15 blocks, 38.0 with six; wide shapes get three CTAs whatever the bound and keep kip_solve<4>'s 121 registers
+ * 39.5 with five and 15 blocks, 38.0 with six; wide shapes (S5: a ring of at least 17 blocks) get four CTAs whatever the bound and keep kip_solve<4>'s 121 registers
  * (S5: 62.6 ms, 63.5 under the five-CTA register budget) */
 #define KS_MINB_MAX 6
 
