@@ -40,6 +40,7 @@ sys.path.insert(0, ROOT)
 PER_GPU = 4096
 GROUP = 8
 IN_FLIGHT = int(os.environ.get("QTOS_IN_FLIGHT", "8"))       # jobs queued in the streaming session
+CSV_DEPTH = int(os.environ.get("QTOS_CSV_DEPTH", "16"))      # half-step jobs queued when every plan's 1 kHz rows are delivered (at most the library's 16 staging areas)
 N_VARIANTS = 8
 COMBO, DURATION = "C1", 2.0
 CPU_SAMPLE = 192
@@ -248,7 +249,7 @@ def run_gpu(args):
         p0 = workloads.replan_sweep_problems(n_total, variants, hids, group_size=GROUP)[idx]
         r0, x0, _ = S.solve(p0, opts)                        # generation 0 (untimed): the plans the timed windows start from
         p = np.ascontiguousarray(workloads.replan_from_rows(p0, S.sample_rows(p0, x0, -1)[:, 0]))
-    streams = [torch.cuda.ExternalStream(S.stream, device=dev)] * IN_FLIGHT
+    streams = [torch.cuda.ExternalStream(S.stream, device=dev)] * max(IN_FLIGHT, CSV_DEPTH)
     p_all_groups = n_total // GROUP                          # group ids are dense over the whole job: 8 candidates per group
 
     # device-resident inputs/outputs for `value`; pinned host buffers for `e2e`
@@ -382,14 +383,23 @@ def run_gpu(args):
     e2e_csv_stream = None
     if world == 1:
         # a job ends with its slowest window (~70 batch iterations after admission), so throughput needs several jobs in flight:
-        # eight half-steps (2048 windows, 1.2 GB of rows each) are queued, like the eight jobs of the headline measurement
-        depth_c, n_sub = 8, n // 2
-        h_rows = [torch.empty((n_sub, S.csv_rows, Q.CSV_COLS), dtype=torch.float64).pin_memory() for _ in range(depth_c)]
+        # half-steps (2048 windows, 1.2 GB of rows each) are queued, as many windows as the headline measurement keeps in flight
+        # (a job's last window ends ~0.8 s after its admission; at 40k solves/s that is ~16 jobs of 2048 windows -- 1.2 GB of page-locked rows each)
+        n_sub = n // 2
+        h_rows = []
+        for _ in range(CSV_DEPTH):
+            try:
+                h_rows.append(torch.empty((n_sub, S.csv_rows, Q.CSV_COLS), dtype=torch.float64).pin_memory())
+            except RuntimeError:                                # the host does not lock that much memory: fewer jobs in flight
+                break
+        depth_c = len(h_rows)
+        h_res_c = [torch.empty(n_sub * Q.RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory() for _ in range(depth_c)]
+        h_x_c = [torch.empty((n_sub, S.n_vars), dtype=torch.float64).pin_memory() for _ in range(depth_c)]
         pp_all = h_p.numpy().view(Q.PROBLEM_DTYPE).reshape(n)
 
         def submit_csv(k):
             half = slice((k % 2) * n_sub, (k % 2 + 1) * n_sub)
-            tickets[k] = S.stream_submit(pp_all[half], (h_res[k].numpy().view(Q.RESULT_DTYPE).reshape(n)[:n_sub], h_x[k].numpy()[:n_sub]),
+            tickets[k] = S.stream_submit(pp_all[half], (h_res_c[k].numpy().view(Q.RESULT_DTYPE).reshape(n_sub), h_x_c[k].numpy()),
                                          csv_out=h_rows[k].numpy())
 
         def collect_csv(k):
@@ -397,7 +407,7 @@ def run_gpu(args):
             return r
 
         timed(depth_c, submit_csv, collect_csv, depth_c)
-        c_steps = max(4, min(args.steps, 10))
+        c_steps = max(4, args.steps)
         c_ms, conv_c = timed(2 * c_steps, submit_csv, collect_csv, depth_c)
         c_ms *= 2.0                                             # two half-steps per 4096-window step
         rows_ok = bool(np.isfinite(h_rows[0].numpy()[::64, ::50]).all()) and float(h_rows[0][0, -1, 0]) > 0.0
