@@ -195,8 +195,8 @@ int  qtos_wait(qtos_ctx *ctx);
  * time and their windows enter the pool as slots fall free, so every launch of the iteration kernels works on a full pool
  * and the last slow windows of one job run beside the fresh windows of the next (the reference's counterpart: 32 worker
  * processes polling one queue, ref: QTOS/generateHeightField.py:344-404).  A window's result is bit-identical to the one
- * qtos_solve_batch returns.  Host-buffer jobs hold at most max_batch windows; all buffers stay valid until the job's
- * qtos_stream_wait returns.  Heightfields are uploaded before qtos_stream_begin. */
+ * qtos_solve_batch returns.  Host-buffer jobs hold at most max_batch windows, and 16 of them are staged on the device at a time
+ * (further ones wait their turn in the queue); all buffers stay valid until the job's qtos_stream_wait returns.  Heightfields are uploaded before qtos_stream_begin. */
 typedef struct {
 	long long iterations;             /* batch iterations launched */
 	long long slot_iterations;        /* occupied slots summed over them (= problem-iterations) */
