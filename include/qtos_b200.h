@@ -252,6 +252,12 @@ int  qtos_measure_heightfield_staging(qtos_ctx *ctx, int hf_id, const double *xy
                                       double *ms_direct, double *ms_staged, double *max_diff, int *fallbacks);
 /* FP64 FMA throughput of the device measured with a register-resident FMA loop, TFLOP/s */
 int  qtos_measure_fp64_peak(qtos_ctx *ctx, double *tflops);
+/* host only, no device needed: the assembly term streams the shape compiler builds for k_asm.  rows_dealt:
+ * 0 = warp w owns panel rows 4 w .. 4 w + 3, 1 = rows dealt to the warps by term count, -1 = what qtos_create would choose.
+ * out[0] terms, out[1] slots (32 x steps, padding included), out[2] slots of the slowest warp summed over the block rows,
+ * out[3] steps that hold a target twice (must be 0: the sums are race-free), out[4] a hash of every target's terms IN ORDER
+ * (equal hashes = the same floating-point sums, whoever owns the row), out[5] 1 if the rows were dealt */
+int  qtos_assembly_table_stats(const qtos_shape *shape, int rows_dealt, unsigned long long out[6]);
 
 #ifdef __cplusplus
 }

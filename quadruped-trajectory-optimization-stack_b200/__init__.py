@@ -115,7 +115,7 @@ EXPORTS = ["qtos_default_shape", "qtos_default_options", "qtos_create", "qtos_de
            "qtos_solve_batch_device_async", "qtos_wait", "qtos_stream_begin", "qtos_stream_submit", "qtos_stream_submit_csv", "qtos_stream_submit_device",
            "qtos_stream_wait", "qtos_stream_stats", "qtos_stream_end", "qtos_make_records", "qtos_select_best", "qtos_get_trace", "qtos_sample_csv", "qtos_sample_csv_rows",
            "qtos_write_csv", "qtos_launch_count", "qtos_set_profiling", "qtos_last_stats", "qtos_stream",
-           "qtos_measure_fp64_peak", "qtos_measure_heightfield_staging"]
+           "qtos_measure_fp64_peak", "qtos_measure_heightfield_staging", "qtos_assembly_table_stats"]
 
 _LIB = None
 
@@ -167,6 +167,7 @@ def lib():
         L.qtos_stream.restype = vp
         L.qtos_measure_fp64_peak.argtypes = [vp, dp]
         L.qtos_measure_heightfield_staging.argtypes = [vp, C.c_int, dp, C.c_int, C.c_int, dp, dp, dp, C.POINTER(C.c_int)]
+        L.qtos_assembly_table_stats.argtypes = [C.POINTER(Shape), C.c_int, C.POINTER(C.c_ulonglong)]
         _LIB = L
     return _LIB
 
@@ -180,6 +181,17 @@ def default_shape(combo="Custom", duration=5.0, mass=None):
     if mass is not None:
         s.mass = float(mass)
     return s
+
+
+def assembly_table_stats(shape, rows_dealt=-1):
+    """The assembly term streams the shape compiler builds for k_asm, inspected on the host (no device needed): terms, slots,
+    slots of the slowest warp summed over the block rows, steps holding a target twice, an order-sensitive hash of every target's
+    terms, whether the panel rows were dealt by term count (rows_dealt: 0 / 1 force a deal, -1 = what Solver would use)."""
+    out = (C.c_ulonglong * 6)()
+    rc = lib().qtos_assembly_table_stats(C.byref(shape), int(rows_dealt), out)
+    if rc:
+        raise RuntimeError("qtos_assembly_table_stats failed with %d" % rc)
+    return dict(zip(("terms", "slots", "slowest_warp_slots", "duplicate_targets", "order_hash", "rows_dealt"), (int(v) for v in out)))
 
 
 def default_options(**kw):

@@ -214,6 +214,8 @@ void lin_add(LinRow &r, int var, double coef)
 
 }  // namespace
 
+int qtos_asm_rows_dealt = -1;
+
 int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int errlen)
 {
 	auto fail = [&](const char *msg) { std::snprintf(err, errlen, "%s", msg); return (int)QTOS_ESHAPE; };
@@ -840,7 +842,8 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 			 * B200: S5, four resident CTAs per SM, 32.5 -> 30.3 ms per 2048-window step; S2, six CTAs per SM (other CTAs fill the
 			 * wait, the kernel is bound by its L1 wavefronts), 20.05 -> 20.27.  So the deal is used where the panel leaves room
 			 * for fewer than six CTAs.  Which warp owns a row changes neither the terms of a target nor their order. */
-			const bool deal_rows = !getenv("QTOS_ASM_ROWS_EVEN") && (getenv("QTOS_ASM_ROWS_DEALT") || 6 * (asm_smem + 1024) > 228 * 1024);
+			const bool deal_rows = qtos_asm_rows_dealt >= 0 ? qtos_asm_rows_dealt != 0
+			                     : !getenv("QTOS_ASM_ROWS_EVEN") && (getenv("QTOS_ASM_ROWS_DEALT") || 6 * (asm_smem + 1024) > 228 * 1024);
 			int owner[NB];
 			{
 				long long cnt[NB] = {0}, load[4] = {0, 0, 0, 0}, even[4] = {0, 0, 0, 0};

@@ -142,5 +142,7 @@ struct HostTables {
 
 /* returns 0 or QTOS_ESHAPE; err receives a message */
 int qtos_compile_shape(const qtos_shape *shape, HostTables *out, char *err, int errlen);
+extern int qtos_asm_rows_dealt;    /* how k_asm's panel rows go to its warps: -1 = by the shape's panel width (default), 0 = rows 4 w .. 4 w + 3,
+                                      1 = dealt by term count (qtos_assembly_table_stats and development only) */
 
 #endif
