@@ -827,23 +827,16 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 		H->as_ptr.assign(1, 0); H->at_ptr.assign(1, 0); H->as_col.clear(); H->at.clear();
 		H->as_max = 0; H->asm_terms_total = 0;
 		long long asm_cost = 0, asm_cost_even = 0;
-		size_t asm_smem = 0;                                /* of the assembly kernel: panel + staged columns of the fullest block row */
-		{
-			std::vector<int> staged(nb, 0);
-			for (size_t e = 0; e < H->elems.size(); ++e) for (int a : ecols[e]) staged[pos[a] / NB]++;
-			const size_t as_max = (size_t)*std::max_element(staged.begin(), staged.end());
-			asm_smem = ((size_t)16 * H->rp_ld + 6 * as_max) * sizeof(double) + ((as_max + 3) & ~(size_t)3) * sizeof(int);
-		}
 		for (int I = 0; I < nb; ++I) {
 			const int s0 = (int)H->as_col.size();
-			/* the CTA of a block row ends with its slowest warp.  With panel rows dealt to the warps by their term counts (longest
-			 * first to the least loaded warp) the slowest warp's stream is 17 % (S2) / 22 % (S5) shorter than with rows
-			 * 4 w .. 4 w + 3, but the streams hold ~6 % more padding (lighter rows, more steps closed early).  Measured on the
-			 * B200: S5, four resident CTAs per SM, 32.5 -> 30.3 ms per 2048-window step; S2, six CTAs per SM (other CTAs fill the
-			 * wait, the kernel is bound by its L1 wavefronts), 20.05 -> 20.27.  So the deal is used where the panel leaves room
-			 * for fewer than six CTAs.  Which warp owns a row changes neither the terms of a target nor their order. */
-			const bool deal_rows = qtos_asm_rows_dealt >= 0 ? qtos_asm_rows_dealt != 0
-			                     : !getenv("QTOS_ASM_ROWS_EVEN") && (getenv("QTOS_ASM_ROWS_DEALT") || 6 * (asm_smem + 1024) > 228 * 1024);
+			/* the CTA of a block row ends with its slowest warp (ncu had 15 % of the kernel's stall samples on that barrier when warp w
+			 * simply took rows 4 w .. 4 w + 3), so the panel rows are DEALT to the warps by their term counts, longest first to the
+			 * least loaded warp, in units of two adjacent rows (adjacent rows are mostly components of one spline node: the same
+			 * elements touch them, an element's terms for the warp stay a (columns b) x (rows a) rectangle and fewer steps are cut
+			 * short).  Slowest warp's stream against rows 4 w .. 4 w + 3, with the step packing below: S2 -24 %, S5 -27 %.
+			 * Measured on the B200 (k_asm per bench step): S2 20.3 -> 19.6 ms, S5 (2048 windows) 32.5 -> 29.1 ms.  Which warp owns
+			 * a row changes neither the terms of a target nor their order (qtos_assembly_table_stats, tests/test_host_logic.py). */
+			const bool deal_rows = qtos_asm_rows_dealt >= 0 ? qtos_asm_rows_dealt != 0 : !getenv("QTOS_ASM_ROWS_EVEN");
 			int owner[NB];
 			{
 				long long cnt[NB] = {0}, load[4] = {0, 0, 0, 0}, even[4] = {0, 0, 0, 0};
@@ -852,20 +845,28 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 						const int pa = pos[ecols[e][a]];
 						if (pa / NB == I) cnt[pa % NB] += (long long)a + 1;
 					}
-				int order[NB];
-				for (int i = 0; i < NB; ++i) order[i] = i;
-				std::stable_sort(order, order + NB, [&](int x, int y) { return cnt[x] > cnt[y]; });
-				for (int q = 0; q < NB; ++q) {
+				const int unit = getenv("QTOS_ASM_DEAL_UNIT") ? atoi(getenv("QTOS_ASM_DEAL_UNIT")) : 2, nu = NB / unit;
+				int order[NB]; long long ucnt[NB] = {0};
+				for (int i = 0; i < NB; ++i) { ucnt[i / unit] += cnt[i]; even[i / 4] += cnt[i]; }
+				for (int u = 0; u < nu; ++u) order[u] = u;
+				std::stable_sort(order, order + nu, [&](int x, int y) { return ucnt[x] > ucnt[y]; });
+				for (int q = 0; q < nu; ++q) {
 					int best = 0;
 					for (int w = 1; w < 4; ++w) if (load[w] < load[best]) best = w;
-					owner[order[q]] = best; load[best] += cnt[order[q]];
-					even[order[q] / 4] += cnt[order[q]];
+					for (int i = order[q] * unit; i < (order[q] + 1) * unit; ++i) owner[i] = best;
+					load[best] += ucnt[order[q]];
 				}
 				if (!deal_rows) for (int i = 0; i < NB; ++i) owner[i] = i / 4;
 				asm_cost += *std::max_element(load, load + 4); asm_cost_even += *std::max_element(even, even + 4);
 			}
+			/* a warp's steps are packed from the next pack_window pending terms: a term whose target the step already holds waits for
+			 * the next step and keeps its place in the queue (so every target still gets its terms in element order) instead of
+			 * cutting the step short -- 19 % of the slots were padding that way, 10 % are with a window of 96 terms (wider windows mix
+			 * more elements into a step and lose again: 160 measured no better) */
+			const int pack_window = getenv("QTOS_ASM_PACK_WINDOW") ? atoi(getenv("QTOS_ASM_PACK_WINDOW")) : 96;
 			for (int w = 0; w < 4; ++w) {
 				std::set<int> in_step;
+				std::vector<std::pair<uint32_t, int>> wt;          /* (descriptor, target) of the warp's terms in canonical order (packed below) */
 				auto close_step = [&]() { while (H->at.size() % 32) H->at.push_back(0u); in_step.clear(); };
 				for (size_t e = 0; e < H->elems.size(); ++e) {
 					const Element &E = H->elems[e];
@@ -891,12 +892,29 @@ int qtos_compile_shape(const qtos_shape *shape, HostTables *H, char *err, int er
 							const int pa = pos[c[a]];
 							const int off = (pa % NB) * H->rp_ld + pos[c[b]] - H->fb[I] * NB;
 							if (a - b > 127) return fail("assembly: element too wide for packed terms");
+							const uint32_t desc = (uint32_t)(E.ld / 2) | ((uint32_t)own_k[j] << 2) | ((uint32_t)(a - b) << 11) | ((uint32_t)off << 18);
+							H->asm_terms_total++;
+							if (pack_window > 0) { wt.push_back({desc, off}); continue; }
 							if (in_step.count(off)) close_step();
 							in_step.insert(off);
-							H->at.push_back((uint32_t)(E.ld / 2) | ((uint32_t)own_k[j] << 2) | ((uint32_t)(a - b) << 11) | ((uint32_t)off << 18));
-							H->asm_terms_total++;
+							H->at.push_back(desc);
 							if (H->at.size() % 32 == 0) in_step.clear();
 						}
+				}
+				if (pack_window > 0) {
+					std::vector<char> taken(wt.size(), 0);
+					size_t head = 0;
+					while (head < wt.size()) {
+						in_step.clear();
+						int n_in = 0;
+						for (size_t q = head; q < wt.size() && q < head + (size_t)pack_window && n_in < 32; ++q) {
+							if (taken[q] || in_step.count(wt[q].second)) { if (!taken[q]) in_step.insert(wt[q].second); continue; }
+							in_step.insert(wt[q].second);
+							taken[q] = 1; H->at.push_back(wt[q].first); ++n_in;
+						}
+						while (head < wt.size() && taken[head]) ++head;
+						while (H->at.size() % 32) H->at.push_back(0u);
+					}
 				}
 				close_step();
 				H->at_ptr.push_back((int)H->at.size());

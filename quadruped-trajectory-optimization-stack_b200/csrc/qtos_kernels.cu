@@ -390,9 +390,9 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
 
 /* Assembly of one block row of the condensed KKT matrix A = sigma I + J' D J, one CTA per (problem, block row):
  * stage A_a = D J[:, a] for every (element, column a) of the block row in shared memory, then every warp walks its
- * flat term stream, one term per lane: panel[i(a)][perm(b)] += A_a . J[:, b].  Warp w owns the panel rows
- * 4 w .. 4 w + 3 and the targets inside one step are distinct, so the sums are race-free and their order is fixed
- * (elements ascending per target).  Terms of an element run in (b, a) order: a step of 32 lanes touches ~8 J columns
+ * flat term stream, one term per lane: panel[i(a)][perm(b)] += A_a . J[:, b].  Every panel row belongs to one warp
+ * (dealt by term count at shape-compile time, qtos_compile.cpp) and the targets inside one step are distinct, so the sums are
+ * race-free and their order is fixed (elements ascending per target).  Terms of an element run in (b, a) order: a step of 32 lanes touches ~8 J columns
  * and the warp's <= 4 staged columns, a third of the L1 wavefronts of the (a, b) order.
  * Block rows are independent, so the grid is problems x block rows and no CTA carries a serial chain; the finished
  * panel (16 x 16 w_I, row-major) goes to the block row's slot of M, where k_factor picks it up. */
