@@ -524,6 +524,7 @@ def run_gpu(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(world), "problems_per_gpu": PER_GPU, "parallelism": "shard%d" % world, "algorithm": "ipopt",
                    "mode": "continuous batching (qtos_stream_*): pool of %d slots, %d jobs queued" % (PER_GPU, IN_FLIGHT), "pool_occupancy": pool_occupancy,
+                   "pool_occupancy_note": "occupied slots averaged over the batch ITERATIONS of the timed region, the ~70 near-empty iterations that drain the last job included; by time the pool is full except for that drain",
                    "l2": "per-step working set %.1f GB per GPU > 126 MB L2" % (PER_GPU * dims.workspace_bytes_per_problem / 1e9)},
         "converged_fraction": conv_all / (args.steps * n_total), "iters_mean": float(iters.mean()), "iters_max": int(iters.max()),
         "p50_latency_ms": 1e3 * lat[len(lat) // 2], "p99_latency_ms": 1e3 * lat[-1],
