@@ -317,7 +317,8 @@ __device__ __forceinline__ void ang_column(const DevTables &T, const DynState &S
 
 /* dense column-major element block of one dynamics sample; sc6 = row scales.  Every column is
  * written exactly once (6 contiguous doubles), driven by the host-compiled column descriptors. */
-__device__ __forceinline__ void dyn_jac(const DevTables &T, const DynSample &D, const DynState &S, const double *sc6, double *blk, int ncols)
+__device__ __forceinline__ void dyn_jac(const DevTables &T, const DynSample &D, const DynState &S, const double *sc6, double *blk, int ncols,
+                                        int first = 0, int stride = 1 /* this thread's share of the columns: first, first + stride, ... */)
 {
 	/* angular rows wrt Euler angle / rate / acceleration */
 	double Gp[9], Gv[9], Ga[9];    /* [r*3+k] */
@@ -351,7 +352,7 @@ __device__ __forceinline__ void dyn_jac(const DevTables &T, const DynSample &D, 
 	}
 	const double s0 = sc6[0], s1 = sc6[1], s2 = sc6[2], s3 = sc6[3], s4 = sc6[4], s5 = sc6[5];
 	const JCol *cols = T.jcols + D.col0;
-	for (int sl = 0; sl < ncols; ++sl) {
+	for (int sl = first; sl < ncols; sl += stride) {
 		const JCol C = ldg_jcol(cols + sl);
 		const int k = C.dim;
 		double a0, a1, a2, l0 = 0.0, l1 = 0.0, l2 = 0.0;

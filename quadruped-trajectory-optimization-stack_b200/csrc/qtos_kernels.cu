@@ -191,18 +191,24 @@ scaling:
 
 /* ------------------------------------------------------------------ k_jac */
 
-/* one thread per (problem, sample): every lane of a warp evaluates the same kind of sample */
+/* every lane of a warp evaluates the same kind of sample.  A dynamics sample is shared by JAC_DYN_SPLIT adjacent lanes: each computes the
+ * sample's state (a few hundred flops, the same in every lane) and writes every JAC_DYN_SPLIT-th of its up to 112 columns -- four times the
+ * threads for a kernel that is bound by the latency of 22 serial samples per problem, and adjacent lanes store adjacent columns */
+#ifndef JAC_DYN_SPLIT
+#define JAC_DYN_SPLIT 4
+#endif
 __global__ void __launch_bounds__(64)
 k_jac_dyn(DevTables T, DevWork W, int n)
 {
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	const int tt = blockIdx.x * blockDim.x + threadIdx.x;
+	const int t = tt / JAC_DYN_SPLIT, q = tt - t * JAC_DYN_SPLIT;
 	if (t >= n * T.n_dyn) return;
 	const int pid = t / T.n_dyn, k = t - pid * T.n_dyn;
 	if (W.status[pid] != QTOS_RUNNING) return;
 	const DynSample &D = T.dyn[k];
 	const Element &E = T.elems[D.elem];
 	DynState S; dyn_state(T, D, WS(x, T.n_all), S);
-	dyn_jac(T, D, S, WS(sc, T.m) + E.row0, WS(Jv, T.nJ) + E.valoff, E.ncols);
+	dyn_jac(T, D, S, WS(sc, T.m) + E.row0, WS(Jv, T.nJ) + E.valoff, E.ncols, q, JAC_DYN_SPLIT);
 }
 
 __global__ void __launch_bounds__(128)
