@@ -393,7 +393,8 @@ __device__ __forceinline__ void rom_rows(const RomState &S, double *g3)
 	mat3T_vec(S.E.R, r, g3);
 }
 
-__device__ __forceinline__ void rom_jac(const DevTables &T, const RomSample &R, const RomState &S, const double *sc3, double *blk, int ncols)
+__device__ __forceinline__ void rom_jac(const DevTables &T, const RomSample &R, const RomState &S, const double *sc3, double *blk, int ncols,
+                                        int first = 0, int stride = 1 /* this thread's share of the columns */)
 {
 	const double rW[3] = {S.p[0] - S.c[0], S.p[1] - S.c[1], S.p[2] - S.c[2]};
 	double Gp[9];
@@ -404,7 +405,7 @@ __device__ __forceinline__ void rom_jac(const DevTables &T, const RomSample &R, 
 	}
 	const JCol *cols = T.jcols + R.col0;
 	const double s0 = sc3[0], s1 = sc3[1], s2 = sc3[2];     /* before the stores below: no reload per column */
-	for (int sl = 0; sl < ncols; ++sl) {          /* column stride 4: 3 rows + zero pad */
+	for (int sl = first; sl < ncols; sl += stride) {          /* column stride 4: 3 rows + zero pad */
 		const JCol C = ldg_jcol(cols + sl);
 		const int k = C.dim;
 		const double w = C.kind == 0 ? -C.w[0] : C.w[0];

@@ -211,17 +211,21 @@ k_jac_dyn(DevTables T, DevWork W, int n)
 	dyn_jac(T, D, S, WS(sc, T.m) + E.row0, WS(Jv, T.nJ) + E.valoff, E.ncols, q, JAC_DYN_SPLIT);
 }
 
+#ifndef JAC_ROM_SPLIT
+#define JAC_ROM_SPLIT 4      /* adjacent lanes per range-of-motion sample, like JAC_DYN_SPLIT (a sample has ~36 columns): jac 6.10 (1) / 5.29 (2) / 5.00 (4) ms per step */
+#endif
 __global__ void __launch_bounds__(128)
 k_jac_rom(DevTables T, DevWork W, int n)
 {
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	const int tt = blockIdx.x * blockDim.x + threadIdx.x;
+	const int t = tt / JAC_ROM_SPLIT, q = tt - t * JAC_ROM_SPLIT;
 	if (t >= n * T.n_rom4) return;
 	const int pid = t / T.n_rom4, k = t - pid * T.n_rom4;
 	if (W.status[pid] != QTOS_RUNNING) return;
 	const RomSample &R = T.rom[k];
 	const Element &E = T.elems[R.elem];
 	RomState S; rom_state(T, R, WS(x, T.n_all), S);
-	rom_jac(T, R, S, WS(sc, T.m) + E.row0, WS(Jv, T.nJ) + E.valoff, E.ncols);
+	rom_jac(T, R, S, WS(sc, T.m) + E.row0, WS(Jv, T.nJ) + E.valoff, E.ncols, q, JAC_ROM_SPLIT);
 }
 
 /* qtos_shape.terrain_gradients: the x-dependent Jacobian values of the terrain rows and the force nodes, one thread per task */
