@@ -1,7 +1,7 @@
 /*
  * qtos_kernels.cu -- sm_100a kernels of the batched interior-point gait-plan solver.
  *
- * One thread block per problem (k_jac: one thread per sample; k_asm: one block per problem and block row).  All launches of a
+ * One thread block per problem (k_jac: four adjacent lanes per sample; k_asm: one block per problem and block row).  All launches of a
  * solve go to the context's stream (k_jac_rom beside k_jac_dyn on a second one).  Kernels shared by both algorithms:
  *   k_init      x0, fixed variables, g(x0), constant J elements; after the first k_jac: row scaling, slack / multiplier
  *               and algorithm-state initialisation (ref: nlp_formulation.cc:100-190; Ipopt initialisation)
@@ -10,6 +10,7 @@
  *   k_factor    left-looking block-skyline Cholesky on 16x16 blocks with FP64 tensor-core MMAs (DMMA m8n8k4);
  *               <., 0>: forward substitution of one right-hand side fused, then the backward substitution -> dx
  *               <., 1>: the 16 right-hand sides of the IPOPT path forward-substituted as one more block row, plus their Gram matrix
+ *               <., ., 1>: the same code with an L1-rich carve-out, for launches with at most one active problem per SM
  *   k_csv       1 kHz trajectory sampler, any row range (ref: main.cpp:92-131)
  *   k_height    batched heightfield queries (ref: custom_terrain.cpp:51-94)
  *   k_results, k_cost, k_admit, k_records, k_select   results, post-hoc plan cost, pool admission, best-plan selection
